@@ -1,0 +1,24 @@
+#!/usr/bin/env bash
+# Builds graphical-gan_b200/lib/libgg_b200.so (sm_100a only) from csrc/*.cu.  nvcc cross-compiles without a GPU.
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+OUT="$HERE/lib"
+OBJ="$HERE/build"
+mkdir -p "$OUT" "$OBJ"
+FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=default --use_fast_math=false)
+FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC)
+[ "${GG_PTXAS_V:-0}" = "1" ] && FLAGS+=(-Xptxas -v)
+pids=()
+objs=()
+for src in "$HERE"/csrc/*.cu; do
+  o="$OBJ/$(basename "${src%.cu}").o"
+  objs+=("$o")
+  if [ ! -f "$o" ] || [ "$src" -nt "$o" ] || [ -n "$(find "$HERE/csrc" "$HERE/../include" -name '*.cuh' -newer "$o" -o -name '*.h' -newer "$o")" ]; then
+    "$NVCC" "${FLAGS[@]}" -c "$src" -o "$o" &
+    pids+=($!)
+  fi
+done
+for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
+"$NVCC" -shared -gencode arch=compute_100a,code=sm_100a "${objs[@]}" -o "$OUT/libgg_b200.so" -cudart static
+echo "built $OUT/libgg_b200.so"

@@ -1,0 +1,97 @@
+// gg_common.cuh — shared helpers for the libgg_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+#include "../../include/gg_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libgg_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace gg {
+
+extern thread_local char g_err[512];
+extern std::atomic<long long> g_launches;
+extern thread_local int g_last_backend;
+extern int g_conv_backend;
+
+inline int fail(int code, const char* fmt, const char* a = "", long long b = 0, long long c = 0) {
+  snprintf(g_err, sizeof(g_err), fmt, a, b, c);
+  return code;
+}
+
+inline int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return GG_ERR_CUDA_BASE + (int)e;
+  }
+  return GG_OK;
+}
+
+#define GG_REQUIRE(cond, msg)                                            \
+  do {                                                                   \
+    if (!(cond)) return gg::fail(GG_ERR_BAD_ARG, "%s: requirement failed: " #cond, msg); \
+  } while (0)
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+constexpr int kNumSMs = 148;  // B200
+
+__device__ __forceinline__ float apply_act(float v, int act, float alpha) {
+  switch (act) {
+    case GG_ACT_RELU: return v > 0.f ? v : 0.f;
+    case GG_ACT_LEAKY: return fmaxf(alpha * v, v);
+    case GG_ACT_TANH: return tanhf(v);
+    case GG_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+    default: return v;
+  }
+}
+
+// derivative of the activation expressed through its OUTPUT y (sign(y)==sign(x) for relu/leaky with alpha>0)
+__device__ __forceinline__ float act_grad_from_out(float y, float g, int act, float alpha) {
+  switch (act) {
+    case GG_ACT_RELU: return y > 0.f ? g : 0.f;
+    case GG_ACT_LEAKY: return y > 0.f ? g : alpha * g;
+    case GG_ACT_TANH: return (1.f - y * y) * g;
+    case GG_ACT_SIGMOID: return y * (1.f - y) * g;
+    default: return g;
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// block-wide sum for blockDim.x <= 1024; result valid in all threads
+__device__ __forceinline__ float block_sum(float v, float* sh /* >= 32 floats */) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  float r = (lane < nw) ? sh[lane] : 0.f;
+  r = warp_sum(r);
+  return r;
+}
+
+}  // namespace gg

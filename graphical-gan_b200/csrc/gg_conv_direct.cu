@@ -1,0 +1,318 @@
+// gg_conv_direct.cu — direct fp32 convolution kernels (any k / stride / padding / channel count), NHWC.
+// They serve (1) the layers that can never be tensor-bound: the first conv (Cin=3, K=75) and the last
+// deconv (Cout=3) of every model (SURVEY.md §7 "Tiny GEMMs"), which are HBM/latency-bound, and (2) as the
+// on-device cross-check of the tcgen05 implicit-GEMM kernels in gg_conv_tc.cu.
+// Reference: tf.nn.conv2d tflib/ops/conv2d.py:106-112; tf.nn.conv2d_transpose tflib/ops/deconv2d.py:101-107.
+#include "gg_common.cuh"
+
+using namespace gg;
+
+namespace gg {
+int conv_tc_fwd(const float* x, const float* w, const float* bias, float* y, int B, int H, int W, int Ci, int Co, int k,
+                int stride, int pad_t, int pad_l, int Ho, int Wo, int act, float alpha, void* ws, size_t ws_bytes,
+                cudaStream_t st, bool* handled);
+int conv_tc_dgrad(const float* dy, const float* w, const float* bias, float* dx, int B, int H, int W, int Ci, int Co, int k,
+                  int stride, int pad_t, int pad_l, int Ho, int Wo, int act, float alpha, void* ws, size_t ws_bytes,
+                  cudaStream_t st, bool* handled);
+int conv_tc_wgrad(const float* x, const float* dy, float* dw, int B, int H, int W, int Ci, int Co, int k, int stride,
+                  int pad_t, int pad_l, int Ho, int Wo, void* ws, size_t ws_bytes, cudaStream_t st, bool* handled);
+size_t conv_tc_wgrad_workspace(int B, int H, int W, int Ci, int Co, int k, int stride, int Ho, int Wo);
+}  // namespace gg
+
+namespace {
+
+struct ConvP {
+  int B, H, W, Ci, Co, k, stride, pad_t, pad_l, Ho, Wo;
+};
+
+// ---- forward: thread = (PIX consecutive wo, CV consecutive co) --------------------------------
+template <int PIX, int CV>
+__global__ void __launch_bounds__(128) conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, float* __restrict__ y, ConvP p, int act,
+                                                       float alpha) {
+  int cog = (p.Co + CV - 1) / CV;           // co groups
+  int wog = (p.Wo + PIX - 1) / PIX;         // wo groups
+  long long total = (long long)p.B * p.Ho * wog * cog;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  int cg = (int)(t % cog); t /= cog;
+  int wg = (int)(t % wog); t /= wog;
+  int ho = (int)(t % p.Ho);
+  int b = (int)(t / p.Ho);
+  int co0 = cg * CV, wo0 = wg * PIX;
+  float acc[PIX][CV];
+#pragma unroll
+  for (int i = 0; i < PIX; ++i)
+#pragma unroll
+    for (int j = 0; j < CV; ++j) acc[i][j] = 0.f;
+  for (int r = 0; r < p.k; ++r) {
+    int hi = ho * p.stride + r - p.pad_t;
+    if (hi < 0 || hi >= p.H) continue;
+    for (int s = 0; s < p.k; ++s) {
+      const float* wp = w + ((long long)(r * p.k + s) * p.Ci) * p.Co + co0;
+      int wi0 = wo0 * p.stride + s - p.pad_l;
+      const float* xrow = x + ((long long)(b * p.H + hi) * p.W) * p.Ci;
+      for (int ci = 0; ci < p.Ci; ++ci) {
+        float wv[CV];
+        if (CV == 4 && co0 + 3 < p.Co) {
+          float4 t4 = *reinterpret_cast<const float4*>(wp + (long long)ci * p.Co);
+          wv[0] = t4.x; wv[1 % CV] = t4.y; wv[2 % CV] = t4.z; wv[3 % CV] = t4.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < CV; ++j) wv[j] = (co0 + j < p.Co) ? wp[(long long)ci * p.Co + j] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < PIX; ++i) {
+          int wi = wi0 + i * p.stride;
+          float xv = (wi >= 0 && wi < p.W && wo0 + i < p.Wo) ? xrow[(long long)wi * p.Ci + ci] : 0.f;
+#pragma unroll
+          for (int j = 0; j < CV; ++j) acc[i][j] = fmaf(xv, wv[j], acc[i][j]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < PIX; ++i) {
+    int wo = wo0 + i;
+    if (wo >= p.Wo) continue;
+    float* yp = y + ((long long)((b * p.Ho + ho) * p.Wo + wo)) * p.Co + co0;
+#pragma unroll
+    for (int j = 0; j < CV; ++j) {
+      if (co0 + j < p.Co) {
+        float v = acc[i][j] + (bias ? bias[co0 + j] : 0.f);
+        yp[j] = apply_act(v, act, alpha);
+      }
+    }
+  }
+}
+
+// ---- dgrad / transposed conv: thread = (input pixel, CV consecutive ci) ------------------------
+template <int CV>
+__global__ void __launch_bounds__(128) conv_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, float* __restrict__ dx, ConvP p,
+                                                         int act, float alpha) {
+  int cig = (p.Ci + CV - 1) / CV;
+  long long total = (long long)p.B * p.H * p.W * cig;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  int cg = (int)(t % cig); t /= cig;
+  int wi = (int)(t % p.W); t /= p.W;
+  int hi = (int)(t % p.H);
+  int b = (int)(t / p.H);
+  int ci0 = cg * CV;
+  float acc[CV];
+#pragma unroll
+  for (int j = 0; j < CV; ++j) acc[j] = 0.f;
+  bool vec = (p.Co % 4) == 0;
+  for (int r = 0; r < p.k; ++r) {
+    int hn = hi + p.pad_t - r;
+    if (hn < 0 || (hn % p.stride) != 0) continue;
+    int ho = hn / p.stride;
+    if (ho >= p.Ho) continue;
+    for (int s = 0; s < p.k; ++s) {
+      int wn = wi + p.pad_l - s;
+      if (wn < 0 || (wn % p.stride) != 0) continue;
+      int wo = wn / p.stride;
+      if (wo >= p.Wo) continue;
+      const float* dyp = dy + ((long long)((b * p.Ho + ho) * p.Wo + wo)) * p.Co;
+      const float* wp = w + ((long long)(r * p.k + s) * p.Ci + ci0) * p.Co;
+      if (vec) {
+        for (int co = 0; co < p.Co; co += 4) {
+          float4 g = *reinterpret_cast<const float4*>(dyp + co);
+#pragma unroll
+          for (int j = 0; j < CV; ++j) {
+            if (ci0 + j < p.Ci) {
+              float4 wv = *reinterpret_cast<const float4*>(wp + (long long)j * p.Co + co);
+              acc[j] = fmaf(g.x, wv.x, acc[j]);
+              acc[j] = fmaf(g.y, wv.y, acc[j]);
+              acc[j] = fmaf(g.z, wv.z, acc[j]);
+              acc[j] = fmaf(g.w, wv.w, acc[j]);
+            }
+          }
+        }
+      } else {
+        for (int co = 0; co < p.Co; ++co) {
+          float g = dyp[co];
+#pragma unroll
+          for (int j = 0; j < CV; ++j)
+            if (ci0 + j < p.Ci) acc[j] = fmaf(g, wp[(long long)j * p.Co + co], acc[j]);
+        }
+      }
+    }
+  }
+  float* xp = dx + ((long long)((b * p.H + hi) * p.W + wi)) * p.Ci + ci0;
+#pragma unroll
+  for (int j = 0; j < CV; ++j) {
+    if (ci0 + j < p.Ci) {
+      float v = acc[j] + (bias ? bias[ci0 + j] : 0.f);
+      xp[j] = apply_act(v, act, alpha);
+    }
+  }
+}
+
+// ---- wgrad: thread = (tap, ci, CV consecutive co), blockIdx.y = pixel slice; partial sums ---------
+template <int CV>
+__global__ void __launch_bounds__(128) conv_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                         float* __restrict__ part, ConvP p, int slices) {
+  int cog = (p.Co + CV - 1) / CV;
+  int total = p.k * p.k * p.Ci * cog;
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  int cg = t % cog; int u = t / cog;
+  int ci = u % p.Ci; u /= p.Ci;
+  int s = u % p.k, r = u / p.k;
+  int co0 = cg * CV;
+  int npix = p.B * p.Ho * p.Wo;
+  int per = (npix + slices - 1) / slices;
+  int p0 = blockIdx.y * per, p1 = min(npix, p0 + per);
+  float acc[CV];
+#pragma unroll
+  for (int j = 0; j < CV; ++j) acc[j] = 0.f;
+  bool vec = (CV == 4) && (p.Co % 4 == 0);
+  for (int pix = p0; pix < p1; ++pix) {
+    int wo = pix % p.Wo; int q = pix / p.Wo;
+    int ho = q % p.Ho; int b = q / p.Ho;
+    int hi = ho * p.stride + r - p.pad_t, wi = wo * p.stride + s - p.pad_l;
+    if (hi < 0 || hi >= p.H || wi < 0 || wi >= p.W) continue;
+    float xv = x[((long long)((b * p.H + hi) * p.W + wi)) * p.Ci + ci];
+    const float* dyp = dy + (long long)pix * p.Co + co0;
+    if (vec) {
+      float4 g = *reinterpret_cast<const float4*>(dyp);
+      acc[0] = fmaf(xv, g.x, acc[0]); acc[1 % CV] = fmaf(xv, g.y, acc[1 % CV]);
+      acc[2 % CV] = fmaf(xv, g.z, acc[2 % CV]); acc[3 % CV] = fmaf(xv, g.w, acc[3 % CV]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < CV; ++j)
+        if (co0 + j < p.Co) acc[j] = fmaf(xv, dyp[j], acc[j]);
+    }
+  }
+  long long wsz = (long long)p.k * p.k * p.Ci * p.Co;
+  float* o = part + (long long)blockIdx.y * wsz + ((long long)(r * p.k + s) * p.Ci + ci) * p.Co + co0;
+#pragma unroll
+  for (int j = 0; j < CV; ++j)
+    if (co0 + j < p.Co) o[j] = acc[j];
+}
+
+__global__ void __launch_bounds__(256) sum_slices_kernel(const float* __restrict__ part, float* __restrict__ out, long long n, int slices) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float a = 0.f;
+  for (int s = 0; s < slices; ++s) a += part[(long long)s * n + i];
+  out[i] = a;
+}
+
+int direct_wgrad_slices(const ConvP& p) {
+  long long threads = (long long)p.k * p.k * p.Ci * ((p.Co + 3) / 4);
+  int blocks = ceil_div(threads, 128);
+  int want = ceil_div(4 * kNumSMs, blocks);
+  int npix = p.B * p.Ho * p.Wo;
+  int maxs = npix / 32;
+  if (maxs < 1) maxs = 1;
+  int S = want < maxs ? want : maxs;
+  if (S > 128) S = 128;
+  if (S < 1) S = 1;
+  return S;
+}
+
+int check_geom(const ConvP& p, const char* who) {
+  if (p.B <= 0 || p.H <= 0 || p.W <= 0 || p.Ci <= 0 || p.Co <= 0 || p.k <= 0 || p.stride <= 0 || p.Ho <= 0 || p.Wo <= 0 ||
+      p.pad_t < 0 || p.pad_l < 0)
+    return fail(GG_ERR_BAD_ARG, "%s: non-positive geometry", who);
+  return GG_OK;
+}
+
+}  // namespace
+
+extern "C" int gg_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, int B, int H, int W, int Ci, int Co,
+                             int k, int stride, int pad_t, int pad_l, int Ho, int Wo, int act, float alpha, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  ConvP p{B, H, W, Ci, Co, k, stride, pad_t, pad_l, Ho, Wo};
+  int rc = check_geom(p, "gg_conv2d_fwd");
+  if (rc) return rc;
+  cudaStream_t st = as_stream(stream);
+  if (g_conv_backend != 1) {
+    bool handled = false;
+    rc = conv_tc_fwd(x, w, bias, y, B, H, W, Ci, Co, k, stride, pad_t, pad_l, Ho, Wo, act, alpha, workspace, workspace_bytes,
+                     st, &handled);
+    if (rc) return rc;
+    if (handled) { g_last_backend = 1; return GG_OK; }
+    if (g_conv_backend == 2) return fail(GG_ERR_UNSUPPORTED, "gg_conv2d_fwd: shape not supported by the tcgen05 path%s");
+  }
+  g_last_backend = 0;
+  if (Co % 4 == 0) {
+    long long total = (long long)B * Ho * ((Wo + 3) / 4) * (Co / 4);
+    conv_fwd_kernel<4, 4><<<ceil_div(total, 128), 128, 0, st>>>(x, w, bias, y, p, act, alpha);
+  } else {
+    long long total = (long long)B * Ho * ((Wo + 3) / 4) * Co;
+    conv_fwd_kernel<4, 1><<<ceil_div(total, 128), 128, 0, st>>>(x, w, bias, y, p, act, alpha);
+  }
+  return check_launch("gg_conv2d_fwd(direct)");
+}
+
+extern "C" int gg_conv2d_dgrad(const float* dy, const float* w, const float* bias, float* dx, int B, int H, int W, int Ci,
+                               int Co, int k, int stride, int pad_t, int pad_l, int Ho, int Wo, int act, float alpha,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  ConvP p{B, H, W, Ci, Co, k, stride, pad_t, pad_l, Ho, Wo};
+  int rc = check_geom(p, "gg_conv2d_dgrad");
+  if (rc) return rc;
+  cudaStream_t st = as_stream(stream);
+  if (g_conv_backend != 1) {
+    bool handled = false;
+    rc = conv_tc_dgrad(dy, w, bias, dx, B, H, W, Ci, Co, k, stride, pad_t, pad_l, Ho, Wo, act, alpha, workspace,
+                       workspace_bytes, st, &handled);
+    if (rc) return rc;
+    if (handled) { g_last_backend = 1; return GG_OK; }
+    if (g_conv_backend == 2) return fail(GG_ERR_UNSUPPORTED, "gg_conv2d_dgrad: shape not supported by the tcgen05 path%s");
+  }
+  g_last_backend = 0;
+  if (Ci % 4 == 0) {
+    long long total = (long long)B * H * W * (Ci / 4);
+    conv_dgrad_kernel<4><<<ceil_div(total, 128), 128, 0, st>>>(dy, w, bias, dx, p, act, alpha);
+  } else {
+    long long total = (long long)B * H * W * Ci;
+    conv_dgrad_kernel<1><<<ceil_div(total, 128), 128, 0, st>>>(dy, w, bias, dx, p, act, alpha);
+  }
+  return check_launch("gg_conv2d_dgrad(direct)");
+}
+
+extern "C" size_t gg_conv2d_wgrad_workspace(int B, int H, int W, int Ci, int Co, int k, int stride, int Ho, int Wo) {
+  ConvP p{B, H, W, Ci, Co, k, stride, 0, 0, Ho, Wo};
+  size_t direct = (size_t)direct_wgrad_slices(p) * k * k * Ci * Co * sizeof(float);
+  size_t tc = conv_tc_wgrad_workspace(B, H, W, Ci, Co, k, stride, Ho, Wo);
+  return direct > tc ? direct : tc;
+}
+
+extern "C" int gg_conv2d_wgrad(const float* x, const float* dy, float* dw, int B, int H, int W, int Ci, int Co, int k,
+                               int stride, int pad_t, int pad_l, int Ho, int Wo, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+  ConvP p{B, H, W, Ci, Co, k, stride, pad_t, pad_l, Ho, Wo};
+  int rc = check_geom(p, "gg_conv2d_wgrad");
+  if (rc) return rc;
+  cudaStream_t st = as_stream(stream);
+  if (g_conv_backend != 1) {
+    bool handled = false;
+    rc = conv_tc_wgrad(x, dy, dw, B, H, W, Ci, Co, k, stride, pad_t, pad_l, Ho, Wo, workspace, workspace_bytes, st, &handled);
+    if (rc) return rc;
+    if (handled) { g_last_backend = 1; return GG_OK; }
+    if (g_conv_backend == 2) return fail(GG_ERR_UNSUPPORTED, "gg_conv2d_wgrad: shape not supported by the tcgen05 path%s");
+  }
+  g_last_backend = 0;
+  int S = direct_wgrad_slices(p);
+  long long wsz = (long long)k * k * Ci * Co;
+  if (workspace == nullptr || workspace_bytes < (size_t)S * wsz * sizeof(float))
+    return fail(GG_ERR_WORKSPACE, "gg_conv2d_wgrad: workspace too small (need %s%lld bytes)", "", (long long)S * wsz * 4);
+  float* part = reinterpret_cast<float*>(workspace);
+  if (Co % 4 == 0) {
+    int threads = k * k * Ci * (Co / 4);
+    dim3 grid(ceil_div(threads, 128), S);
+    conv_wgrad_kernel<4><<<grid, 128, 0, st>>>(x, dy, part, p, S);
+  } else {
+    int threads = k * k * Ci * Co;
+    dim3 grid(ceil_div(threads, 128), S);
+    conv_wgrad_kernel<1><<<grid, 128, 0, st>>>(x, dy, part, p, S);
+  }
+  rc = check_launch("gg_conv2d_wgrad(direct)");
+  if (rc) return rc;
+  sum_slices_kernel<<<ceil_div(wsz, 256), 256, 0, st>>>(part, dw, wsz, S);
+  return check_launch("gg_conv2d_wgrad(direct)/sum");
+}

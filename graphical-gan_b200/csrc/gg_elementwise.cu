@@ -1,0 +1,480 @@
+// gg_elementwise.cu — script-level glue of the hot path:
+// activations, broadcasting arithmetic, reductions, softmax, layout permutes, concat/slice copies,
+// one-hot/argmax and the int->float input decode.  All HBM-bound: coalesced, float4 where the
+// shape allows, grid sized to a multiple of the 148 SMs for the large cases.
+#include "gg_common.cuh"
+
+namespace gg {
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+thread_local int g_last_backend = 0;
+int g_conv_backend = 0;
+}  // namespace gg
+
+using namespace gg;
+
+extern "C" const char* gg_last_error(void) { return g_err; }
+extern "C" int gg_version(void) { return 100; }
+extern "C" long long gg_launch_count(void) { return g_launches.load(); }
+extern "C" void gg_reset_launch_count(void) { g_launches.store(0); }
+extern "C" int gg_set_conv_backend(int mode) {
+  if (mode < 0 || mode > 2) return fail(GG_ERR_BAD_ARG, "gg_set_conv_backend: mode must be 0,1,2%s");
+  g_conv_backend = mode;
+  return GG_OK;
+}
+extern "C" int gg_get_conv_backend(void) { return g_conv_backend; }
+extern "C" int gg_last_backend(void) { return g_last_backend; }
+
+// ------------------------------------------------------------------------------------------
+// unary
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float unary_apply(int op, float x, float a, float b) {
+  switch (op) {
+    case GG_U_COPY: return x;
+    case GG_U_RELU: return x > 0.f ? x : 0.f;
+    case GG_U_LEAKY: return fmaxf(a * x, x);
+    case GG_U_TANH: return tanhf(x);
+    case GG_U_SIGMOID: return 1.f / (1.f + expf(-x));
+    case GG_U_EXP: return expf(x);
+    case GG_U_LOG: return logf(x);
+    case GG_U_SQRT: return sqrtf(x);
+    case GG_U_SQUARE: return x * x;
+    case GG_U_NEG: return -x;
+    case GG_U_ABS: return fabsf(x);
+    case GG_U_AFFINE: return a * x + b;
+    case GG_U_POW: return powf(x, a);
+    case GG_U_RSQRT: return rsqrtf(x);
+    case GG_U_RECIP: return 1.f / x;
+    case GG_U_BCE: return fmaxf(x, 0.f) - x * a + log1pf(expf(-fabsf(x)));
+    case GG_U_CLIP: return fminf(fmaxf(x, a), b);
+    case GG_U_SIGN: return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f);
+    case GG_U_SOFTSIGN: return x / (1.f + fabsf(x));
+    default: return x;
+  }
+}
+
+template <int OP>
+__global__ void __launch_bounds__(256) unary_kernel(const float* __restrict__ x, float* __restrict__ y, long long n,
+                                                    float a, float b) {
+  long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  long long stride = (long long)gridDim.x * blockDim.x * 4;
+  bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  for (; i4 < n; i4 += stride) {
+    if (vec && i4 + 3 < n) {
+      float4 v = *reinterpret_cast<const float4*>(x + i4);
+      v.x = unary_apply(OP, v.x, a, b);
+      v.y = unary_apply(OP, v.y, a, b);
+      v.z = unary_apply(OP, v.z, a, b);
+      v.w = unary_apply(OP, v.w, a, b);
+      *reinterpret_cast<float4*>(y + i4) = v;
+    } else {
+      for (long long j = i4; j < n && j < i4 + 4; ++j) y[j] = unary_apply(OP, x[j], a, b);
+    }
+  }
+}
+
+static int ew_grid(long long n, int per_thread = 4, int threads = 256) {
+  long long blocks = (n + (long long)threads * per_thread - 1) / ((long long)threads * per_thread);
+  long long cap = (long long)kNumSMs * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+#define GG_UNARY_CASE(OPC) \
+  case OPC: unary_kernel<OPC><<<grid, 256, 0, st>>>(x, y, n, a, b); break;
+
+extern "C" int gg_unary(int op, const float* x, float* y, long long n, float a, float b, void* stream) {
+  if (n <= 0) return GG_OK;
+  cudaStream_t st = as_stream(stream);
+  int grid = ew_grid(n);
+  switch (op) {
+    GG_UNARY_CASE(GG_U_COPY) GG_UNARY_CASE(GG_U_RELU) GG_UNARY_CASE(GG_U_LEAKY) GG_UNARY_CASE(GG_U_TANH)
+    GG_UNARY_CASE(GG_U_SIGMOID) GG_UNARY_CASE(GG_U_EXP) GG_UNARY_CASE(GG_U_LOG) GG_UNARY_CASE(GG_U_SQRT)
+    GG_UNARY_CASE(GG_U_SQUARE) GG_UNARY_CASE(GG_U_NEG) GG_UNARY_CASE(GG_U_ABS) GG_UNARY_CASE(GG_U_AFFINE)
+    GG_UNARY_CASE(GG_U_POW) GG_UNARY_CASE(GG_U_RSQRT) GG_UNARY_CASE(GG_U_RECIP) GG_UNARY_CASE(GG_U_BCE)
+    GG_UNARY_CASE(GG_U_CLIP) GG_UNARY_CASE(GG_U_SIGN) GG_UNARY_CASE(GG_U_SOFTSIGN)
+    default: return fail(GG_ERR_BAD_ARG, "gg_unary: unknown op%s");
+  }
+  return check_launch("gg_unary");
+}
+
+// ------------------------------------------------------------------------------------------
+// binary with broadcasting
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float binary_apply(int op, float a, float b, float alpha) {
+  switch (op) {
+    case GG_B_ADD: return a + b;
+    case GG_B_SUB: return a - b;
+    case GG_B_MUL: return a * b;
+    case GG_B_DIV: return a / b;
+    case GG_B_MAX: return fmaxf(a, b);
+    case GG_B_MIN: return fminf(a, b);
+    case GG_B_RELU_GRAD: return a > 0.f ? b : 0.f;
+    case GG_B_LEAKY_GRAD: return a > 0.f ? b : alpha * b;
+    case GG_B_TANH_GRAD: return (1.f - a * a) * b;
+    case GG_B_SIGMOID_GRAD: return a * (1.f - a) * b;
+    case GG_B_BCE_GRAD: return (1.f / (1.f + expf(-a)) - alpha) * b;
+    case GG_B_GE_MASK: return a >= b ? 1.f : 0.f;
+    case GG_B_GT_MASK: return a > b ? 1.f : 0.f;
+    case GG_B_ABS_GRAD: return (a > 0.f ? 1.f : (a < 0.f ? -1.f : 0.f)) * b;
+    case GG_B_POW: return powf(a, b);
+    default: return a;
+  }
+}
+
+// same-shape contiguous fast path
+__global__ void __launch_bounds__(256) binary_flat_kernel(int op, const float* __restrict__ a, const float* __restrict__ b,
+                                                          float* __restrict__ out, long long n, float alpha) {
+  long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  long long stride = (long long)gridDim.x * blockDim.x * 4;
+  bool vec = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  for (; i4 < n; i4 += stride) {
+    if (vec && i4 + 3 < n) {
+      float4 va = *reinterpret_cast<const float4*>(a + i4);
+      float4 vb = *reinterpret_cast<const float4*>(b + i4);
+      float4 r;
+      r.x = binary_apply(op, va.x, vb.x, alpha);
+      r.y = binary_apply(op, va.y, vb.y, alpha);
+      r.z = binary_apply(op, va.z, vb.z, alpha);
+      r.w = binary_apply(op, va.w, vb.w, alpha);
+      *reinterpret_cast<float4*>(out + i4) = r;
+    } else {
+      for (long long j = i4; j < n && j < i4 + 4; ++j) out[j] = binary_apply(op, a[j], b[j], alpha);
+    }
+  }
+}
+
+struct Dims4 { int d[4]; int sa[4]; int sb[4]; };
+
+__global__ void __launch_bounds__(256) binary_bcast_kernel(int op, const float* __restrict__ a, const float* __restrict__ b,
+                                                           float* __restrict__ out, Dims4 p, long long n, float alpha) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    long long r = i;
+    int i3 = (int)(r % p.d[3]); r /= p.d[3];
+    int i2 = (int)(r % p.d[2]); r /= p.d[2];
+    int i1 = (int)(r % p.d[1]); r /= p.d[1];
+    int i0 = (int)r;
+    long long oa = (long long)i0 * p.sa[0] + (long long)i1 * p.sa[1] + (long long)i2 * p.sa[2] + (long long)i3 * p.sa[3];
+    long long ob = (long long)i0 * p.sb[0] + (long long)i1 * p.sb[1] + (long long)i2 * p.sb[2] + (long long)i3 * p.sb[3];
+    out[i] = binary_apply(op, a[oa], b[ob], alpha);
+  }
+}
+
+extern "C" int gg_binary(int op, const float* a, const float* b, float* out, const int* dims4, const int* sa4,
+                         const int* sb4, float alpha, void* stream) {
+  if (op < 0 || op > GG_B_POW) return fail(GG_ERR_BAD_ARG, "gg_binary: unknown op%s");
+  long long n = 1;
+  for (int i = 0; i < 4; ++i) {
+    if (dims4[i] <= 0) return GG_OK;
+    n *= dims4[i];
+  }
+  // contiguous same-shape?
+  bool flat = true;
+  long long expect = 1;
+  for (int i = 3; i >= 0; --i) {
+    if (dims4[i] != 1 && (sa4[i] != expect || sb4[i] != expect)) flat = false;
+    expect *= dims4[i];
+  }
+  cudaStream_t st = as_stream(stream);
+  if (flat) {
+    binary_flat_kernel<<<ew_grid(n), 256, 0, st>>>(op, a, b, out, n, alpha);
+  } else {
+    Dims4 p;
+    for (int i = 0; i < 4; ++i) { p.d[i] = dims4[i]; p.sa[i] = sa4[i]; p.sb[i] = sb4[i]; }
+    binary_bcast_kernel<<<ew_grid(n, 1), 256, 0, st>>>(op, a, b, out, p, n, alpha);
+  }
+  return check_launch("gg_binary");
+}
+
+// ------------------------------------------------------------------------------------------
+// reduce over the middle axis of [outer, red, inner]
+// ------------------------------------------------------------------------------------------
+// inner == 1: one warp (or block) per output row, lanes stride over `red`.
+__global__ void __launch_bounds__(256) reduce_rows_kernel(int op, const float* __restrict__ x, float* __restrict__ y,
+                                                          int outer, int red) {
+  __shared__ float sh[32];
+  int o = blockIdx.x;
+  if (o >= outer) return;
+  const float* row = x + (long long)o * red;
+  float acc = (op == 2) ? -INFINITY : 0.f;
+  for (int r = threadIdx.x; r < red; r += blockDim.x) {
+    float v = row[r];
+    acc = (op == 2) ? fmaxf(acc, v) : acc + v;
+  }
+  // block reduce
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  acc = (op == 2) ? warp_max(acc) : warp_sum(acc);
+  if (lane == 0) sh[w] = acc;
+  __syncthreads();
+  if (w == 0) {
+    float r = (lane < nw) ? sh[lane] : ((op == 2) ? -INFINITY : 0.f);
+    r = (op == 2) ? warp_max(r) : warp_sum(r);
+    if (lane == 0) y[o] = (op == 1) ? r / (float)red : r;
+  }
+}
+
+// inner > 1: thread per (outer, inner) column, coalesced over inner; rows split over threadIdx.y then smem-combined
+__global__ void __launch_bounds__(256) reduce_cols_kernel(int op, const float* __restrict__ x, float* __restrict__ y,
+                                                          int outer, int red, int inner) {
+  __shared__ float sh[8][33];
+  int i = blockIdx.x * 32 + threadIdx.x;
+  int o = blockIdx.y;
+  float acc = (op == 2) ? -INFINITY : 0.f;
+  if (i < inner) {
+    const float* base = x + (long long)o * red * inner + i;
+    for (int r = threadIdx.y; r < red; r += 8) {
+      float v = base[(long long)r * inner];
+      acc = (op == 2) ? fmaxf(acc, v) : acc + v;
+    }
+  }
+  sh[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && i < inner) {
+    float r = sh[0][threadIdx.x];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) r = (op == 2) ? fmaxf(r, sh[k][threadIdx.x]) : r + sh[k][threadIdx.x];
+    y[(long long)o * inner + i] = (op == 1) ? r / (float)red : r;
+  }
+}
+
+extern "C" int gg_reduce(int op, const float* x, float* y, int outer, int red, int inner, void* stream) {
+  if (op < 0 || op > 2) return fail(GG_ERR_BAD_ARG, "gg_reduce: unknown op%s");
+  if (outer <= 0 || inner <= 0 || red <= 0) return GG_OK;
+  cudaStream_t st = as_stream(stream);
+  if (inner == 1) {
+    int threads = red >= 1024 ? 256 : (red >= 128 ? 128 : 32);
+    reduce_rows_kernel<<<outer, threads, 0, st>>>(op, x, y, outer, red);
+  } else {
+    dim3 grid(ceil_div(inner, 32), outer), block(32, 8);
+    reduce_cols_kernel<<<grid, block, 0, st>>>(op, x, y, outer, red, inner);
+  }
+  return check_launch("gg_reduce");
+}
+
+// ------------------------------------------------------------------------------------------
+// softmax over the last axis (HyperExtractor, gmgan_inference_cifar10.py:162-163): one warp per row
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) softmax_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int R, int C) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= R) return;
+  const float* xr = x + (long long)row * C;
+  float m = -INFINITY;
+  for (int c = lane; c < C; c += 32) m = fmaxf(m, xr[c]);
+  m = warp_max(m);
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += expf(xr[c] - m);
+  s = warp_sum(s);
+  float inv = 1.f / s;
+  for (int c = lane; c < C; c += 32) y[(long long)row * C + c] = expf(xr[c] - m) * inv;
+}
+
+__global__ void __launch_bounds__(128) softmax_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy,
+                                                          float* __restrict__ dx, int R, int C) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= R) return;
+  const float* yr = y + (long long)row * C;
+  const float* gr = dy + (long long)row * C;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += yr[c] * gr[c];
+  s = warp_sum(s);
+  for (int c = lane; c < C; c += 32) dx[(long long)row * C + c] = yr[c] * (gr[c] - s);
+}
+
+extern "C" int gg_softmax_fwd(const float* x, float* y, int R, int C, void* stream) {
+  if (R <= 0 || C <= 0) return GG_OK;
+  softmax_fwd_kernel<<<ceil_div(R, 4), 128, 0, as_stream(stream)>>>(x, y, R, C);
+  return check_launch("gg_softmax_fwd");
+}
+extern "C" int gg_softmax_bwd(const float* y, const float* dy, float* dx, int R, int C, void* stream) {
+  if (R <= 0 || C <= 0) return GG_OK;
+  softmax_bwd_kernel<<<ceil_div(R, 4), 128, 0, as_stream(stream)>>>(y, dy, dx, R, C);
+  return check_launch("gg_softmax_bwd");
+}
+
+// ------------------------------------------------------------------------------------------
+// transposes
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) transpose_b2d_kernel(const float* __restrict__ x, float* __restrict__ y, int R, int C) {
+  __shared__ float tile[32][33];
+  int b = blockIdx.z;
+  const float* xb = x + (long long)b * R * C;
+  float* yb = y + (long long)b * R * C;
+  int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    int r = r0 + j, c = c0 + threadIdx.x;
+    if (r < R && c < C) tile[j][threadIdx.x] = xb[(long long)r * C + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    int c = c0 + j, r = r0 + threadIdx.x;
+    if (r < R && c < C) yb[(long long)c * R + r] = tile[threadIdx.x][j];
+  }
+}
+
+extern "C" int gg_transpose_b2d(const float* x, float* y, int Bt, int R, int C, void* stream) {
+  if (Bt <= 0 || R <= 0 || C <= 0) return GG_OK;
+  GG_REQUIRE(Bt <= 65535, "gg_transpose_b2d");
+  dim3 grid(ceil_div(C, 32), ceil_div(R, 32), Bt), block(32, 8);
+  transpose_b2d_kernel<<<grid, block, 0, as_stream(stream)>>>(x, y, R, C);
+  return check_launch("gg_transpose_b2d");
+}
+
+struct Perm4 { int od[4]; long long is[4]; };
+__global__ void __launch_bounds__(256) transpose4_kernel(const float* __restrict__ x, float* __restrict__ y, Perm4 p, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    long long r = i;
+    int i3 = (int)(r % p.od[3]); r /= p.od[3];
+    int i2 = (int)(r % p.od[2]); r /= p.od[2];
+    int i1 = (int)(r % p.od[1]); r /= p.od[1];
+    int i0 = (int)r;
+    y[i] = x[i0 * p.is[0] + i1 * p.is[1] + i2 * p.is[2] + i3 * p.is[3]];
+  }
+}
+
+extern "C" int gg_transpose4(const float* x, float* y, const int* dims4, const int* perm4, void* stream) {
+  long long istr[4];
+  long long n = 1;
+  for (int i = 3; i >= 0; --i) { istr[i] = n; n *= dims4[i]; }
+  if (n <= 0) return GG_OK;
+  Perm4 p;
+  bool seen[4] = {false, false, false, false};
+  for (int i = 0; i < 4; ++i) {
+    int s = perm4[i];
+    if (s < 0 || s > 3 || seen[s]) return fail(GG_ERR_BAD_ARG, "gg_transpose4: bad permutation%s");
+    seen[s] = true;
+    p.od[i] = dims4[s];
+    p.is[i] = istr[s];
+  }
+  transpose4_kernel<<<ew_grid(n, 1), 256, 0, as_stream(stream)>>>(x, y, p, n);
+  return check_launch("gg_transpose4");
+}
+
+// ------------------------------------------------------------------------------------------
+// strided copy, fill, one-hot, argmax, casts, add_n
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) copy2d_kernel(const float* __restrict__ src, long long src_ld, float* __restrict__ dst,
+                                                     long long dst_ld, long long rows, long long cols, int accumulate) {
+  long long n = rows * cols;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    long long r = i / cols, c = i - r * cols;
+    float v = src[r * src_ld + c];
+    float* d = dst + r * dst_ld + c;
+    *d = accumulate ? (*d + v) : v;
+  }
+}
+extern "C" int gg_copy2d(const float* src, long long src_ld, float* dst, long long dst_ld, long long rows,
+                         long long cols, int accumulate, void* stream) {
+  if (rows <= 0 || cols <= 0) return GG_OK;
+  copy2d_kernel<<<ew_grid(rows * cols, 1), 256, 0, as_stream(stream)>>>(src, src_ld, dst, dst_ld, rows, cols, accumulate);
+  return check_launch("gg_copy2d");
+}
+
+__global__ void __launch_bounds__(256) fill_kernel(float* x, long long n, float v) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) x[i] = v;
+}
+extern "C" int gg_fill(float* x, long long n, float v, void* stream) {
+  if (n <= 0) return GG_OK;
+  fill_kernel<<<ew_grid(n, 1), 256, 0, as_stream(stream)>>>(x, n, v);
+  return check_launch("gg_fill");
+}
+
+__global__ void __launch_bounds__(256) one_hot_kernel(const int32_t* __restrict__ idx, float* __restrict__ out, int n, int depth) {
+  long long total = (long long)n * depth;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    int r = (int)(i / depth), c = (int)(i - (long long)r * depth);
+    out[i] = (idx[r] == c) ? 1.f : 0.f;
+  }
+}
+extern "C" int gg_one_hot(const int32_t* idx, float* out, int n, int depth, void* stream) {
+  if (n <= 0 || depth <= 0) return GG_OK;
+  one_hot_kernel<<<ew_grid((long long)n * depth, 1), 256, 0, as_stream(stream)>>>(idx, out, n, depth);
+  return check_launch("gg_one_hot");
+}
+
+// first maximal index, like tf.argmax
+__global__ void __launch_bounds__(128) argmax_kernel(const float* __restrict__ x, int32_t* __restrict__ idx, int R, int C) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= R) return;
+  const float* xr = x + (long long)row * C;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int c = lane; c < C; c += 32) {
+    float v = xr[c];
+    if (v > best) { best = v; bi = c; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+  }
+  if (lane == 0) idx[row] = (bi == 0x7fffffff) ? 0 : bi;
+}
+extern "C" int gg_argmax(const float* x, int32_t* idx, int R, int C, void* stream) {
+  if (R <= 0 || C <= 0) return GG_OK;
+  argmax_kernel<<<ceil_div(R, 4), 128, 0, as_stream(stream)>>>(x, idx, R, C);
+  return check_launch("gg_argmax");
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) cast_to_f32_kernel(const T* __restrict__ x, float* __restrict__ y, long long n, float a, float b) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  // TF evaluates 2*((float(x)/255.)-.5): the host passes (a, b) and we keep the same operation order
+  // as the graph that produced them by applying a single fused multiply-add only when exact parity is not
+  // required; exact parity is handled on the host by emitting the op chain unfused.
+  for (; i < n; i += stride) y[i] = a * (float)x[i] + b;
+}
+extern "C" int gg_cast_i32_f32(const int32_t* x, float* y, long long n, float a, float b, void* stream) {
+  if (n <= 0) return GG_OK;
+  cast_to_f32_kernel<int32_t><<<ew_grid(n, 1), 256, 0, as_stream(stream)>>>(x, y, n, a, b);
+  return check_launch("gg_cast_i32_f32");
+}
+extern "C" int gg_cast_u8_f32(const uint8_t* x, float* y, long long n, float a, float b, void* stream) {
+  if (n <= 0) return GG_OK;
+  cast_to_f32_kernel<uint8_t><<<ew_grid(n, 1), 256, 0, as_stream(stream)>>>(x, y, n, a, b);
+  return check_launch("gg_cast_u8_f32");
+}
+__global__ void __launch_bounds__(256) cast_f32_i32_kernel(const float* __restrict__ x, int32_t* __restrict__ y, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) y[i] = (int32_t)x[i];  // truncation toward zero, like tf.cast / numpy astype
+}
+extern "C" int gg_cast_f32_i32(const float* x, int32_t* y, long long n, void* stream) {
+  if (n <= 0) return GG_OK;
+  cast_f32_i32_kernel<<<ew_grid(n, 1), 256, 0, as_stream(stream)>>>(x, y, n);
+  return check_launch("gg_cast_f32_i32");
+}
+
+struct PtrList { const float* p[16]; };
+__global__ void __launch_bounds__(256) add_n_kernel(PtrList pl, int count, float* __restrict__ out, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    float acc = pl.p[0][i];
+    for (int k = 1; k < count; ++k) acc += pl.p[k][i];
+    out[i] = acc;
+  }
+}
+extern "C" int gg_add_n(const float* const* ptrs, int count, float* out, long long n, void* stream) {
+  if (n <= 0) return GG_OK;
+  if (count < 1 || count > 16) return fail(GG_ERR_BAD_ARG, "gg_add_n: count must be in [1,16]%s");
+  PtrList pl;
+  for (int i = 0; i < count; ++i) pl.p[i] = ptrs[i];
+  add_n_kernel<<<ew_grid(n, 1), 256, 0, as_stream(stream)>>>(pl, count, out, n);
+  return check_launch("gg_add_n");
+}

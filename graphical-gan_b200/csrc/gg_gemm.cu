@@ -1,0 +1,144 @@
+// gg_gemm.cu — dense layers (tf.matmul + bias, tflib/ops/linear.py:132-146, and the two transposed products
+// autodiff adds).  The Linear layers of the hot path have M = batch = 64: they are weight-bandwidth / latency
+// bound, so this is an fp32 FFMA kernel with split-K sized to fill the 148 SMs and a
+// fused bias+activation epilogue, not a tensor-core kernel.
+#include "gg_common.cuh"
+
+using namespace gg;
+
+namespace {
+
+constexpr int TM = 64, TN = 64, TK = 16;
+
+template <int TA, int TB>
+__global__ void __launch_bounds__(256) gemm_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                   const float* __restrict__ bias, float* __restrict__ C, int M, int N, int K,
+                                                   int k_per_split, int splits, int act, float alpha) {
+  __shared__ float As[TK][TM + 4];
+  __shared__ float Bs[TK][TN + 4];
+  int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  int split = blockIdx.z;
+  int kb = split * k_per_split, ke = min(K, kb + k_per_split);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = kb; k0 < ke; k0 += TK) {
+    // load A tile: As[kk][mm] = opA[m0+mm, k0+kk]
+#pragma unroll
+    for (int it = 0; it < (TM * TK) / 256; ++it) {
+      int e = threadIdx.x + it * 256;
+      int mm, kk;
+      if (TA) { mm = e % TM; kk = e / TM; }  // stored [K,M]: m fastest
+      else { kk = e % TK; mm = e / TK; }     // stored [M,K]: k fastest
+      int m = m0 + mm, k = k0 + kk;
+      float v = 0.f;
+      if (m < M && k < ke) v = TA ? A[(long long)k * M + m] : A[(long long)m * K + k];
+      As[kk][mm] = v;
+    }
+#pragma unroll
+    for (int it = 0; it < (TN * TK) / 256; ++it) {
+      int e = threadIdx.x + it * 256;
+      int nn, kk;
+      if (TB) { kk = e % TK; nn = e / TK; }  // stored [N,K]: k fastest
+      else { nn = e % TN; kk = e / TN; }     // stored [K,N]: n fastest
+      int n = n0 + nn, k = k0 + kk;
+      float v = 0.f;
+      if (n < N && k < ke) v = TB ? B[(long long)n * K + k] : B[(long long)k * N + n];
+      Bs[kk][nn] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < TK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* out = C;
+  if (splits > 1) out = C + (long long)split * M * N;  // C is the workspace here
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j];
+      if (splits == 1) {
+        if (bias) v += bias[n];
+        v = apply_act(v, act, alpha);
+      }
+      out[(long long)m * N + n] = v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) gemm_splitk_finish(const float* __restrict__ ws, const float* __restrict__ bias,
+                                                          float* __restrict__ C, long long MN, int N, int splits, int act,
+                                                          float alpha) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= MN) return;
+  float v = 0.f;
+  for (int s = 0; s < splits; ++s) v += ws[(long long)s * MN + i];
+  if (bias) v += bias[i % N];
+  C[i] = apply_act(v, act, alpha);
+}
+
+int choose_splits(int M, int N, int K) {
+  int tiles = ceil_div(M, TM) * ceil_div(N, TN);
+  int splits = ceil_div(2 * kNumSMs, tiles);
+  int maxs = K / 64;
+  if (maxs < 1) maxs = 1;
+  if (splits > maxs) splits = maxs;
+  if (splits > 32) splits = 32;
+  if (splits < 1) splits = 1;
+  return splits;
+}
+
+}  // namespace
+
+extern "C" size_t gg_gemm_workspace(int M, int N, int K) {
+  int s = choose_splits(M, N, K);
+  return s > 1 ? (size_t)s * M * N * sizeof(float) : 0;
+}
+
+extern "C" int gg_gemm(const float* A, const float* Bm, const float* bias, float* C, int M, int N, int K, int ta, int tb,
+                       int act, float alpha, void* workspace, size_t workspace_bytes, void* stream) {
+  if (M <= 0 || N <= 0) return GG_OK;
+  GG_REQUIRE(K > 0, "gg_gemm");
+  cudaStream_t st = as_stream(stream);
+  int splits = choose_splits(M, N, K);
+  if (splits > 1 && (workspace == nullptr || workspace_bytes < (size_t)splits * M * N * sizeof(float))) splits = 1;
+  int k_per = ceil_div(ceil_div(K, splits), TK) * TK;
+  splits = ceil_div(K, k_per);
+  dim3 grid(ceil_div(N, TN), ceil_div(M, TM), splits);
+  float* out = splits > 1 ? reinterpret_cast<float*>(workspace) : C;
+  g_last_backend = 0;
+#define GG_LAUNCH_GEMM(TA, TB) \
+  gemm_kernel<TA, TB><<<grid, 256, 0, st>>>(A, Bm, bias, out, M, N, K, k_per, splits, act, alpha)
+  if (!ta && !tb) GG_LAUNCH_GEMM(0, 0);
+  else if (ta && !tb) GG_LAUNCH_GEMM(1, 0);
+  else if (!ta && tb) GG_LAUNCH_GEMM(0, 1);
+  else GG_LAUNCH_GEMM(1, 1);
+#undef GG_LAUNCH_GEMM
+  int rc = check_launch("gg_gemm");
+  if (rc) return rc;
+  if (splits > 1) {
+    long long MN = (long long)M * N;
+    gemm_splitk_finish<<<ceil_div(MN, 256), 256, 0, st>>>(out, bias, C, MN, N, splits, act, alpha);
+    rc = check_launch("gg_gemm/finish");
+  }
+  return rc;
+}
