@@ -36,7 +36,7 @@ extern "C" int gg_probe_tma_strided(const float* x, int B, int H, int W, int C, 
   uint64_t strides[4] = {1, (uint64_t)C, (uint64_t)W * C, (uint64_t)H * W * C};
   uint32_t box[4] = {32, (uint32_t)(2 * wb), (uint32_t)(2 * hb), 1};
   uint32_t es[4] = {1, 2, 2, 1};
-  int rc = encode_tmap(&tmap, x, 4, dims, strides, box, es, swizzle128 != 0);
+  int rc = encode_tmap(&tmap, x, 4, dims, strides, box, es, swizzle128);
   if (rc) return rc;
   int nfloats = hb * wb * 32;
   size_t smem = (size_t)nfloats * 4 + 1024;
@@ -83,8 +83,12 @@ __global__ void __launch_bounds__(128) probe_umma_kernel(const __grid_constant__
       tc_fence_after();
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        uint64_t ad = a_mn ? make_smem_desc(smem_u32(sA) + j * 1024, 4096, 1024) : make_smem_desc(smem_u32(sA) + j * 32, 16, 1024);
-        uint64_t bd = b_mn ? make_smem_desc(smem_u32(sB) + j * 1024, 4096, 1024) : make_smem_desc(smem_u32(sB) + j * 32, 16, 1024);
+        // K-major: 8-row x 128B swizzle atoms, k-step = 32 bytes inside the row.  MN-major (tf32): 4-row x 128B
+        // atoms (32-byte swizzle chunks), one MMA (K=8) spans two atoms: SBO = 512, k-step = 1024 bytes.
+        uint64_t ad = a_mn ? make_smem_desc(smem_u32(sA) + j * 1024, 4096, 512, kLayoutSW128_32B)
+                           : make_smem_desc(smem_u32(sA) + j * 32, 16, 1024);
+        uint64_t bd = b_mn ? make_smem_desc(smem_u32(sB) + j * 1024, 4096, 512, kLayoutSW128_32B)
+                           : make_smem_desc(smem_u32(sB) + j * 32, 16, 1024);
         umma_tf32(tmem_d, ad, bd, idesc, (kb | j) != 0);
       }
       umma_commit(&mma_bar);
@@ -115,21 +119,21 @@ extern "C" int gg_probe_umma_tf32(const float* A, const float* Bm, float* D, int
   if (!a_mn_major) {
     uint64_t dims[2] = {(uint64_t)K, 128}, str[2] = {1, (uint64_t)K};
     uint32_t box[2] = {32, 128};
-    rc = encode_tmap(&tmA, A, 2, dims, str, box, nullptr, true, cv);
+    rc = encode_tmap(&tmA, A, 2, dims, str, box, nullptr, 1, cv);
   } else {
     uint64_t dims[2] = {128, (uint64_t)K}, str[2] = {1, 128};
     uint32_t box[2] = {32, 32};
-    rc = encode_tmap(&tmA, A, 2, dims, str, box, nullptr, true, cv);
+    rc = encode_tmap(&tmA, A, 2, dims, str, box, nullptr, 2, cv);
   }
   if (rc) return rc;
   if (!b_mn_major) {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}, str[2] = {1, (uint64_t)K};
     uint32_t box[2] = {32, (uint32_t)N};
-    rc = encode_tmap(&tmB, Bm, 2, dims, str, box, nullptr, true, cv);
+    rc = encode_tmap(&tmB, Bm, 2, dims, str, box, nullptr, 1, cv);
   } else {
     uint64_t dims[2] = {(uint64_t)N, (uint64_t)K}, str[2] = {1, (uint64_t)N};
     uint32_t box[2] = {32, 32};
-    rc = encode_tmap(&tmB, Bm, 2, dims, str, box, nullptr, true, cv);
+    rc = encode_tmap(&tmB, Bm, 2, dims, str, box, nullptr, 2, cv);
   }
   if (rc) return rc;
   size_t smem = (size_t)(128 + N) * 32 * 4 + 1024;

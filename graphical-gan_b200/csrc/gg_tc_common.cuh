@@ -114,15 +114,19 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
 // ------------------------------------------------------------------------------------------------
 // descriptors (bit layouts: cute/arch/mma_sm100_desc.hpp SmemDescriptor / InstrDescriptor)
 // ------------------------------------------------------------------------------------------------
-constexpr uint32_t kSwizzle128B = 2;  // UMMA::LayoutType::SWIZZLE_128B
-// smem operand descriptor: start address, leading/stride byte offsets (all >>4), version 1 (Blackwell), 128B swizzle
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+constexpr uint32_t kLayoutSW128 = 2;      // UMMA::LayoutType::SWIZZLE_128B          (16-byte chunks; K-major operands)
+constexpr uint32_t kLayoutSW128_32B = 1;  // UMMA::LayoutType::SWIZZLE_128B_BASE32B  (32-byte chunks; the only layout the
+                                          // hardware accepts for MN-major tf32 operands — measured: with SWIZZLE_128B and a
+                                          // transpose bit set the MMA silently writes zeros)
+// smem operand descriptor: start address, leading/stride byte offsets (all >>4), version 1 (Blackwell), swizzle layout
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout = kLayoutSW128) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)kSwizzle128B << 61;
+  d |= (uint64_t)layout << 61;
   return d;
 }
 // kind::tf32, fp32 accumulate. a_mn / b_mn = 1 when the operand is MN-major in shared memory.
@@ -155,7 +159,8 @@ inline PFN_encodeTiled get_encode_tiled() {
 // fp32 tensor, `rank` dims listed innermost first; strides in ELEMENTS for dims 1..rank-1 (dim 0 is contiguous).
 // tf32_convert: let the TMA unit round fp32 -> tf32 while loading (CU_TENSOR_MAP_DATA_TYPE_TFLOAT32).
 inline int encode_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
-                       const uint32_t* box, const uint32_t* elem_strides, bool swizzle128, bool tf32_convert = false) {
+                       const uint32_t* box, const uint32_t* elem_strides, int swizzle /*0 none, 1 128B, 2 128B_ATOM_32B*/,
+                       bool tf32_convert = false) {
   PFN_encodeTiled fn = get_encode_tiled();
   if (!fn) return fail(GG_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available%s");
   cuuint64_t gdim[5], gstr[4];
@@ -164,7 +169,9 @@ inline int encode_tmap(CUtensorMap* out, const void* base, int rank, const uint6
   for (int i = 1; i < rank; ++i) gstr[i - 1] = strides_elems[i] * sizeof(float);
   CUresult r = fn(out, tf32_convert ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
                   const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B
+                               : (swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_NONE),
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(GG_ERR_DRIVER, "cuTensorMapEncodeTiled failed (CUresult %s%lld)", "", (long long)r);
   return GG_OK;

@@ -175,13 +175,15 @@ def test_unary_binary_reduce_softmax():
     z = torch.randn(64, 128, generator=g)
     mu = torch.randn(30, 128, generator=g)
     out = torch.empty(64, 30, 128, device="cuda")
-    cabi.call("gg_binary", cabi.BINARY["sub"], cabi.ptr(U.dev(z)), cabi.ptr(U.dev(mu)), cabi.ptr(out),
+    zd, mud = U.dev(z), U.dev(mu)
+    cabi.call("gg_binary", cabi.BINARY["sub"], cabi.ptr(zd), cabi.ptr(mud), cabi.ptr(out),
               cabi.int4([1, 64, 30, 128]), cabi.int4([0, 128, 0, 1]), cabi.int4([0, 0, 128, 1]), 0.0, st)
     U.assert_close(out, z[:, None, :] - mu[None, :, :], 1e-6, "binary bcast")
     # flat
     y = torch.randn(64, 3072, generator=g)
     out = torch.empty_like(xd)
-    cabi.call("gg_binary", cabi.BINARY["mul"], cabi.ptr(xd), cabi.ptr(U.dev(y)), cabi.ptr(out),
+    yd = U.dev(y)
+    cabi.call("gg_binary", cabi.BINARY["mul"], cabi.ptr(xd), cabi.ptr(yd), cabi.ptr(out),
               cabi.int4([1, 1, 64, 3072]), cabi.int4([0, 0, 3072, 1]), cabi.int4([0, 0, 3072, 1]), 0.0, st)
     U.assert_close(out, x * y, 1e-6, "binary flat")
     # reduce: sum over last axis, mean over rows, max
@@ -202,10 +204,12 @@ def test_unary_binary_reduce_softmax():
     gy = torch.randn(64, 30, generator=g, dtype=torch.float64)
     (dl,) = torch.autograd.grad(sm, lg, gy)
     smd = torch.empty(64, 30, device="cuda")
-    cabi.call("gg_softmax_fwd", cabi.ptr(U.dev(lg.detach() / 0.1)), cabi.ptr(smd), 64, 30, st)
+    lgd = U.dev(lg.detach() / 0.1)
+    cabi.call("gg_softmax_fwd", cabi.ptr(lgd), cabi.ptr(smd), 64, 30, st)
     U.assert_close(smd, sm, 1e-5, "softmax fwd")
     dld = torch.empty(64, 30, device="cuda")
-    cabi.call("gg_softmax_bwd", cabi.ptr(smd), cabi.ptr(U.dev(gy)), cabi.ptr(dld), 64, 30, st)
+    gyd = U.dev(gy)
+    cabi.call("gg_softmax_bwd", cabi.ptr(smd), cabi.ptr(gyd), cabi.ptr(dld), 64, 30, st)
     U.assert_close(dld / 0.1, dl, 1e-4, "softmax bwd")
 
 
@@ -224,23 +228,27 @@ def test_layout_index_and_cast_ops_bit_exact():
     # concat along axis 1 through copy2d
     a, b = torch.randn(64, 4096, generator=g), torch.randn(64, 512, generator=g)
     cat = torch.empty(64, 4608, device="cuda")
-    cabi.call("gg_copy2d", cabi.ptr(U.dev(a)), 4096, cabi.ptr(cat), 4608, 64, 4096, 0, st)
-    cabi.call("gg_copy2d", cabi.ptr(U.dev(b)), 512, cat.data_ptr() + 4096 * 4, 4608, 64, 512, 0, st)
+    ad, bd = U.dev(a), U.dev(b)
+    cabi.call("gg_copy2d", cabi.ptr(ad), 4096, cabi.ptr(cat), 4608, 64, 4096, 0, st)
+    cabi.call("gg_copy2d", cabi.ptr(bd), 512, cat.data_ptr() + 4096 * 4, 4608, 64, 512, 0, st)
     assert torch.equal(cat.cpu(), torch.cat([a, b], 1))
     # one_hot / argmax
     idx = torch.randint(0, 30, (64,), generator=g, dtype=torch.int32)
     oh = torch.empty(64, 30, device="cuda")
-    cabi.call("gg_one_hot", cabi.ptr(idx.cuda()), cabi.ptr(oh), 64, 30, st)
+    idxd = idx.cuda()
+    cabi.call("gg_one_hot", cabi.ptr(idxd), cabi.ptr(oh), 64, 30, st)
     assert torch.equal(oh.cpu(), torch.nn.functional.one_hot(idx.long(), 30).float())
     lg = torch.randn(64, 30, generator=g)
     lg[3, 5] = lg[3, 9] = 100.0   # tie -> first index, like tf.argmax
     am = torch.empty(64, dtype=torch.int32, device="cuda")
-    cabi.call("gg_argmax", cabi.ptr(U.dev(lg)), cabi.ptr(am), 64, 30, st)
+    lgd = U.dev(lg)
+    cabi.call("gg_argmax", cabi.ptr(lgd), cabi.ptr(am), 64, 30, st)
     assert torch.equal(am.cpu().long(), lg.argmax(1)) and int(am[3]) == 5
     # int32 image decode: the host emits cast (a=1,b=0) and the affine chain separately for exact parity
     xi = torch.randint(0, 256, (64, 3072), generator=g, dtype=torch.int32)
     xf = torch.empty(64, 3072, device="cuda")
-    cabi.call("gg_cast_i32_f32", cabi.ptr(xi.cuda()), cabi.ptr(xf), xi.numel(), 1.0, 0.0, st)
+    xid = xi.cuda()
+    cabi.call("gg_cast_i32_f32", cabi.ptr(xid), cabi.ptr(xf), xi.numel(), 1.0, 0.0, st)
     assert torch.equal(xf.cpu(), xi.float())
     back = torch.empty(64, 3072, dtype=torch.int32, device="cuda")
     cabi.call("gg_cast_f32_i32", cabi.ptr(xf), cabi.ptr(back), xi.numel(), st)
@@ -276,12 +284,14 @@ def test_losses():
     b = torch.randn(64, 3072, generator=g, dtype=torch.float64)
     for p, name in ((2, 'l2'), (1, 'l1')):
         out = torch.zeros(1, device="cuda")
-        cabi.call("gg_dist_mean", cabi.ptr(U.dev(a)), cabi.ptr(U.dev(b)), a.numel(), p, 1.0, cabi.ptr(out), 0, st)
+        ad, bd = U.dev(a), U.dev(b)
+        cabi.call("gg_dist_mean", cabi.ptr(ad), cabi.ptr(bd), a.numel(), p, 1.0, cabi.ptr(out), 0, st)
         U.assert_close(out, O.distance(a, b, name).reshape(1), 1e-5, "distance " + name)
     gr = torch.randn(64, 3072, generator=g, dtype=torch.float64) * 0.02
     slopes = torch.empty(64, device="cuda")
     out = torch.zeros(1, device="cuda")
-    cabi.call("gg_gp_slope_penalty", cabi.ptr(U.dev(gr)), 64, 3072, 10.0, cabi.ptr(slopes), cabi.ptr(out), st)
+    grd = U.dev(gr)
+    cabi.call("gg_gp_slope_penalty", cabi.ptr(grd), 64, 3072, 10.0, cabi.ptr(slopes), cabi.ptr(out), st)
     U.assert_close(out, O.gradient_penalty(gr, 10.0).reshape(1), 1e-5, "gp")
 
 

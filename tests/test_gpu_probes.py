@@ -41,7 +41,8 @@ def test_tma_strided_box_gathers_conv_tap(swz, h0, w0):
     x = rs.randn(B, H, W, Cc).astype(np.float32)
     hb, wb, b, c0 = 8, 8, 1, 32
     out = torch.empty(hb * wb * 32, device="cuda")
-    cabi.call("gg_probe_tma_strided", cabi.ptr(U.dev(x)), B, H, W, Cc, b, h0, w0, c0, hb, wb, swz, cabi.ptr(out),
+    xd = U.dev(x)
+    cabi.call("gg_probe_tma_strided", cabi.ptr(xd), B, H, W, Cc, b, h0, w0, c0, hb, wb, swz, cabi.ptr(out),
               cabi.stream_ptr())
     torch.cuda.synchronize()
     got = out.cpu().numpy()
@@ -80,7 +81,8 @@ def test_umma_tf32_operand_layouts(a_mn, b_mn, N, K, cv):
     A_st = np.ascontiguousarray(A.T) if a_mn else A          # MN-major A is stored [K,128]
     B_st = Bm if b_mn else np.ascontiguousarray(Bm.T)        # K-major B is stored [N,K]
     D = torch.full((128, N), float("nan"), device="cuda")
-    cabi.call("gg_probe_umma_tf32", cabi.ptr(U.dev(A_st)), cabi.ptr(U.dev(B_st)), cabi.ptr(D), N, K, a_mn, b_mn, cv,
+    Ad, Bd = U.dev(A_st), U.dev(B_st)    # keep the device buffers alive across the call
+    cabi.call("gg_probe_umma_tf32", cabi.ptr(Ad), cabi.ptr(Bd), cabi.ptr(D), N, K, a_mn, b_mn, cv,
               cabi.stream_ptr())
     torch.cuda.synchronize()
     got = D.cpu().numpy().astype(np.float64)
