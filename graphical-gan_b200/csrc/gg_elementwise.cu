@@ -49,6 +49,8 @@ __device__ __forceinline__ float unary_apply(int op, float x, float a, float b) 
     case GG_U_CLIP: return fminf(fmaxf(x, a), b);
     case GG_U_SIGN: return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f);
     case GG_U_SOFTSIGN: return x / (1.f + fabsf(x));
+    case GG_U_DIVC: return x / a;
+    case GG_U_RDIVC: return a / x;
     default: return x;
   }
 }
@@ -94,6 +96,7 @@ extern "C" int gg_unary(int op, const float* x, float* y, long long n, float a, 
     GG_UNARY_CASE(GG_U_SQUARE) GG_UNARY_CASE(GG_U_NEG) GG_UNARY_CASE(GG_U_ABS) GG_UNARY_CASE(GG_U_AFFINE)
     GG_UNARY_CASE(GG_U_POW) GG_UNARY_CASE(GG_U_RSQRT) GG_UNARY_CASE(GG_U_RECIP) GG_UNARY_CASE(GG_U_BCE)
     GG_UNARY_CASE(GG_U_CLIP) GG_UNARY_CASE(GG_U_SIGN) GG_UNARY_CASE(GG_U_SOFTSIGN)
+    GG_UNARY_CASE(GG_U_DIVC) GG_UNARY_CASE(GG_U_RDIVC)
     default: return fail(GG_ERR_BAD_ARG, "gg_unary: unknown op%s");
   }
   return check_launch("gg_unary");

@@ -90,7 +90,7 @@ GG_ADAM_CHUNK = 4096
 ACT = {None: 0, "none": 0, "relu": 1, "leaky": 2, "tanh": 3, "sigmoid": 4}
 UNARY = {"copy": 0, "relu": 1, "leaky": 2, "tanh": 3, "sigmoid": 4, "exp": 5, "log": 6, "sqrt": 7, "square": 8,
          "neg": 9, "abs": 10, "affine": 11, "pow": 12, "rsqrt": 13, "recip": 14, "bce": 15, "clip": 16, "sign": 17,
-         "softsign": 18}
+         "softsign": 18, "divc": 19, "rdivc": 20}
 BINARY = {"add": 0, "sub": 1, "mul": 2, "div": 3, "max": 4, "min": 5, "relu_grad": 6, "leaky_grad": 7,
           "tanh_grad": 8, "sigmoid_grad": 9, "bce_grad": 10, "ge_mask": 11, "gt_mask": 12, "abs_grad": 13, "pow": 14}
 REDUCE = {"sum": 0, "mean": 1, "max": 2}

@@ -1,0 +1,51 @@
+"""Convolution geometry (TensorFlow SAME / VALID rules) and the conv node builders used by tflib.ops.* and tf.nn.*.
+
+tf.nn.conv2d(padding='SAME', stride s): out = ceil(in/s), pad_total = max((out-1)*s + k - in, 0),
+pad_before = pad_total // 2 (the remainder goes AFTER) — so a 5x5 stride-2 conv on an even input pads (1,2), not the
+symmetric (2,2) of most frameworks (call site tflib/ops/conv2d.py:106-112).
+tf.nn.conv2d_transpose is defined as the input-gradient of that conv (tflib/ops/deconv2d.py:101-107).
+"""
+from . import ops as O
+
+
+def same_padding(in_size, k, stride):
+    out = -(-in_size // stride)
+    total = max((out - 1) * stride + k - in_size, 0)
+    return out, total // 2
+
+
+def conv_geometry(B, H, W, Ci, Co, k, stride, padding):
+    if padding == "SAME":
+        Ho, pt = same_padding(H, k, stride)
+        Wo, pl = same_padding(W, k, stride)
+    elif padding == "VALID":
+        Ho, Wo, pt, pl = (H - k) // stride + 1, (W - k) // stride + 1, 0, 0
+    else:
+        raise ValueError("padding must be 'SAME' or 'VALID', got %r" % (padding,))
+    return dict(B=B, H=H, W=W, Ci=Ci, Co=Co, k=k, stride=stride, pad_t=pt, pad_l=pl, Ho=Ho, Wo=Wo)
+
+
+def conv2d_nhwc(x, filters, stride, padding, bias=None):
+    B, H, W, Ci = x.shape
+    k, k2, Ci2, Co = filters.shape
+    if k != k2 or Ci != Ci2:
+        raise ValueError("filter %s does not match input %s" % (tuple(filters.shape), tuple(x.shape)))
+    return O.conv("fwd", x, filters, conv_geometry(B, H, W, Ci, Co, k, stride, padding), bias)
+
+
+def conv2d_nchw(x, filters, stride, padding, bias=None):
+    return O.to_nchw(conv2d_nhwc(O.to_nhwc(x), filters, stride, padding, bias))
+
+
+def conv2d_transpose_nhwc(x, filters, output_shape, stride, padding, bias=None):
+    """x [B,Hin,Win,Cin]; filters (k,k,Cout,Cin); output_shape [B,Hout,Wout,Cout]: the dgrad of the conv
+    Cout -> Cin over an Hout x Wout image."""
+    B, Hin, Win, Cin = x.shape
+    k, k2, Cout, Cin2 = filters.shape
+    if k != k2 or Cin != Cin2:
+        raise ValueError("filter %s does not match input %s" % (tuple(filters.shape), tuple(x.shape)))
+    Hout, Wout = int(output_shape[1]), int(output_shape[2])
+    geom = conv_geometry(B, Hout, Wout, Cout, Cin, k, stride, padding)
+    if (geom["Ho"], geom["Wo"]) != (Hin, Win):
+        raise ValueError("conv2d_transpose: output_shape %s is not consistent with input %s" % (output_shape, tuple(x.shape)))
+    return O.conv("dgrad", x, filters, geom, bias)

@@ -137,6 +137,8 @@ int gg_bn_fold_partials(const float* partial, int S, float* out, int C, void* st
 #define GG_U_CLIP 16     /* min(max(x,a),b) */
 #define GG_U_SIGN 17
 #define GG_U_SOFTSIGN 18
+#define GG_U_DIVC 19     /* x / a  (true division, e.g. the /255. of the input decode) */
+#define GG_U_RDIVC 20    /* a / x */
 int gg_unary(int op, const float* x, float* y, long long n, float a, float b, void* stream);
 
 #define GG_B_ADD 0
