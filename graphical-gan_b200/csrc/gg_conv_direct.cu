@@ -17,6 +17,7 @@ int conv_tc_dgrad(const float* dy, const float* w, const float* bias, float* dx,
 int conv_tc_wgrad(const float* x, const float* dy, float* dw, int B, int H, int W, int Ci, int Co, int k, int stride,
                   int pad_t, int pad_l, int Ho, int Wo, void* ws, size_t ws_bytes, cudaStream_t st, bool* handled);
 size_t conv_tc_wgrad_workspace(int B, int H, int W, int Ci, int Co, int k, int stride, int Ho, int Wo);
+size_t conv_tc_workspace(int mode, int B, int H, int W, int Ci, int Co, int k, int stride, int Ho, int Wo);
 }  // namespace gg
 
 namespace {
@@ -280,6 +281,12 @@ extern "C" size_t gg_conv2d_wgrad_workspace(int B, int H, int W, int Ci, int Co,
   size_t direct = (size_t)direct_wgrad_slices(p) * k * k * Ci * Co * sizeof(float);
   size_t tc = conv_tc_wgrad_workspace(B, H, W, Ci, Co, k, stride, Ho, Wo);
   return direct > tc ? direct : tc;
+}
+
+extern "C" size_t gg_conv2d_workspace(int mode, int B, int H, int W, int Ci, int Co, int k, int stride, int Ho, int Wo) {
+  if (mode == 2) return gg_conv2d_wgrad_workspace(B, H, W, Ci, Co, k, stride, Ho, Wo);
+  size_t tc = conv_tc_workspace(mode, B, H, W, Ci, Co, k, stride, Ho, Wo);
+  return tc > 256 ? tc : 256;
 }
 
 extern "C" int gg_conv2d_wgrad(const float* x, const float* dy, float* dw, int B, int H, int W, int Ci, int Co, int k,

@@ -210,7 +210,8 @@ class Plan(object):
 
     def _ws(self, nbytes):
         torch = _torch()
-        return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=self.rt.dev())
+        # zero-initialised once: the tensor-core conv kernels keep self-cleaning arrival tickets at its start
+        return torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=self.rt.dev())
 
     def _emit(self, node):
         if node.id in self.fed:
@@ -460,7 +461,8 @@ class Plan(object):
             return
         bias = self._in(node, 2).data_ptr() if len(node.inputs) == 3 else None
         act, alpha = cabi.ACT[g["act"]], g["alpha"]
-        ws = self._ws(1 << 16)
+        ws = self._ws(cabi.lib.gg_conv2d_workspace(0 if mode == "fwd" else 1, g["B"], g["H"], g["W"], g["Ci"], g["Co"], g["k"],
+                                                   g["stride"], g["Ho"], g["Wo"]))
         self.keep.append(ws)
         wp, wn = ws.data_ptr(), ws.numel()
         name = "gg_conv2d_fwd" if mode == "fwd" else "gg_conv2d_dgrad"

@@ -85,6 +85,10 @@ int gg_conv2d_wgrad(const float* x, const float* dy, float* dw,
                     int pad_t, int pad_l, int Ho, int Wo,
                     void* workspace, size_t workspace_bytes, void* stream);
 size_t gg_conv2d_wgrad_workspace(int B, int H, int W, int Ci, int Co, int k, int stride, int Ho, int Wo);
+/* workspace bytes for mode 0 fwd / 1 dgrad / 2 wgrad.  The workspace holds split-K partial tiles and, in its first
+ * bytes, per-tile arrival tickets: it must be ZERO-INITIALISED ONCE by the caller; every call leaves the tickets zero.
+ * A smaller (or NULL) workspace is legal: the call then runs unsplit or on the direct kernels. */
+size_t gg_conv2d_workspace(int mode, int B, int H, int W, int Ci, int Co, int k, int stride, int Ho, int Wo);
 
 /* ---- dense (tf.matmul, tflib/ops/linear.py:132-146) -------------------------------- */
 /* C[M,N] = act( op(A) * op(B) + bias[N] ),  op(A) is [M,K], op(B) is [K,N]; row-major storage,

@@ -30,8 +30,8 @@ def geom(H, W, k, stride, padding):
 
 
 def ws(nbytes):
-    n = max(int(nbytes), 16)
-    return torch.empty(n, dtype=torch.uint8, device=DEV)
+    n = max(int(nbytes), 256)
+    return torch.zeros(n, dtype=torch.uint8, device=DEV)   # zero once: arrival tickets of the split-K conv kernels
 
 
 def conv_fwd(x_nhwc, w, bias, stride, padding, act=None, alpha=0.2):
@@ -39,7 +39,7 @@ def conv_fwd(x_nhwc, w, bias, stride, padding, act=None, alpha=0.2):
     k, _, _, Co = w.shape
     Ho, Wo, pt, pl = geom(H, W, k, stride, padding)
     y = torch.empty(B, Ho, Wo, Co, device=DEV)
-    wsp = ws(1 << 20)
+    wsp = ws(cabi.lib.gg_conv2d_workspace(0, B, H, W, Ci, Co, k, stride, Ho, Wo))
     cabi.call("gg_conv2d_fwd", cabi.ptr(x_nhwc), cabi.ptr(w), cabi.ptr(bias), cabi.ptr(y), B, H, W, Ci, Co, k, stride, pt, pl,
               Ho, Wo, cabi.ACT[act], alpha, cabi.ptr(wsp), wsp.numel(), cabi.stream_ptr())
     return y
@@ -51,7 +51,7 @@ def conv_dgrad(dy_nhwc, w, bias, H, W, stride, padding, act=None, alpha=0.2):
     Ho2, Wo2, pt, pl = geom(H, W, k, stride, padding)
     assert (Ho2, Wo2) == (Ho, Wo)
     dx = torch.empty(B, H, W, Ci, device=DEV)
-    wsp = ws(1 << 20)
+    wsp = ws(cabi.lib.gg_conv2d_workspace(1, B, H, W, Ci, Co, k, stride, Ho, Wo))
     cabi.call("gg_conv2d_dgrad", cabi.ptr(dy_nhwc), cabi.ptr(w), cabi.ptr(bias), cabi.ptr(dx), B, H, W, Ci, Co, k, stride, pt,
               pl, Ho, Wo, cabi.ACT[act], alpha, cabi.ptr(wsp), wsp.numel(), cabi.stream_ptr())
     return dx
