@@ -18,6 +18,7 @@ int conv_tc_wgrad(const float* x, const float* dy, float* dw, int B, int H, int 
                   int pad_t, int pad_l, int Ho, int Wo, void* ws, size_t ws_bytes, cudaStream_t st, bool* handled);
 size_t conv_tc_wgrad_workspace(int B, int H, int W, int Ci, int Co, int k, int stride, int Ho, int Wo);
 size_t conv_tc_workspace(int mode, int B, int H, int W, int Ci, int Co, int k, int stride, int Ho, int Wo);
+void conv_tc_set_debug(void* p);
 }  // namespace gg
 
 namespace {
@@ -281,6 +282,11 @@ extern "C" size_t gg_conv2d_wgrad_workspace(int B, int H, int W, int Ci, int Co,
   size_t direct = (size_t)direct_wgrad_slices(p) * k * k * Ci * Co * sizeof(float);
   size_t tc = conv_tc_wgrad_workspace(B, H, W, Ci, Co, k, stride, Ho, Wo);
   return direct > tc ? direct : tc;
+}
+
+extern "C" int gg_debug_set_buffer(void* device_buffer_256_int64) {
+  conv_tc_set_debug(device_buffer_256_int64);
+  return GG_OK;
 }
 
 extern "C" size_t gg_conv2d_workspace(int mode, int B, int H, int W, int Ci, int Co, int k, int stride, int Ho, int Wo) {

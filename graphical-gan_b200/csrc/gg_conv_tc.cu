@@ -27,7 +27,7 @@ namespace gg {
 
 namespace {
 
-constexpr int kStages = 4;
+constexpr int kMaxStages = 6;                  // 6 x 32 KB operand stages + 1 KB alignment slack fit the 227 KB of an SM
 constexpr int kABytes = 128 * 32 * 4;          // 16 KB: 128 rows (or 4 x 32 MN-blocks) of 32 fp32
 constexpr int kMaxNTile = 128;
 constexpr int kThreads = 192;
@@ -40,20 +40,34 @@ struct TcParams {
   int n_tile, n_tiles;        // GEMM N tiling
   int m_tiles;                // fwd/dgrad: tw*th*tb (per class); wgrad: ceil(taps*Ci/128)
   int splits;
+  int stages;                 // depth of the operand ring (as many as fit)
   int act;
   float alpha;
   float* out;
   const float* bias;
   float* partial;             // [splits][tiles][128][n_tile]
   unsigned* counters;         // [tiles], zero on entry, left zero
+  long long* dbg;             // optional timeline of CTA (0,0): see gg_debug_set_buffer
 };
+
+__device__ __forceinline__ long long gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#ifdef GG_TIMELINE
+#define GG_DBG(slot) do { if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0) p.dbg[slot] = gtime(); } while (0)
+#else
+#define GG_DBG(slot) do { } while (0)
+#endif
 
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t full_bar[kStages], empty_bar[kStages], accum_bar;
+  __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], accum_bar;
+  const int kStages = p.stages;
   __shared__ uint32_t tmem_base_sh;
   __shared__ int last_flag;
 
@@ -98,7 +112,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   // ---- one-time setup ------------------------------------------------------------------------------------
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&accum_bar, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
@@ -110,46 +124,69 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = tmem_base_sh;
+  if (threadIdx.x == 0) GG_DBG(0);
+  if (p.dbg && threadIdx.x == 0) atomicMin(reinterpret_cast<unsigned long long*>(p.dbg + 201), (unsigned long long)gtime());
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
+    // Coordinates advance incrementally (no integer divisions in the issue loop: one elected lane issues every TMA of
+    // the CTA, so its instruction stream IS the load-issue rate); each operand stage is one TMA where the layout allows.
     if (lane == 0) {
+      int c_cb = 0, c_s = 0, c_r = 0;          // fwd / dgrad: channel block, tap column, tap row (dgrad: class-local)
+      int px_w = 0, px_h = 0, px_b = 0;        // wgrad: pixel-block origin
+      int qa_c[4], qa_w[4], qa_h[4];           // wgrad: loop-invariant (ci block, tap offsets) of the 4 A boxes
+      if (MODE == 2) {
+        px_w = (kb0 % p.tw) * p.wt;
+        px_h = ((kb0 / p.tw) % p.th) * p.ht;
+        px_b = (kb0 / (p.tw * p.th)) * p.bt;
+        const int qblocks = p.Ci / 32;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          int q = mt * 4 + j;
+          if (q >= taps * qblocks) q = taps * qblocks - 1;        // padded rows: valid data, masked at the store
+          const int tap = q / qblocks;
+          qa_c[j] = (q % qblocks) * 32;
+          qa_w[j] = tap % p.k - p.pad_l;
+          qa_h[j] = tap / p.k - p.pad_t;
+        }
+      } else {
+        const int t0 = kb0 / cblocks;
+        c_cb = kb0 % cblocks;
+        const int row_len = (MODE == 0) ? p.k : ns;
+        c_r = t0 / row_len;
+        c_s = t0 % row_len;
+      }
+      int s = 0;
+      uint32_t ph = 0;
       for (int i = 0; i < nkb; ++i) {
-        const int kb = kb0 + i;
-        const int s = i % kStages;
-        if (i >= kStages) mbar_wait(&empty_bar[s], ((i / kStages) - 1) & 1);
+        mbar_wait(&empty_bar[s], ph ^ 1);            // a fresh barrier passes a parity-1 wait: first lap never blocks
         uint8_t* sA = smem + s * stage_bytes;
         uint8_t* sB = sA + kABytes;
+        if (i < 60) GG_DBG(1 + i);
         mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
         if (MODE == 0) {
-          const int tap = kb / cblocks, cb = kb % cblocks;
-          const int r = tap / p.k, sx = tap % p.k;
-          tma_load_4d(sA, &tmA, &full_bar[s], cb * 32, w0 * p.stride + sx - p.pad_l, h0 * p.stride + r - p.pad_t, b0);
-          for (int nb = 0; nb < p.n_tile / 32; ++nb)
-            tma_load_3d(sB + nb * 4096, &tmB, &full_bar[s], n0 + nb * 32, cb * 32, tap);
+          tma_load_4d(sA, &tmA, &full_bar[s], c_cb * 32, w0 * p.stride + c_s - p.pad_l, h0 * p.stride + c_r - p.pad_t, b0);
+          tma_load_4d(sB, &tmB, &full_bar[s], 0, c_cb * 32, n0 / 32, c_r * p.k + c_s);
         } else if (MODE == 1) {
-          const int t = kb / cblocks, cb = kb % cblocks;
-          const int rq = t / ns, sq = t % ns;
-          const int r = a_h + p.stride * rq, sx = a_w + p.stride * sq;
-          tma_load_4d(sA, &tmA, &full_bar[s], cb * 32, w0 + d_w - sq, h0 + d_h - rq, b0);
-          tma_load_3d(sB, &tmB, &full_bar[s], cb * 32, n0, r * p.k + sx);
+          tma_load_4d(sA, &tmA, &full_bar[s], c_cb * 32, w0 + d_w - c_s, h0 + d_h - c_r, b0);
+          tma_load_3d(sB, &tmB, &full_bar[s], c_cb * 32, n0, (a_h + p.stride * c_r) * p.k + a_w + p.stride * c_s);
         } else {
-          // pixel block kb -> (b, ho, wo) box of 32 pixels
-          const int pw0 = (kb % p.tw) * p.wt;
-          const int ph0 = ((kb / p.tw) % p.th) * p.ht;
-          const int pb0 = (kb / (p.tw * p.th)) * p.bt;
-          const int qblocks = p.Ci / 32;
-          for (int j = 0; j < 4; ++j) {
-            int q = mt * 4 + j;
-            if (q >= taps * qblocks) q = taps * qblocks - 1;      // padded rows: valid data, masked at the store
-            const int tap = q / qblocks, cb = q % qblocks;
-            const int r = tap / p.k, sx = tap % p.k;
-            tma_load_4d(sA + j * 4096, &tmA, &full_bar[s], cb * 32, pw0 * p.stride + sx - p.pad_l,
-                        ph0 * p.stride + r - p.pad_t, pb0);
-          }
-          for (int nb = 0; nb < p.n_tile / 32; ++nb)
-            tma_load_2d(sB + nb * 4096, &tmB, &full_bar[s], n0 + nb * 32, kb * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            tma_load_4d(sA + j * 4096, &tmA, &full_bar[s], qa_c[j], px_w * p.stride + qa_w[j], px_h * p.stride + qa_h[j], px_b);
+          tma_load_3d(sB, &tmB, &full_bar[s], 0, (kb0 + i) * 32, n0 / 32);
         }
+        if (MODE == 2) {
+          px_w += p.wt;
+          if (px_w == p.PW) { px_w = 0; px_h += p.ht; if (px_h == p.PH) { px_h = 0; px_b += p.bt; } }
+        } else {
+          if (++c_cb == cblocks) {
+            c_cb = 0;
+            const int row_len = (MODE == 0) ? p.k : ns;
+            if (++c_s == row_len) { c_s = 0; ++c_r; }
+          }
+        }
+        if (++s == kStages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -158,10 +195,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       constexpr int a_mn = (MODE == 2) ? 1 : 0;
       constexpr int b_mn = (MODE == 1) ? 0 : 1;
       const uint32_t idesc = make_idesc_tf32(128, p.n_tile, a_mn, b_mn);
+      int s = 0;
+      uint32_t ph = 0;
       for (int i = 0; i < nkb; ++i) {
-        const int s = i % kStages;
-        mbar_wait(&full_bar[s], (i / kStages) & 1);
+        mbar_wait(&full_bar[s], ph);
         tc_fence_after();
+        if (i < 60) GG_DBG(64 + i);
         const uint32_t aBase = smem_u32(smem + s * stage_bytes);
         const uint32_t bBase = aBase + kABytes;
 #pragma unroll
@@ -173,6 +212,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           umma_tf32(tmem_d, ad, bd, idesc, (i | j) != 0);
         }
         umma_commit(&empty_bar[s]);          // frees the smem stage once these MMAs have read it
+        if (++s == kStages) { s = 0; ph ^= 1; }
       }
       umma_commit(&accum_bar);               // accumulator complete
     }
@@ -183,6 +223,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int et = threadIdx.x - 64;              // 0..127
     mbar_wait(&accum_bar, 0);
     tc_fence_after();
+    if (et == 0) GG_DBG(128);
     bool valid;
     float* orow;
     if (MODE == 0) {
@@ -200,36 +241,52 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       orow = p.out + (size_t)row * p.Co + n0;
     }
     const uint32_t taddr = tmem_d + ((uint32_t)(quad * 32) << 16);
+    // The operand ring is idle once accum_bar has fired: reuse it as a [128][n_tile+4] staging tile so that the final
+    // global stores are row-coalesced (a warp writes one whole output row per instruction).
+    float* stage_tile = reinterpret_cast<float*>(smem);
+    long long* row_off = reinterpret_cast<long long*>(smem + 128 * (kMaxNTile + 4) * 4);
+    const int ld = p.n_tile + 4;
+    row_off[m] = valid ? (long long)(orow - p.out) : -1;
+    bool do_store = true;
+    // activation / bias parameters hoisted into registers: none / relu / leaky are max(a*v, v) with a = 1 / 0 / alpha
+    const float a_eff = act_slope(p.act, p.alpha);
+    const bool slow_act = (MODE != 2) && p.act >= GG_ACT_TANH;
+    const int act_code = p.act;
+    const float* bias_n0 = (MODE != 2 && p.bias != nullptr) ? p.bias + n0 : nullptr;
+#define GG_FINISH4(o, col)                                                                        \
+    do {                                                                                          \
+      if (bias_n0) {                                                                              \
+        const float4 bb = *reinterpret_cast<const float4*>(bias_n0 + (col));                      \
+        o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;                                       \
+      }                                                                                           \
+      if (MODE != 2) {                                                                            \
+        if (!slow_act) {                                                                          \
+          o.x = fmaxf(o.x * a_eff, o.x); o.y = fmaxf(o.y * a_eff, o.y);                           \
+          o.z = fmaxf(o.z * a_eff, o.z); o.w = fmaxf(o.w * a_eff, o.w);                           \
+        } else {                                                                                  \
+          o.x = apply_act_slow(o.x, act_code); o.y = apply_act_slow(o.y, act_code);               \
+          o.z = apply_act_slow(o.z, act_code); o.w = apply_act_slow(o.w, act_code);               \
+        }                                                                                         \
+      }                                                                                           \
+    } while (0)
+    int cbeg = 0, cend = p.n_tile / 4;          // float4 column range of the tile this CTA writes out
     if (p.splits == 1) {
       for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
         float v[32];
-        if (nkb > 0) tmem_ld_32x32(taddr + (uint32_t)c0, v);
-        else {
+        tmem_ld_32x32(taddr + (uint32_t)c0, v);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = 0.f;
-        }
-        if (valid) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            float4 o;
-            o.x = v[i], o.y = v[i + 1], o.z = v[i + 2], o.w = v[i + 3];
-            if (MODE != 2) {
-              if (p.bias) {
-                const float4 bb = *reinterpret_cast<const float4*>(p.bias + n0 + c0 + i);
-                o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-              }
-              o.x = apply_act(o.x, p.act, p.alpha); o.y = apply_act(o.y, p.act, p.alpha);
-              o.z = apply_act(o.z, p.act, p.alpha); o.w = apply_act(o.w, p.act, p.alpha);
-            }
-            *reinterpret_cast<float4*>(orow + c0 + i) = o;
-          }
+        for (int i = 0; i < 32; i += 4) {
+          float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          GG_FINISH4(o, c0 + i);
+          *reinterpret_cast<float4*>(stage_tile + m * ld + c0 + i) = o;
         }
       }
     } else {
-      // split-K: park the partial tile in the (L2-resident) workspace, last CTA on this tile reduces in split order
+      // split-K: park the partial tile in the (L2-resident) workspace in a [n_tile/4][128 rows] float4 layout (coalesced
+      // for the thread-per-row TMEM readout); the last CTA to take a ticket on this tile sums the splits in split order.
       const size_t tile_elems = (size_t)128 * p.n_tile;
       const size_t ntiles_all = gridDim.x;
-      float* prow = p.partial + ((size_t)split * ntiles_all + blockIdx.x) * tile_elems + (size_t)m * p.n_tile;
+      float4* pme = reinterpret_cast<float4*>(p.partial + ((size_t)split * ntiles_all + blockIdx.x) * tile_elems) + m;
       for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
         float v[32];
         if (nkb > 0) tmem_ld_32x32(taddr + (uint32_t)c0, v);
@@ -238,42 +295,98 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int i = 0; i < 32; ++i) v[i] = 0.f;
         }
 #pragma unroll
-        for (int i = 0; i < 32; i += 4)
-          *reinterpret_cast<float4*>(prow + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        for (int i = 0; i < 32; i += 4) pme[(size_t)((c0 + i) >> 2) * 128] = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
       }
+      if (et == 0) GG_DBG(129);
+      // All `splits` CTAs of this tile are co-resident (cooperative launch, grid <= #SMs): rendezvous on a ticket, then
+      // EVERY CTA reduces its own 1/splits column slice of the tile (summing the splits in split order: deterministic)
+      // instead of one CTA serially re-reading all partials — the reduction's L2 round trips run on `splits` SMs at once.
       __threadfence();
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (et == 0) {
-        const unsigned old = atomicAdd(&p.counters[blockIdx.x], 1u);
-        const int last = (old == (unsigned)(p.splits - 1));
-        if (last) p.counters[blockIdx.x] = 0u;      // self-cleaning ticket
-        last_flag = last;
+        atomicAdd(&p.counters[blockIdx.x], 1u);
+        unsigned seen;
+        unsigned spins = 0;
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.counters + blockIdx.x) : "memory");
+          if (seen < (unsigned)p.splits) { __nanosleep(32); if (++spins > (1u << 22)) __trap(); }
+        } while (seen < (unsigned)p.splits);
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (last_flag) {
-        __threadfence();
-        if (valid) {
-          for (int c0 = 0; c0 < p.n_tile; c0 += 4) {
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int sp = 0; sp < p.splits; ++sp) {
-              const float4 t = __ldcg(reinterpret_cast<const float4*>(
-                  p.partial + ((size_t)sp * ntiles_all + blockIdx.x) * tile_elems + (size_t)m * p.n_tile + c0));
-              acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
-            }
-            if (MODE != 2) {
-              if (p.bias) {
-                const float4 bb = *reinterpret_cast<const float4*>(p.bias + n0 + c0);
-                acc.x += bb.x; acc.y += bb.y; acc.z += bb.z; acc.w += bb.w;
+      const int nc = p.n_tile / 4;
+      cbeg = (split * nc) / p.splits;
+      cend = ((split + 1) * nc) / p.splits;
+      {
+        const float4* pbase = reinterpret_cast<const float4*>(p.partial + (size_t)blockIdx.x * tile_elems) + m;
+        const size_t split_stride4 = ntiles_all * tile_elems / 4;
+        // up to 16 independent L2 loads in flight per thread (4 column groups x 4 splits)
+        for (int c4 = cbeg; c4 < cend; c4 += 4) {
+          float4 acc[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int sp = 0; sp < p.splits; sp += 4) {
+            float4 t[4][4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                t[q][u] = (sp + q < p.splits && c4 + u < cend)
+                              ? __ldcg(pbase + (size_t)(sp + q) * split_stride4 + (size_t)(c4 + u) * 128)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                acc[u].x += t[q][u].x; acc[u].y += t[q][u].y; acc[u].z += t[q][u].z; acc[u].w += t[q][u].w;
               }
-              acc.x = apply_act(acc.x, p.act, p.alpha); acc.y = apply_act(acc.y, p.act, p.alpha);
-              acc.z = apply_act(acc.z, p.act, p.alpha); acc.w = apply_act(acc.w, p.act, p.alpha);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (c4 + u < cend) {
+              float4 o = acc[u];
+              GG_FINISH4(o, (c4 + u) * 4);
+              *reinterpret_cast<float4*>(stage_tile + m * ld + (c4 + u) * 4) = o;
             }
-            *reinterpret_cast<float4*>(orow + c0) = acc;
           }
         }
       }
+      // second ticket: the last CTA to finish reading the partials re-arms both counters for the next launch
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et == 0) {
+        const unsigned old = atomicAdd(&p.counters[gridDim.x + blockIdx.x], 1u);
+        if (old == (unsigned)(p.splits - 1)) { p.counters[blockIdx.x] = 0u; p.counters[gridDim.x + blockIdx.x] = 0u; }
+      }
+    }
+#undef GG_FINISH4
+    (void)do_store;
+    {
+      if (p.dbg && et == 0) p.dbg[140] = gtime();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (p.dbg && et == 0) p.dbg[141] = gtime();
+      // coalesced write-out of columns [cbeg, cend): consecutive threads take consecutive float4 of a row
+      const int ncol = cend - cbeg;
+      const int total = 128 * ncol;
+      for (int base = et; base < total; base += 4 * 128) {
+        float4 val[4];
+        long long off[4];
+        int cc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int idx = base + u * 128;
+          const int r = (idx < total) ? idx / ncol : 0;
+          cc[u] = cbeg + ((idx < total) ? idx - r * ncol : 0);
+          off[u] = (idx < total) ? row_off[r] : -1;
+          val[u] = *reinterpret_cast<const float4*>(stage_tile + r * ld + cc[u] * 4);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (off[u] >= 0) *reinterpret_cast<float4*>(p.out + off[u] + cc[u] * 4) = val[u];
+      }
+      if (p.dbg && et == 0) p.dbg[203] = gtime();
     }
   }
+  if (threadIdx.x == 64) GG_DBG(131);
+  if (p.dbg && threadIdx.x == 64) atomicMax(reinterpret_cast<unsigned long long*>(p.dbg + 200), (unsigned long long)gtime());
   // ---- teardown -----------------------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
@@ -291,7 +404,9 @@ bool pixel_box(int PW, int PH, int PB, int target, int* wt, int* ht, int* bt) {
   if (h > PH) h = PH;
   if (h <= 0 || (target / w) % h != 0 || PH % h != 0) return false;
   int b = target / (w * h);
-  if (b <= 0 || w * h * b != target || PB % b != 0) return false;
+  // a batch box larger than / not dividing the batch is fine: TMA zero-fills the missing images and the epilogue masks
+  // their rows (this is how M = 64-row dense layers ride the 128-row MMA)
+  if (b <= 0 || w * h * b != target) return false;
   if (w > 256 || h > 256 || b > 256) return false;
   *wt = w; *ht = h; *bt = b;
   return true;
@@ -304,8 +419,15 @@ int pick_n_tile(int n) {
   return 0;
 }
 
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && e[0]) ? atoi(e) : dflt;
+}
+
 int pick_splits(int tiles, int kb_min) {
-  int s = (kNumSMs + tiles - 1) / tiles;     // aim at >= one full wave of CTAs
+  int forced = env_int("GG_TC_SPLITS", 0);   // experiment knob
+  if (forced > 0) return forced;
+  int s = kNumSMs / tiles;                   // fill (at most) one wave of CTAs: 1 CTA per SM (shared-memory bound)
   int cap = kb_min / 3;                      // keep >= 3 k-blocks per CTA so the pipeline fills
   if (cap < 1) cap = 1;
   if (s > cap) s = cap;
@@ -313,6 +435,8 @@ int pick_splits(int tiles, int kb_min) {
   if (s < 1) s = 1;
   return s;
 }
+
+long long* g_dbg = nullptr;
 
 struct TcPlan {
   bool ok;
@@ -345,7 +469,7 @@ TcPlan make_plan(int mode, int B, int H, int W, int Ci, int Co, int k, int strid
     p.n_tile = pick_n_tile(Co);
     if (!p.n_tile) return pl;
     p.n_tiles = Co / p.n_tile;
-    p.tw = Wo / p.wt; p.th = Ho / p.ht; p.tb = B / p.bt;
+    p.tw = Wo / p.wt; p.th = Ho / p.ht; p.tb = (B + p.bt - 1) / p.bt;
     p.m_tiles = p.tw * p.th * p.tb;
     pl.grid_x = p.m_tiles * p.n_tiles;
     kb_min = k * k * (Ci / 32);
@@ -356,7 +480,7 @@ TcPlan make_plan(int mode, int B, int H, int W, int Ci, int Co, int k, int strid
     p.n_tile = pick_n_tile(Ci);
     if (!p.n_tile) return pl;
     p.n_tiles = Ci / p.n_tile;
-    p.tw = p.PW / p.wt; p.th = p.PH / p.ht; p.tb = B / p.bt;
+    p.tw = p.PW / p.wt; p.th = p.PH / p.ht; p.tb = (B + p.bt - 1) / p.bt;
     p.m_tiles = p.tw * p.th * p.tb;
     pl.grid_x = stride * stride * p.m_tiles * p.n_tiles;
     int nmin = k / stride;                    // fewest taps a class sees along one axis
@@ -364,7 +488,7 @@ TcPlan make_plan(int mode, int B, int H, int W, int Ci, int Co, int k, int strid
     kb_min = nmin * nmin * (Co / 32);
   } else {
     p.PH = Ho; p.PW = Wo;
-    if (!pixel_box(Wo, Ho, B, 32, &p.wt, &p.ht, &p.bt)) return pl;
+    if (!pixel_box(Wo, Ho, B, 32, &p.wt, &p.ht, &p.bt) || B % p.bt != 0) return pl;
     p.n_tile = pick_n_tile(Co);
     if (!p.n_tile) return pl;
     p.n_tiles = Co / p.n_tile;
@@ -376,7 +500,7 @@ TcPlan make_plan(int mode, int B, int H, int W, int Ci, int Co, int k, int strid
   if (p.wt * stride > 256 || p.ht * stride > 256) return pl;
   p.splits = pick_splits(pl.grid_x, kb_min);
   pl.partial_bytes = p.splits > 1 ? (size_t)p.splits * pl.grid_x * 128 * p.n_tile * sizeof(float) : 0;
-  pl.counter_bytes = ((size_t)pl.grid_x * sizeof(unsigned) + 255) & ~size_t(255);
+  pl.counter_bytes = ((size_t)2 * pl.grid_x * sizeof(unsigned) + 255) & ~size_t(255);   // arrival + completion tickets
   pl.ok = true;
   return pl;
 }
@@ -391,32 +515,58 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, TcPlan& pl, void* ws,
     p.splits = 1;
   }
   p.counters = reinterpret_cast<unsigned*>(ws);
+  p.dbg = g_dbg;
   p.partial = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + pl.counter_bytes);
-  const size_t smem = (size_t)kStages * (kABytes + p.n_tile * 128) + 1024;
+  p.stages = kMaxStages;
+  if ((long long)pl.grid_x * p.splits > kNumSMs) {
+    // more CTAs than SMs: keep the footprint under half an SM so two CTAs co-reside and one's epilogue overlaps the
+    // other's main loop
+    int fit = (int)((113 * 1024 - 1024) / (kABytes + p.n_tile * 128));
+    p.stages = fit < 3 ? 3 : (fit > kMaxStages ? kMaxStages : fit);
+  }
+  const size_t smem = (size_t)p.stages * (kABytes + p.n_tile * 128) + 1024;
   static bool attr_set[3] = {false, false, false};
   if (!attr_set[MODE]) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kStages * (kABytes + kMaxNTile * 128) + 1024);
+                                         kMaxStages * (kABytes + kMaxNTile * 128) + 1024);
     if (e != cudaSuccess) return fail(GG_ERR_CUDA_BASE + (int)e, "conv_tc: cudaFuncSetAttribute failed%s");
     attr_set[MODE] = true;
   }
   dim3 grid(pl.grid_x, p.splits);
-  conv_tc_kernel<MODE><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
+  if (p.splits > 1) {
+    // the split-K rendezvous spins on a ticket: all CTAs of the grid must be co-resident -> cooperative launch
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<MODE>, tmA, tmB, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(GG_ERR_CUDA_BASE + (int)e, "conv_tc: cooperative launch failed: %s", cudaGetErrorString(e)); }
+  } else {
+    conv_tc_kernel<MODE><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
+  }
   return check_launch(MODE == 0 ? "gg_conv2d_fwd(tcgen05)" : (MODE == 1 ? "gg_conv2d_dgrad(tcgen05)" : "gg_conv2d_wgrad(tcgen05)"));
 }
 
 // filter tensor map: w [taps][Ci][Co] viewed as dims (Co, Ci, taps)
-int filter_map_mn(CUtensorMap* tm, const float* w, int Ci, int Co, int taps) {   // boxes of 32 co x 32 ci, MN-major operand
-  uint64_t dims[3] = {(uint64_t)Co, (uint64_t)Ci, (uint64_t)taps};
-  uint64_t str[3] = {1, (uint64_t)Co, (uint64_t)Ci * Co};
-  uint32_t box[3] = {32, 32, 1};
-  return encode_tmap(tm, w, 3, dims, str, box, nullptr, 2, true);
+// MN-major B stage in ONE TMA: Co is split into (32 co, Co/32 blocks) so the box (32 co, 32 ci, n_tile/32 blocks, 1 tap)
+// lands as [co block][ci][32 co] = n_tile/32 swizzle atoms of 4 KB, LBO = 4096
+int filter_map_mn(CUtensorMap* tm, const float* w, int Ci, int Co, int taps, int n_tile) {
+  uint64_t dims[4] = {32, (uint64_t)Ci, (uint64_t)(Co / 32), (uint64_t)taps};
+  uint64_t str[4] = {1, (uint64_t)Co, 32, (uint64_t)Ci * Co};
+  uint32_t box[4] = {32, 32, (uint32_t)(n_tile / 32), 1};
+  return encode_tmap(tm, w, 4, dims, str, box, nullptr, 2, env_int("GG_TC_NOCVT", 0) == 0);
 }
 int filter_map_k(CUtensorMap* tm, const float* w, int Ci, int Co, int taps, int n_tile) {  // 32 co x n_tile ci rows, K-major
   uint64_t dims[3] = {(uint64_t)Co, (uint64_t)Ci, (uint64_t)taps};
   uint64_t str[3] = {1, (uint64_t)Co, (uint64_t)Ci * Co};
   uint32_t box[3] = {32, (uint32_t)n_tile, 1};
-  return encode_tmap(tm, w, 3, dims, str, box, nullptr, 1, true);
+  return encode_tmap(tm, w, 3, dims, str, box, nullptr, 1, env_int("GG_TC_NOCVT", 0) == 0);
 }
 // activation tensor map over an NHWC tensor (C,W,H,B); box = 32 channels x (wt,ht,bt) pixels gathered with stride es
 int act_map(CUtensorMap* tm, const float* x, int B, int H, int W, int C, int wt, int ht, int bt, int es, int swizzle) {
@@ -424,7 +574,7 @@ int act_map(CUtensorMap* tm, const float* x, int B, int H, int W, int C, int wt,
   uint64_t str[4] = {1, (uint64_t)C, (uint64_t)W * C, (uint64_t)H * W * C};
   uint32_t box[4] = {32, (uint32_t)(wt * es), (uint32_t)(ht * es), (uint32_t)bt};
   uint32_t estr[4] = {1, (uint32_t)es, (uint32_t)es, 1};
-  return encode_tmap(tm, x, 4, dims, str, box, estr, swizzle, true);
+  return encode_tmap(tm, x, 4, dims, str, box, estr, swizzle, env_int("GG_TC_NOCVT", 0) == 0);
 }
 
 }  // namespace
@@ -439,7 +589,7 @@ int conv_tc_fwd(const float* x, const float* w, const float* bias, float* y, int
   CUtensorMap tmA, tmB;
   int rc = act_map(&tmA, x, B, H, W, Ci, pl.p.wt, pl.p.ht, pl.p.bt, stride, 1);
   if (rc) return rc;
-  rc = filter_map_mn(&tmB, w, Ci, Co, k * k);
+  rc = filter_map_mn(&tmB, w, Ci, Co, k * k, pl.p.n_tile);
   if (rc) return rc;
   pl.p.out = y; pl.p.bias = bias; pl.p.act = act; pl.p.alpha = alpha;
   rc = launch<0>(tmA, tmB, pl, ws, ws_bytes, st);
@@ -477,10 +627,10 @@ int conv_tc_wgrad(const float* x, const float* dy, float* dw, int B, int H, int 
   int rc = act_map(&tmA, x, B, H, W, Ci, pl.p.wt, pl.p.ht, pl.p.bt, stride, 2);
   if (rc) return rc;
   {
-    uint64_t dims[2] = {(uint64_t)Co, (uint64_t)B * Ho * Wo};
-    uint64_t str[2] = {1, (uint64_t)Co};
-    uint32_t box[2] = {32, 32};
-    rc = encode_tmap(&tmB, dy, 2, dims, str, box, nullptr, 2, true);
+    uint64_t dims[3] = {32, (uint64_t)B * Ho * Wo, (uint64_t)(Co / 32)};
+    uint64_t str[3] = {1, (uint64_t)Co, 32};
+    uint32_t box[3] = {32, 32, (uint32_t)(pl.p.n_tile / 32)};
+    rc = encode_tmap(&tmB, dy, 3, dims, str, box, nullptr, 2, env_int("GG_TC_NOCVT", 0) == 0);
     if (rc) return rc;
   }
   pl.p.out = dw; pl.p.bias = nullptr; pl.p.act = 0; pl.p.alpha = 0.f;
@@ -489,6 +639,8 @@ int conv_tc_wgrad(const float* x, const float* dy, float* dw, int B, int H, int 
   *handled = true;
   return GG_OK;
 }
+
+void conv_tc_set_debug(void* p) { g_dbg = reinterpret_cast<long long*>(p); }
 
 size_t conv_tc_workspace(int mode, int B, int H, int W, int Ci, int Co, int k, int stride, int Ho, int Wo) {
   TcPlan pl = make_plan(mode, B, H, W, Ci, Co, k, stride, 0, 0, Ho, Wo);

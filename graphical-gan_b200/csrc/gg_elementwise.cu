@@ -243,6 +243,62 @@ __global__ void __launch_bounds__(256) reduce_cols_kernel(int op, const float* _
   }
 }
 
+// two-stage column reduction for tall matrices (bias gradients: [B*H*W, C] -> [C]): S row slices -> partial[S][inner],
+// then the same kernel folds the S partial rows.  Deterministic (fixed summation order), fills the SMs.
+__global__ void __launch_bounds__(256) reduce_cols_sliced_kernel(int op, const float* __restrict__ x, float* __restrict__ part,
+                                                                 int red, int inner, int rows_per) {
+  __shared__ float sh[8][33];
+  int i = blockIdx.x * 32 + threadIdx.x;
+  int s = blockIdx.y;
+  int r0 = s * rows_per, r1 = min(red, r0 + rows_per);
+  float acc = (op == 2) ? -INFINITY : 0.f;
+  if (i < inner) {
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+      float v = x[(long long)r * inner + i];
+      acc = (op == 2) ? fmaxf(acc, v) : acc + v;
+    }
+  }
+  sh[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && i < inner) {
+    float r = sh[0][threadIdx.x];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) r = (op == 2) ? fmaxf(r, sh[k][threadIdx.x]) : r + sh[k][threadIdx.x];
+    part[(long long)s * inner + i] = r;
+  }
+}
+
+extern "C" int gg_reduce_ws(int op, const float* x, float* y, int outer, int red, int inner, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  if (op < 0 || op > 2) return fail(GG_ERR_BAD_ARG, "gg_reduce_ws: unknown op%s");
+  if (outer <= 0 || inner <= 0 || red <= 0) return GG_OK;
+  int ctiles = ceil_div(inner, 32);
+  int S = ceil_div(2 * kNumSMs, ctiles);
+  if (S > red / 16) S = red / 16;
+  if (S > 256) S = 256;
+  if (outer != 1 || inner == 1 || S < 2 || workspace == nullptr || workspace_bytes < (size_t)S * inner * sizeof(float))
+    return gg_reduce(op, x, y, outer, red, inner, stream);
+  cudaStream_t st = as_stream(stream);
+  int rows_per = ceil_div(red, S);
+  S = ceil_div(red, rows_per);
+  float* part = reinterpret_cast<float*>(workspace);
+  dim3 block(32, 8);
+  reduce_cols_sliced_kernel<<<dim3(ctiles, S), block, 0, st>>>(op == 1 ? 0 : op, x, part, red, inner, rows_per);
+  int rc = check_launch("gg_reduce_ws/slices");
+  if (rc) return rc;
+  // fold the S partial rows; the mean divides by the true row count
+  reduce_cols_kernel<<<dim3(ctiles, 1), block, 0, st>>>(op == 1 ? 0 : op, part, y, 1, S, inner);
+  rc = check_launch("gg_reduce_ws/fold");
+  if (rc || op != 1) return rc;
+  return gg_unary(GG_U_DIVC, y, y, inner, (float)red, 0.f, stream);
+}
+extern "C" size_t gg_reduce_workspace(int outer, int red, int inner) {
+  if (outer != 1 || inner == 1) return 0;
+  int S = ceil_div(2 * kNumSMs, ceil_div(inner, 32));
+  if (S > 256) S = 256;
+  return (size_t)S * inner * sizeof(float);
+}
+
 extern "C" int gg_reduce(int op, const float* x, float* y, int outer, int red, int inner, void* stream) {
   if (op < 0 || op > 2) return fail(GG_ERR_BAD_ARG, "gg_reduce: unknown op%s");
   if (outer <= 0 || inner <= 0 || red <= 0) return GG_OK;

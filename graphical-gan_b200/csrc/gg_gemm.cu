@@ -6,6 +6,18 @@
 
 using namespace gg;
 
+namespace gg {
+int conv_tc_fwd(const float* x, const float* w, const float* bias, float* y, int B, int H, int W, int Ci, int Co, int k,
+                int stride, int pad_t, int pad_l, int Ho, int Wo, int act, float alpha, void* ws, size_t ws_bytes,
+                cudaStream_t st, bool* handled);
+int conv_tc_dgrad(const float* dy, const float* w, const float* bias, float* dx, int B, int H, int W, int Ci, int Co, int k,
+                  int stride, int pad_t, int pad_l, int Ho, int Wo, int act, float alpha, void* ws, size_t ws_bytes,
+                  cudaStream_t st, bool* handled);
+int conv_tc_wgrad(const float* x, const float* dy, float* dw, int B, int H, int W, int Ci, int Co, int k, int stride,
+                  int pad_t, int pad_l, int Ho, int Wo, void* ws, size_t ws_bytes, cudaStream_t st, bool* handled);
+size_t conv_tc_workspace(int mode, int B, int H, int W, int Ci, int Co, int k, int stride, int Ho, int Wo);
+}  // namespace gg
+
 namespace {
 
 constexpr int TM = 64, TN = 64, TK = 16;
@@ -109,9 +121,21 @@ int choose_splits(int M, int N, int K) {
 
 }  // namespace
 
+// A dense layer is a 1x1 convolution over a 1x1 image: the three products of a Linear layer (y = xW, dx = dy W^T,
+// dW = x^T dy) map onto the fwd / dgrad / wgrad modes of the tcgen05 implicit-GEMM kernel (gg_conv_tc.cu).
+static size_t tc_ws(int M, int N, int K) {
+  size_t a = conv_tc_workspace(0, M, 1, 1, K, N, 1, 1, 1, 1);
+  size_t b = conv_tc_workspace(1, M, 1, 1, N, K, 1, 1, 1, 1);
+  size_t c = conv_tc_workspace(2, K, 1, 1, M, N, 1, 1, 1, 1);
+  size_t m = a > b ? a : b;
+  return m > c ? m : c;
+}
+
 extern "C" size_t gg_gemm_workspace(int M, int N, int K) {
   int s = choose_splits(M, N, K);
-  return s > 1 ? (size_t)s * M * N * sizeof(float) : 0;
+  size_t simt = s > 1 ? (size_t)s * M * N * sizeof(float) : 0;
+  size_t tc = tc_ws(M, N, K);
+  return simt > tc ? simt : tc;
 }
 
 extern "C" int gg_gemm(const float* A, const float* Bm, const float* bias, float* C, int M, int N, int K, int ta, int tb,
@@ -119,6 +143,16 @@ extern "C" int gg_gemm(const float* A, const float* Bm, const float* bias, float
   if (M <= 0 || N <= 0) return GG_OK;
   GG_REQUIRE(K > 0, "gg_gemm");
   cudaStream_t st = as_stream(stream);
+  if (g_conv_backend != 1 && workspace != nullptr) {
+    bool handled = false;
+    int rc = GG_OK;
+    if (!ta && !tb) rc = conv_tc_fwd(A, Bm, bias, C, M, 1, 1, K, N, 1, 1, 0, 0, 1, 1, act, alpha, workspace, workspace_bytes, st, &handled);
+    else if (!ta && tb) rc = conv_tc_dgrad(A, Bm, bias, C, M, 1, 1, N, K, 1, 1, 0, 0, 1, 1, act, alpha, workspace, workspace_bytes, st, &handled);
+    else if (ta && !tb && bias == nullptr && act == GG_ACT_NONE)
+      rc = conv_tc_wgrad(A, Bm, C, K, 1, 1, M, N, 1, 1, 0, 0, 1, 1, workspace, workspace_bytes, st, &handled);
+    if (rc) return rc;
+    if (handled) { g_last_backend = 1; return GG_OK; }
+  }
   int splits = choose_splits(M, N, K);
   if (splits > 1 && (workspace == nullptr || workspace_bytes < (size_t)splits * M * N * sizeof(float))) splits = 1;
   int k_per = ceil_div(ceil_div(K, splits), TK) * TK;

@@ -54,6 +54,8 @@ SIGNATURES = {
     "gg_unary": (c_i, [c_i, c_p, c_p, c_ll, c_f, c_f, c_p]),
     "gg_binary": (c_i, [c_i, c_p, c_p, c_p, C.POINTER(c_i), C.POINTER(c_i), C.POINTER(c_i), c_f, c_p]),
     "gg_reduce": (c_i, [c_i, c_p, c_p, c_i, c_i, c_i, c_p]),
+    "gg_reduce_ws": (c_i, [c_i, c_p, c_p, c_i, c_i, c_i, c_p, c_sz, c_p]),
+    "gg_reduce_workspace": (c_sz, [c_i, c_i, c_i]),
     "gg_softmax_fwd": (c_i, [c_p, c_p, c_i, c_i, c_p]),
     "gg_softmax_bwd": (c_i, [c_p, c_p, c_p, c_i, c_i, c_p]),
     "gg_transpose_b2d": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p]),
@@ -77,6 +79,7 @@ SIGNATURES = {
     "gg_rng_normal": (c_i, [c_p, c_ll, c_f, c_f, C.c_uint64, C.c_uint32, c_p, c_p]),
     "gg_rng_uniform": (c_i, [c_p, c_ll, c_f, c_f, C.c_uint64, C.c_uint32, c_p, c_p]),
     "gg_rng_categorical": (c_i, [c_p, c_i, c_p, c_i, C.c_uint64, C.c_uint32, c_p, c_p]),
+    "gg_debug_set_buffer": (c_i, [c_p]),
     "gg_probe_tma_strided": (c_i, [c_p] + [c_i] * 11 + [c_p, c_p]),
     "gg_probe_umma_tf32": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
 }

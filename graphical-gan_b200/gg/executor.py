@@ -322,7 +322,14 @@ class Plan(object):
         axes = node.attrs["axes"]
         outer, red, inner = prod(shp[:axes[0]]), prod(shp[axes[0]:axes[-1] + 1]), prod(shp[axes[-1] + 1:])
         code, xp, yp = cabi.REDUCE[node.attrs["fn"]], x.data_ptr(), y.data_ptr()
-        self.steps.append(lambda st: cabi.call("gg_reduce", code, xp, yp, outer, red, inner, st))
+        need = cabi.lib.gg_reduce_workspace(outer, red, inner)
+        if need and red >= 256:
+            ws = self._ws(need)
+            self.keep.append(ws)
+            wp, wn = ws.data_ptr(), ws.numel()
+            self.steps.append(lambda st: cabi.call("gg_reduce_ws", code, xp, yp, outer, red, inner, wp, wn, st))
+        else:
+            self.steps.append(lambda st: cabi.call("gg_reduce", code, xp, yp, outer, red, inner, st))
 
     def _emit_softmax(self, node):
         x, y = self._in(node, 0), self._alloc(node)

@@ -166,6 +166,10 @@ int gg_binary(int op, const float* a, const float* b, float* out,
 
 /* y[o,i] = reduce_r x[o,r,i]; op 0 sum, 1 mean, 2 max */
 int gg_reduce(int op, const float* x, float* y, int outer, int red, int inner, void* stream);
+/* same, with a scratch buffer (gg_reduce_workspace bytes) that lets tall column reductions (bias gradients) use all SMs */
+int gg_reduce_ws(int op, const float* x, float* y, int outer, int red, int inner, void* workspace, size_t workspace_bytes,
+                 void* stream);
+size_t gg_reduce_workspace(int outer, int red, int inner);
 /* row-wise softmax of x[R,C] and its backward dx = y*(dy - sum(dy*y)) */
 int gg_softmax_fwd(const float* x, float* y, int R, int C, void* stream);
 int gg_softmax_bwd(const float* y, const float* dy, float* dx, int R, int C, void* stream);
@@ -236,6 +240,11 @@ int gg_probe_tma_strided(const float* x, int B, int H, int W, int C, int b, int 
  * (stored [K,128]) and B K-major (stored [N,K]) or MN-major (stored [K,N]); K multiple of 32, N multiple of 32 <= 256 */
 int gg_probe_umma_tf32(const float* A, const float* Bm, float* D, int N, int K, int a_mn_major, int b_mn_major,
                        int tma_tf32_convert, void* stream);
+
+/* development aid: when set to a device buffer of >= 256 int64, CTA (0,0) of every tensor-core conv launch writes a
+ * %globaltimer timeline (slot 0 start, 1+i TMA issue of k-block i, 64+i operands landed, 128 accumulator ready,
+ * 129 partial written, 131 epilogue done).  NULL disables it. */
+int gg_debug_set_buffer(void* device_buffer_256_int64);
 
 #ifdef __cplusplus
 }
