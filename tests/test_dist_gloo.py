@@ -51,7 +51,7 @@ WORKER = textwrap.dedent('''
     except ValueError:
         pass
     torch.distributed.barrier()
-    sys.stdout.write("rank%d-ok\n" % rank)
+    print("rank" + str(rank) + "-ok", flush=True)
 ''') % ROOT
 
 
