@@ -496,7 +496,7 @@ class Plan(object):
             self.keep.append(folded)
             fp = folded.data_ptr()
             self.steps.append(lambda st: cabi.call("gg_bn_fold_partials", pp, S, fp, Cc, st))
-            self.steps.append(lambda st: ggdist.all_reduce_sum(folded))
+            self.steps.append(self._collective(lambda st: ggdist.all_reduce_sum(folded)))
             cnt = float(R * world)
             self.steps.append(lambda st: cabi.call("gg_bn_apply", xp, fp, 1, cnt, gp, bp, eps, yp, mp, rp, R, Cc, act, alpha, st))
         else:
@@ -524,7 +524,7 @@ class Plan(object):
             self.keep.append(glob)
             glp = glob.data_ptr()
             self.steps.append(lambda st: cabi.call("gg_unary", cabi.UNARY["copy"], dgbp, glp, 2 * Cc, 0.0, 0.0, st))
-            self.steps.append(lambda st: ggdist.all_reduce_sum(glob))
+            self.steps.append(self._collective(lambda st: ggdist.all_reduce_sum(glob)))
             cnt = float(R * world)
             self.steps.append(lambda st: cabi.call("gg_bn_bwd_apply", gyp, xp, yp, mp, rp, gp, None, glp, 1, cnt, dxp, None, None,
                                                    R, Cc, act, alpha, st))
@@ -585,9 +585,9 @@ class Plan(object):
             offs_d = torch.from_numpy(offs[:-1].copy()).to(rt.dev())
             adam_tab = table([flat.data_ptr() + int(o) * 4 for o in offs[:-1]])
             self.keep += [flat, offs_d, adam_tab]
-            tp, cp, op_, fp = tab.data_ptr(), chk.data_ptr(), offs_d.data_ptr(), flat.data_ptr()
-            self.steps.append(lambda st: cabi.call("gg_pack_grads", tp, cp, n_chunks, op_, fp, 1, st))
-            self.steps.append(lambda st: ggdist.all_reduce_sum(flat))
+            ptab, pchk, poff, pflat = tab.data_ptr(), chk.data_ptr(), offs_d.data_ptr(), flat.data_ptr()
+            self.steps.append(lambda st: cabi.call("gg_pack_grads", ptab, pchk, n_chunks, poff, pflat, 1, st))
+            self.steps.append(self._collective(lambda st: ggdist.all_reduce_sum(flat)))
             gscale = 1.0 / world
         tp, cp, sp = adam_tab.data_ptr(), chk.data_ptr(), state.data_ptr()
         a = op.attrs
@@ -599,10 +599,46 @@ class Plan(object):
             self.steps.append(lambda st: cabi.call("gg_rmsprop_multi", tp, cp, n_chunks, lr, decay, eps, gscale, st))
 
     # ---- execution ------------------------------------------------------------------------------
+    @staticmethod
+    def _collective(fn):
+        """tag a step as a cross-rank collective: it runs eagerly BETWEEN captured CUDA-graph segments (NCCL stays
+        outside stream capture; the kernels on either side of the exchange are still one graph launch each)"""
+        fn.is_collective = True
+        return fn
+
     def _launch_all(self):
         st = cabi.stream_ptr()
         for f in self.steps:
             f(st)
+
+    def _capture_segments(self):
+        torch = _torch()
+        segments, cur = [], []
+        for f in self.steps:
+            if getattr(f, "is_collective", False):
+                if cur:
+                    segments.append(cur)
+                    cur = []
+                segments.append(f)
+            else:
+                cur.append(f)
+        if cur:
+            segments.append(cur)
+        out = []
+        torch.cuda.synchronize()
+        before = cabi.lib.gg_launch_count()
+        for seg in segments:
+            if callable(seg):
+                out.append(seg)
+                continue
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                st = cabi.stream_ptr()
+                for f in seg:
+                    f(st)
+            out.append(g)
+        self.kernel_launches = cabi.lib.gg_launch_count() - before
+        return out
 
     def run(self, feed_dict, to_host=True):
         torch = _torch()
@@ -620,14 +656,14 @@ class Plan(object):
         if self.rt.use_cuda_graph:
             if self.graph is None:
                 # capture without executing: no side effect (Adam / RNG tick) happens until the first replay
-                torch.cuda.synchronize()
-                g = torch.cuda.CUDAGraph()
-                before = cabi.lib.gg_launch_count()
-                with torch.cuda.graph(g):
-                    self._launch_all()
-                self.kernel_launches = cabi.lib.gg_launch_count() - before
-                self.graph = g
-            self.graph.replay()
+                self.graph = self._capture_segments()
+            st = None
+            for seg in self.graph:
+                if callable(seg):
+                    st = st or cabi.stream_ptr()
+                    seg(st)
+                else:
+                    seg.replay()
         else:
             before = cabi.lib.gg_launch_count()
             self._launch_all()

@@ -33,6 +33,7 @@ local = args.global_batch // world
 g = S.build_graph(BATCH_SIZE=local)
 sess = tf.Session()
 costs = []
+snap = {}
 for step, (cost, op) in enumerate(((g.disc_cost, g.disc_train_op), (g.gen_cost, g.gen_train_op), (g.disc_cost, g.disc_train_op))):
     inp = OM.synthetic_inputs(args.global_batch, step)
     lo, hi = ggdist.shard_bounds(args.global_batch, rank, world)
@@ -43,10 +44,13 @@ for step, (cost, op) in enumerate(((g.disc_cost, g.disc_train_op), (g.gen_cost, 
     if world > 1:
         torch.distributed.all_reduce(t)
     costs.append(float(t) / world)               # mean of equal-sized shard means == global mean
+    from gg.executor import RT as _RT
+    for n_ in ('Discriminator.zx1.W', 'Discriminator.2.Filters', 'Generator.3.Filters', 'Generator.BN2.scale'):
+        snap['s%d_%s' % (step, n_.replace('.', '_'))] = _RT.get_param(lib._params[n_]).reshape(-1)[:4096].copy()
 from gg.executor import RT
 names = ['Discriminator.2.Filters', 'Discriminator.zx1.W', 'Generator.3.Filters', 'Generator.BN2.scale', 'Extractor.BN3.offset',
          'Generator.Hyper.Mu', 'Extractor.Output.W']
-params = {n: RT.get_param(lib._params[n]) for n in names}
+params = {n: RT.get_param(lib._params[n]).reshape(-1)[:65536] for n in names}
 if world > 1:
     # every rank must hold identical parameters after the all-reduced update
     for n in names:
@@ -56,7 +60,7 @@ if world > 1:
         torch.distributed.all_reduce(hi_, op=torch.distributed.ReduceOp.MAX)
         assert torch.equal(lo_, hi_), "parameter %s diverged across ranks" % n
 if rank == 0:
-    np.savez(args.out, costs=np.array(costs), **{n.replace('.', '_'): v for n, v in params.items()})
+    np.savez(args.out, costs=np.array(costs), **snap, **{n.replace('.', '_'): v for n, v in params.items()})
     print("dp_check world=%d costs=%s" % (world, costs))
 if world > 1:
     torch.distributed.barrier()
