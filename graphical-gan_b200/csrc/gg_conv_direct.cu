@@ -10,12 +10,12 @@ using namespace gg;
 namespace gg {
 int conv_tc_fwd(const float* x, const float* w, const float* bias, float* y, int B, int H, int W, int Ci, int Co, int k,
                 int stride, int pad_t, int pad_l, int Ho, int Wo, int act, float alpha, void* ws, size_t ws_bytes,
-                cudaStream_t st, bool* handled);
+                cudaStream_t st, bool* handled, int filt_rows = 0);
 int conv_tc_dgrad(const float* dy, const float* w, const float* bias, float* dx, int B, int H, int W, int Ci, int Co, int k,
                   int stride, int pad_t, int pad_l, int Ho, int Wo, int act, float alpha, void* ws, size_t ws_bytes,
-                  cudaStream_t st, bool* handled);
+                  cudaStream_t st, bool* handled, int filt_rows = 0);
 int conv_tc_wgrad(const float* x, const float* dy, float* dw, int B, int H, int W, int Ci, int Co, int k, int stride,
-                  int pad_t, int pad_l, int Ho, int Wo, void* ws, size_t ws_bytes, cudaStream_t st, bool* handled);
+                  int pad_t, int pad_l, int Ho, int Wo, void* ws, size_t ws_bytes, cudaStream_t st, bool* handled, int out_rows = 0);
 size_t conv_tc_wgrad_workspace(int B, int H, int W, int Ci, int Co, int k, int stride, int Ho, int Wo);
 size_t conv_tc_workspace(int mode, int B, int H, int W, int Ci, int Co, int k, int stride, int Ho, int Wo);
 void conv_tc_set_debug(void* p);
@@ -203,6 +203,98 @@ __global__ void __launch_bounds__(256) sum_slices_kernel(const float* __restrict
   out[i] = a;
 }
 
+
+// ---- 3-channel (Cin <= 4) layers on the tensor cores ----------------------------------------------------------------
+// The first conv of every net (Cin = 1 or 3) and the last deconv (Cout = 1 or 3) have K = k*k*Cin = 25..100: too thin for
+// a per-tap implicit GEMM (a 32-channel K block would be 90 % padding).  For these layers only, the patch matrix
+// P[B*Ho*Wo, Kp] (Kp = k*k*Cin rounded up to 32; 6 MB at B=64) is materialised by one coalesced kernel and the three
+// products run as plain GEMMs on the tcgen05 kernel:  y = P W,  dW = P^T dy,  dP = dy W^T followed by a col2im gather.
+// The filter matrix is read in place: its rows beyond k*k*Cin are TMA out-of-bounds zeros.
+__global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x, float* __restrict__ P, ConvP p, int Kp) {
+  const int kv = Kp / 4;
+  const long long total = (long long)p.B * p.Ho * p.Wo * kv;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int j4 = (int)(t % kv);
+  long long m = t / kv;
+  const int wo = (int)(m % p.Wo);
+  const int ho = (int)((m / p.Wo) % p.Ho);
+  const int b = (int)(m / ((long long)p.Wo * p.Ho));
+  const int kreal = p.k * p.k * p.Ci;
+  float v[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int kk = j4 * 4 + e;
+    float val = 0.f;
+    if (kk < kreal) {
+      const int tap = kk / p.Ci, c = kk - tap * p.Ci;
+      const int r = tap / p.k, s = tap - r * p.k;
+      const int hi = ho * p.stride + r - p.pad_t, wi = wo * p.stride + s - p.pad_l;
+      if (hi >= 0 && hi < p.H && wi >= 0 && wi < p.W) val = x[((long long)(b * p.H + hi) * p.W + wi) * p.Ci + c];
+    }
+    v[e] = val;
+  }
+  *reinterpret_cast<float4*>(P + m * Kp + j4 * 4) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+__global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ dP, const float* __restrict__ bias,
+                                                     float* __restrict__ dx, ConvP p, int Kp, int act, float alpha) {
+  const long long total = (long long)p.B * p.H * p.W * p.Ci;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int c = (int)(t % p.Ci);
+  long long q = t / p.Ci;
+  const int w = (int)(q % p.W);
+  const int h = (int)((q / p.W) % p.H);
+  const int b = (int)(q / ((long long)p.W * p.H));
+  float acc = 0.f;
+  for (int r = 0; r < p.k; ++r) {
+    const int hn = h + p.pad_t - r;
+    if (hn < 0 || hn % p.stride) continue;
+    const int ho = hn / p.stride;
+    if (ho >= p.Ho) continue;
+    for (int s = 0; s < p.k; ++s) {
+      const int wn = w + p.pad_l - s;
+      if (wn < 0 || wn % p.stride) continue;
+      const int wo = wn / p.stride;
+      if (wo >= p.Wo) continue;
+      acc += dP[((long long)(b * p.Ho + ho) * p.Wo + wo) * Kp + (r * p.k + s) * p.Ci + c];
+    }
+  }
+  if (bias) acc += bias[c];
+  dx[t] = apply_act(acc, act, alpha);
+}
+
+struct SmallCi {
+  bool ok;
+  int Kp;
+  long long M;
+  size_t tc_bytes, p_bytes;
+};
+
+SmallCi smallci_plan(int mode, const ConvP& p) {
+  SmallCi sc{};
+  sc.ok = false;
+  if (g_conv_backend == 1) return sc;
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("GG_IM2COL"); enabled = (e && e[0] == '0') ? 0 : 1; }
+  if (!enabled) return sc;
+  if (p.Ci > 4 || p.Co % 32 != 0) return sc;
+  sc.Kp = ((p.k * p.k * p.Ci + 31) / 32) * 32;
+  if (sc.Kp > 128) return sc;
+  sc.M = (long long)p.B * p.Ho * p.Wo;
+  if (sc.M % 32 != 0 || sc.M > (1 << 24)) return sc;
+  size_t tc;
+  if (mode == 0) tc = conv_tc_workspace(0, (int)sc.M, 1, 1, sc.Kp, p.Co, 1, 1, 1, 1);
+  else if (mode == 1) tc = conv_tc_workspace(1, (int)sc.M, 1, 1, sc.Kp, p.Co, 1, 1, 1, 1);
+  else tc = conv_tc_workspace(2, (int)sc.M, 1, 1, sc.Kp, p.Co, 1, 1, 1, 1);
+  if (tc == 0) return sc;
+  sc.tc_bytes = (tc + 255) & ~size_t(255);
+  sc.p_bytes = (size_t)sc.M * sc.Kp * sizeof(float);
+  sc.ok = true;
+  return sc;
+}
+
 int direct_wgrad_slices(const ConvP& p) {
   long long threads = (long long)p.k * p.k * p.Ci * ((p.Co + 3) / 4);
   int blocks = ceil_div(threads, 128);
@@ -232,6 +324,21 @@ extern "C" int gg_conv2d_fwd(const float* x, const float* w, const float* bias, 
   int rc = check_geom(p, "gg_conv2d_fwd");
   if (rc) return rc;
   cudaStream_t st = as_stream(stream);
+  {
+    SmallCi sc = smallci_plan(0, p);
+    if (sc.ok && workspace != nullptr && workspace_bytes >= sc.tc_bytes + sc.p_bytes) {
+      float* P = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + sc.tc_bytes);
+      const long long total = sc.M * (sc.Kp / 4);
+      im2col_kernel<<<ceil_div(total, 256), 256, 0, st>>>(x, P, p, sc.Kp);
+      rc = check_launch("gg_conv2d_fwd/im2col");
+      if (rc) return rc;
+      bool handled = false;
+      rc = conv_tc_fwd(P, w, bias, y, (int)sc.M, 1, 1, sc.Kp, Co, 1, 1, 0, 0, 1, 1, act, alpha, workspace, sc.tc_bytes, st,
+                       &handled, k * k * Ci);
+      if (rc) return rc;
+      if (handled) { g_last_backend = 1; return GG_OK; }
+    }
+  }
   if (g_conv_backend != 1) {
     bool handled = false;
     rc = conv_tc_fwd(x, w, bias, y, B, H, W, Ci, Co, k, stride, pad_t, pad_l, Ho, Wo, act, alpha, workspace, workspace_bytes,
@@ -258,6 +365,22 @@ extern "C" int gg_conv2d_dgrad(const float* dy, const float* w, const float* bia
   int rc = check_geom(p, "gg_conv2d_dgrad");
   if (rc) return rc;
   cudaStream_t st = as_stream(stream);
+  {
+    SmallCi sc = smallci_plan(1, p);
+    if (sc.ok && workspace != nullptr && workspace_bytes >= sc.tc_bytes + sc.p_bytes) {
+      float* dP = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + sc.tc_bytes);
+      bool handled = false;
+      rc = conv_tc_dgrad(dy, w, nullptr, dP, (int)sc.M, 1, 1, sc.Kp, Co, 1, 1, 0, 0, 1, 1, GG_ACT_NONE, 0.f, workspace,
+                         sc.tc_bytes, st, &handled, k * k * Ci);
+      if (rc) return rc;
+      if (handled) {
+        const long long total = (long long)B * H * W * Ci;
+        col2im_kernel<<<ceil_div(total, 256), 256, 0, st>>>(dP, bias, dx, p, sc.Kp, act, alpha);
+        g_last_backend = 1;
+        return check_launch("gg_conv2d_dgrad/col2im");
+      }
+    }
+  }
   if (g_conv_backend != 1) {
     bool handled = false;
     rc = conv_tc_dgrad(dy, w, bias, dx, B, H, W, Ci, Co, k, stride, pad_t, pad_l, Ho, Wo, act, alpha, workspace,
@@ -281,6 +404,8 @@ extern "C" size_t gg_conv2d_wgrad_workspace(int B, int H, int W, int Ci, int Co,
   ConvP p{B, H, W, Ci, Co, k, stride, 0, 0, Ho, Wo};
   size_t direct = (size_t)direct_wgrad_slices(p) * k * k * Ci * Co * sizeof(float);
   size_t tc = conv_tc_wgrad_workspace(B, H, W, Ci, Co, k, stride, Ho, Wo);
+  SmallCi sc = smallci_plan(2, p);
+  if (sc.ok && sc.tc_bytes + sc.p_bytes > tc) tc = sc.tc_bytes + sc.p_bytes;
   return direct > tc ? direct : tc;
 }
 
@@ -292,6 +417,9 @@ extern "C" int gg_debug_set_buffer(void* device_buffer_256_int64) {
 extern "C" size_t gg_conv2d_workspace(int mode, int B, int H, int W, int Ci, int Co, int k, int stride, int Ho, int Wo) {
   if (mode == 2) return gg_conv2d_wgrad_workspace(B, H, W, Ci, Co, k, stride, Ho, Wo);
   size_t tc = conv_tc_workspace(mode, B, H, W, Ci, Co, k, stride, Ho, Wo);
+  ConvP p{B, H, W, Ci, Co, k, stride, 0, 0, Ho, Wo};
+  SmallCi sc = smallci_plan(mode, p);
+  if (sc.ok && sc.tc_bytes + sc.p_bytes > tc) tc = sc.tc_bytes + sc.p_bytes;
   return tc > 256 ? tc : 256;
 }
 
@@ -302,6 +430,21 @@ extern "C" int gg_conv2d_wgrad(const float* x, const float* dy, float* dw, int B
   int rc = check_geom(p, "gg_conv2d_wgrad");
   if (rc) return rc;
   cudaStream_t st = as_stream(stream);
+  {
+    SmallCi sc = smallci_plan(2, p);
+    if (sc.ok && workspace != nullptr && workspace_bytes >= sc.tc_bytes + sc.p_bytes) {
+      float* P = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + sc.tc_bytes);
+      const long long total = sc.M * (sc.Kp / 4);
+      im2col_kernel<<<ceil_div(total, 256), 256, 0, st>>>(x, P, p, sc.Kp);
+      rc = check_launch("gg_conv2d_wgrad/im2col");
+      if (rc) return rc;
+      bool handled = false;
+      rc = conv_tc_wgrad(P, dy, dw, (int)sc.M, 1, 1, sc.Kp, Co, 1, 1, 0, 0, 1, 1, workspace, sc.tc_bytes, st, &handled,
+                         k * k * Ci);
+      if (rc) return rc;
+      if (handled) { g_last_backend = 1; return GG_OK; }
+    }
+  }
   if (g_conv_backend != 1) {
     bool handled = false;
     rc = conv_tc_wgrad(x, dy, dw, B, H, W, Ci, Co, k, stride, pad_t, pad_l, Ho, Wo, workspace, workspace_bytes, st, &handled);

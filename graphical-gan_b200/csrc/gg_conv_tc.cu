@@ -48,6 +48,7 @@ struct TcParams {
   float* partial;             // [splits][tiles][128][n_tile]
   unsigned* counters;         // [tiles], zero on entry, left zero
   long long* dbg;             // optional timeline of CTA (0,0): see gg_debug_set_buffer
+  int out_rows;               // wgrad: rows of the [taps*Ci, Co] result that exist in memory (im2col-padded K)
 };
 
 __device__ __forceinline__ long long gtime() {
@@ -237,7 +238,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       orow = p.out + ((size_t)(((size_t)(b0 + bi) * p.H + hh) * p.W + ww)) * p.Ci + n0;
     } else {
       const int row = mt * 128 + m;
-      valid = row < taps * p.Ci;
+      valid = row < p.out_rows;
       orow = p.out + (size_t)row * p.Co + n0;
     }
     const uint32_t taddr = tmem_d + ((uint32_t)(quad * 32) << 16);
@@ -556,14 +557,16 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, TcPlan& pl, void* ws,
 // filter tensor map: w [taps][Ci][Co] viewed as dims (Co, Ci, taps)
 // MN-major B stage in ONE TMA: Co is split into (32 co, Co/32 blocks) so the box (32 co, 32 ci, n_tile/32 blocks, 1 tap)
 // lands as [co block][ci][32 co] = n_tile/32 swizzle atoms of 4 KB, LBO = 4096
-int filter_map_mn(CUtensorMap* tm, const float* w, int Ci, int Co, int taps, int n_tile) {
-  uint64_t dims[4] = {32, (uint64_t)Ci, (uint64_t)(Co / 32), (uint64_t)taps};
+int filter_map_mn(CUtensorMap* tm, const float* w, int Ci, int Co, int taps, int n_tile, int rows_valid = 0) {
+  // rows_valid < Ci: the filter matrix in memory has fewer rows than the (im2col-padded) K the kernel walks; the
+  // missing rows are TMA out-of-bounds = zeros
+  uint64_t dims[4] = {32, (uint64_t)(rows_valid ? rows_valid : Ci), (uint64_t)(Co / 32), (uint64_t)taps};
   uint64_t str[4] = {1, (uint64_t)Co, 32, (uint64_t)Ci * Co};
   uint32_t box[4] = {32, 32, (uint32_t)(n_tile / 32), 1};
   return encode_tmap(tm, w, 4, dims, str, box, nullptr, 2, env_int("GG_TC_NOCVT", 0) == 0);
 }
-int filter_map_k(CUtensorMap* tm, const float* w, int Ci, int Co, int taps, int n_tile) {  // 32 co x n_tile ci rows, K-major
-  uint64_t dims[3] = {(uint64_t)Co, (uint64_t)Ci, (uint64_t)taps};
+int filter_map_k(CUtensorMap* tm, const float* w, int Ci, int Co, int taps, int n_tile, int rows_valid = 0) {  // 32 co x n_tile ci rows, K-major
+  uint64_t dims[3] = {(uint64_t)Co, (uint64_t)(rows_valid ? rows_valid : Ci), (uint64_t)taps};
   uint64_t str[3] = {1, (uint64_t)Co, (uint64_t)Ci * Co};
   uint32_t box[3] = {32, (uint32_t)n_tile, 1};
   return encode_tmap(tm, w, 3, dims, str, box, nullptr, 1, env_int("GG_TC_NOCVT", 0) == 0);
@@ -581,7 +584,7 @@ int act_map(CUtensorMap* tm, const float* x, int B, int H, int W, int C, int wt,
 
 int conv_tc_fwd(const float* x, const float* w, const float* bias, float* y, int B, int H, int W, int Ci, int Co, int k,
                 int stride, int pad_t, int pad_l, int Ho, int Wo, int act, float alpha, void* ws, size_t ws_bytes,
-                cudaStream_t st, bool* handled) {
+                cudaStream_t st, bool* handled, int filt_rows) {
   *handled = false;
   TcPlan pl = make_plan(0, B, H, W, Ci, Co, k, stride, pad_t, pad_l, Ho, Wo);
   if (!pl.ok) return GG_OK;
@@ -589,7 +592,7 @@ int conv_tc_fwd(const float* x, const float* w, const float* bias, float* y, int
   CUtensorMap tmA, tmB;
   int rc = act_map(&tmA, x, B, H, W, Ci, pl.p.wt, pl.p.ht, pl.p.bt, stride, 1);
   if (rc) return rc;
-  rc = filter_map_mn(&tmB, w, Ci, Co, k * k, pl.p.n_tile);
+  rc = filter_map_mn(&tmB, w, Ci, Co, k * k, pl.p.n_tile, filt_rows);
   if (rc) return rc;
   pl.p.out = y; pl.p.bias = bias; pl.p.act = act; pl.p.alpha = alpha;
   rc = launch<0>(tmA, tmB, pl, ws, ws_bytes, st);
@@ -600,7 +603,7 @@ int conv_tc_fwd(const float* x, const float* w, const float* bias, float* y, int
 
 int conv_tc_dgrad(const float* dy, const float* w, const float* bias, float* dx, int B, int H, int W, int Ci, int Co, int k,
                   int stride, int pad_t, int pad_l, int Ho, int Wo, int act, float alpha, void* ws, size_t ws_bytes,
-                  cudaStream_t st, bool* handled) {
+                  cudaStream_t st, bool* handled, int filt_rows) {
   *handled = false;
   TcPlan pl = make_plan(1, B, H, W, Ci, Co, k, stride, pad_t, pad_l, Ho, Wo);
   if (!pl.ok) return GG_OK;
@@ -608,7 +611,7 @@ int conv_tc_dgrad(const float* dy, const float* w, const float* bias, float* dx,
   CUtensorMap tmA, tmB;
   int rc = act_map(&tmA, dy, B, Ho, Wo, Co, pl.p.wt, pl.p.ht, pl.p.bt, 1, 1);
   if (rc) return rc;
-  rc = filter_map_k(&tmB, w, Ci, Co, k * k, pl.p.n_tile);
+  rc = filter_map_k(&tmB, w, Ci, Co, k * k, pl.p.n_tile, filt_rows);
   if (rc) return rc;
   pl.p.out = dx; pl.p.bias = bias; pl.p.act = act; pl.p.alpha = alpha;
   rc = launch<1>(tmA, tmB, pl, ws, ws_bytes, st);
@@ -618,9 +621,10 @@ int conv_tc_dgrad(const float* dy, const float* w, const float* bias, float* dx,
 }
 
 int conv_tc_wgrad(const float* x, const float* dy, float* dw, int B, int H, int W, int Ci, int Co, int k, int stride,
-                  int pad_t, int pad_l, int Ho, int Wo, void* ws, size_t ws_bytes, cudaStream_t st, bool* handled) {
+                  int pad_t, int pad_l, int Ho, int Wo, void* ws, size_t ws_bytes, cudaStream_t st, bool* handled, int out_rows) {
   *handled = false;
   TcPlan pl = make_plan(2, B, H, W, Ci, Co, k, stride, pad_t, pad_l, Ho, Wo);
+  pl.p.out_rows = out_rows ? out_rows : k * k * Ci;
   if (!pl.ok) return GG_OK;
   if (ws == nullptr || ws_bytes < pl.counter_bytes) return GG_OK;
   CUtensorMap tmA, tmB;
