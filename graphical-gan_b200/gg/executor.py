@@ -163,17 +163,41 @@ class Plan(object):
             elif isinstance(f, Tensor):
                 roots.append(f)
         self.order = self._toposort(roots)
+        # scheduling metadata: one group per node that launches kernels; `owner` resolves views (reshape / aux / fed)
+        # to the node whose kernels produce the storage
+        self.groups = []     # dicts: start, end, reads (owner ids), writes (owner id), barrier
+        self.owner = {}
+        if any(n.op == "random" and n.id not in self.fed for n in self.order):
+            self.has_random = True
+            tick = rt.tick()
+            self.steps.append(lambda st, tick=tick: cabi.call("gg_rng_tick", tick.data_ptr(), st))
+            self.groups.append(dict(start=0, end=1, reads=set(), writes="tick", barrier=False))
         for node in self.order:
+            s0 = len(self.steps)
             self._emit(node)
+            self._note_group(node, s0)
         for f in fetches:
             if isinstance(f, Operation):
+                s0 = len(self.steps)
                 self._emit_operation(f)
-        if self.has_random:
-            tick = rt.tick()
-            self.steps.insert(0, lambda st, tick=tick: cabi.call("gg_rng_tick", tick.data_ptr(), st))
+                if len(self.steps) > s0:
+                    self.groups.append(dict(start=s0, end=len(self.steps), reads=set(), writes="op%d" % f.id, barrier=True))
         self.graph = None
         self.kernel_launches = 0   # libgg_b200 kernels per run (counted at capture / eager launch)
         self.runs = 0
+
+    def _note_group(self, node, s0):
+        if len(self.steps) == s0:        # no kernels: a view or a leaf
+            if node.inputs and node.op in ALIAS_OPS and node.id not in self.fed:
+                self.owner[node.id] = self.owner.get(node.inputs[0].id, node.inputs[0].id)
+            else:
+                self.owner[node.id] = node.id
+            return
+        self.owner[node.id] = node.id
+        reads = set(self.owner.get(i.id, i.id) for i in node.inputs)
+        if node.op == "random":
+            reads.add("tick")
+        self.groups.append(dict(start=s0, end=len(self.steps), reads=reads, writes=node.id, barrier=False))
 
     # ---- graph walking ---------------------------------------------------------------------
     def _op_roots(self, op):
@@ -611,8 +635,74 @@ class Plan(object):
         for f in self.steps:
             f(st)
 
+    def _schedule(self, n_streams):
+        """static list scheduling of the kernel groups onto `n_streams` streams: a group continues the stream of its
+        most recent producer when that producer is still the stream's tail, otherwise it takes the least recently used
+        stream; cross-stream dependencies become event waits.  Independent branches of the step (E(real) vs G(p_z),
+        the two discriminator applications, every wgrad / bias-gradient leaf vs the dgrad chain) then overlap inside the
+        captured CUDA graph — most kernels of this workload are latency-bound and fill a fraction of the 148 SMs."""
+        producer, assign, waits, need_event = {}, [], [], set()
+        tail = [None] * n_streams
+        last_barrier = None
+        for gi, g in enumerate(self.groups):
+            deps = set(producer[o] for o in g["reads"] if o in producer)
+            if last_barrier is not None:
+                deps.add(last_barrier)
+            if g["barrier"]:
+                deps |= set(t for t in tail if t is not None)
+            cand = [s for s in range(n_streams) if tail[s] is not None and tail[s] in deps]
+            if cand:
+                s = max(cand, key=lambda q: tail[q])
+            else:
+                free = [q for q in range(n_streams) if tail[q] is None]
+                s = free[0] if free else min(range(n_streams), key=lambda q: tail[q])
+            w = sorted(d for d in deps if assign[d] != s)
+            need_event.update(w)
+            assign.append(s)
+            waits.append(w)
+            tail[s] = gi
+            producer[g["writes"]] = gi
+            if g["barrier"]:
+                last_barrier = gi
+        return assign, waits, need_event
+
+    def _capture_multi_stream(self, n_streams):
+        torch = _torch()
+        assign, waits, need_event = self._schedule(n_streams)
+        torch.cuda.synchronize()
+        before = cabi.lib.gg_launch_count()
+        g = torch.cuda.CUDAGraph()
+        side = [torch.cuda.Stream() for _ in range(n_streams - 1)]
+        self.keep.append(side)
+        with torch.cuda.graph(g):
+            cs = torch.cuda.current_stream()
+            streams = [cs] + side
+            for sd in side:
+                sd.wait_stream(cs)
+            events = {}
+            for gi, grp in enumerate(self.groups):
+                st = streams[assign[gi]]
+                for d in waits[gi]:
+                    st.wait_event(events[d])
+                sp = st.cuda_stream
+                for f in self.steps[grp["start"]:grp["end"]]:
+                    f(sp)
+                if gi in need_event:
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                    events[gi] = ev
+            for sd in side:
+                cs.wait_stream(sd)
+            self.keep.append(events)
+        self.kernel_launches = cabi.lib.gg_launch_count() - before
+        self.streams_used = len(set(assign))
+        return [g]
+
     def _capture_segments(self):
         torch = _torch()
+        n_streams = int(os.environ.get("GG_STREAMS", "4"))
+        if n_streams > 1 and not any(getattr(f, "is_collective", False) for f in self.steps):
+            return self._capture_multi_stream(n_streams)
         segments, cur = [], []
         for f in self.steps:
             if getattr(f, "is_collective", False):

@@ -365,12 +365,13 @@ def reduce(fn, x, axes=None, keepdims=False):
             groups.append([a])
     out = x
     total = prod(x.shape[a] for a in axes)
+    fused_mean = fn == "mean" and len(groups) == 1      # one kernel: sum and divide by the row count
     for g in reversed(groups):
         shape = list(out.shape)
         kept = shape[:g[0]] + [1] * len(g) + shape[g[-1] + 1:]
-        sub_fn = "sum" if fn == "mean" else fn
+        sub_fn = "mean" if fused_mean else ("sum" if fn == "mean" else fn)
         out = Tensor("reduce", (out,), {"fn": sub_fn, "axes": tuple(g)}, kept, float32)
-    if fn == "mean":
+    if fn == "mean" and not fused_mean:
         out = unary("divc", out, float(total))
     if not keepdims:
         out = reshape(out, [s for a, s in enumerate(x.shape) if a not in axes])
@@ -567,6 +568,9 @@ def _grad_reduce(n, g, need):
     fn = n.attrs["fn"]
     if fn == "sum":
         return [broadcast_to(g, x.shape)]
+    if fn == "mean":
+        count = prod(x.shape[a] for a in n.attrs["axes"])
+        return [broadcast_to(div(g, float(count)), x.shape)]
     if fn == "max":
         m = binary("ge_mask", x, broadcast_to(n, x.shape))
         return [mul(broadcast_to(g, x.shape), m)]
