@@ -9,6 +9,7 @@ mkdir -p "$OUT" "$OBJ"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=default --use_fast_math=false)
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC)
 [ "${GG_PTXAS_V:-0}" = "1" ] && FLAGS+=(-Xptxas -v)
+[ -n "${GG_EXTRA_FLAGS:-}" ] && FLAGS+=(${GG_EXTRA_FLAGS})
 pids=()
 objs=()
 for src in "$HERE"/csrc/*.cu; do

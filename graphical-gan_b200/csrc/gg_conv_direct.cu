@@ -19,6 +19,7 @@ int conv_tc_wgrad(const float* x, const float* dy, float* dw, int B, int H, int 
 size_t conv_tc_wgrad_workspace(int B, int H, int W, int Ci, int Co, int k, int stride, int Ho, int Wo);
 size_t conv_tc_workspace(int mode, int B, int H, int W, int Ci, int Co, int k, int stride, int Ho, int Wo);
 void conv_tc_set_debug(void* p);
+void conv_tc_set_max_ctas(int n);
 }  // namespace gg
 
 namespace {
@@ -407,6 +408,11 @@ extern "C" size_t gg_conv2d_wgrad_workspace(int B, int H, int W, int Ci, int Co,
   SmallCi sc = smallci_plan(2, p);
   if (sc.ok && sc.tc_bytes + sc.p_bytes > tc) tc = sc.tc_bytes + sc.p_bytes;
   return direct > tc ? direct : tc;
+}
+
+extern "C" int gg_set_tc_max_ctas(int n) {
+  conv_tc_set_max_ctas(n);
+  return GG_OK;
 }
 
 extern "C" int gg_debug_set_buffer(void* device_buffer_256_int64) {

@@ -420,6 +420,8 @@ int pick_n_tile(int n) {
   return 0;
 }
 
+int g_tc_max_ctas = kNumSMs;
+
 int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return (e && e[0]) ? atoi(e) : dflt;
@@ -428,7 +430,8 @@ int env_int(const char* name, int dflt) {
 int pick_splits(int tiles, int kb_min) {
   int forced = env_int("GG_TC_SPLITS", 0);   // experiment knob
   if (forced > 0) return forced;
-  int s = kNumSMs / tiles;                   // fill (at most) one wave of CTAs: 1 CTA per SM (shared-memory bound)
+  const int max_ctas = g_tc_max_ctas;       // < 148 leaves SMs for kernels running concurrently on other streams
+  int s = max_ctas / tiles;                  // fill (at most) one wave of CTAs: 1 CTA per SM (shared-memory bound)
   int cap = kb_min / 3;                      // keep >= 3 k-blocks per CTA so the pipeline fills
   if (cap < 1) cap = 1;
   if (s > cap) s = cap;
@@ -643,6 +646,8 @@ int conv_tc_wgrad(const float* x, const float* dy, float* dw, int B, int H, int 
   *handled = true;
   return GG_OK;
 }
+
+void conv_tc_set_max_ctas(int n) { g_tc_max_ctas = n < 1 ? 1 : (n > kNumSMs ? kNumSMs : n); }
 
 void conv_tc_set_debug(void* p) { g_dbg = reinterpret_cast<long long*>(p); }
 

@@ -163,6 +163,10 @@ class Plan(object):
             elif isinstance(f, Tensor):
                 roots.append(f)
         self.order = self._toposort(roots)
+        # split-K of the tensor-core kernels is sized to half the GPU when the plan will run multi-stream (two launches can
+        # then overlap); workspace sizes depend on it, so it is fixed before emission
+        self.n_streams = int(os.environ.get("GG_STREAMS", "6")) if (rt.use_cuda_graph and ggdist.world_size() == 1) else 1
+        cabi.call("gg_set_tc_max_ctas", int(os.environ.get("GG_TC_MAX_CTAS", "74" if self.n_streams > 1 else "148")))
         # scheduling metadata: one group per node that launches kernels; `owner` resolves views (reshape / aux / fed)
         # to the node whose kernels produce the storage
         self.groups = []     # dicts: start, end, reads (owner ids), writes (owner id), barrier
@@ -700,7 +704,7 @@ class Plan(object):
 
     def _capture_segments(self):
         torch = _torch()
-        n_streams = int(os.environ.get("GG_STREAMS", "4"))
+        n_streams = self.n_streams
         if n_streams > 1 and not any(getattr(f, "is_collective", False) for f in self.steps):
             return self._capture_multi_stream(n_streams)
         segments, cur = [], []

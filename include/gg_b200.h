@@ -53,6 +53,9 @@ int gg_set_conv_backend(int mode);
 int gg_get_conv_backend(void);
 /* which backend the most recent conv / gemm call on this thread used: 0 direct, 1 tcgen05 */
 int gg_last_backend(void);
+/* upper bound on the CTAs one tensor-core conv / dense launch may occupy (split-K is sized to it).  148 = the whole
+ * GPU (default, best for a kernel running alone); the multi-stream executor sets 74 so two launches can overlap. */
+int gg_set_tc_max_ctas(int n);
 
 /* ---- activation codes ------------------------------------------------------------ */
 #define GG_ACT_NONE 0
