@@ -41,6 +41,7 @@ struct TcParams {
   int m_tiles;                // fwd/dgrad: tw*th*tb (per class); wgrad: ceil(taps*Ci/128)
   int splits;
   int stages;                 // depth of the operand ring (as many as fit)
+  int cluster;                // 1: the `splits` CTAs of a tile form a thread-block cluster and reduce through DSMEM
   int act;
   float alpha;
   float* out;
@@ -56,6 +57,35 @@ __device__ __forceinline__ long long gtime() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+__device__ __forceinline__ void cluster_sync_all() {   // every thread of every CTA of the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t remote_bar_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t done, spins = 0;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (!done && ++spins > (1u << 24)) __trap();
+  } while (!done);
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 #ifdef GG_TIMELINE
 #define GG_DBG(slot) do { if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0) p.dbg[slot] = gtime(); } while (0)
 #else
@@ -67,10 +97,9 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], accum_bar;
+  __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], accum_bar, cl_bar;
   const int kStages = p.stages;
   __shared__ uint32_t tmem_base_sh;
-  __shared__ int last_flag;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int stage_bytes = kABytes + p.n_tile * 128;
@@ -115,6 +144,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kMaxStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&accum_bar, 1);
+    mbar_init(&cl_bar, (uint32_t)p.splits);      // cluster mode: one arrival per CTA of the tile
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -122,7 +152,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_cols = p.n_tile <= 32 ? 32 : (p.n_tile <= 64 ? 64 : 128);
   if (warp == 2) tmem_alloc(&tmem_base_sh, tmem_cols);
   tc_fence_before();
-  __syncthreads();
+  const bool cl = p.cluster != 0;
+  if (cl) cluster_sync_all();                  // peers must not signal cl_bar before it is initialised
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = tmem_base_sh;
   if (threadIdx.x == 0) GG_DBG(0);
@@ -244,8 +276,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t taddr = tmem_d + ((uint32_t)(quad * 32) << 16);
     // The operand ring is idle once accum_bar has fired: reuse it as a [128][n_tile+4] staging tile so that the final
     // global stores are row-coalesced (a warp writes one whole output row per instruction).
-    float* stage_tile = reinterpret_cast<float*>(smem);
-    long long* row_off = reinterpret_cast<long long*>(smem + 128 * (kMaxNTile + 4) * 4);
+    // (cluster mode keeps this CTA's partial tile in the first 64 KB for its peers to read; staging goes behind it)
+    const int stage_off = cl ? 128 * p.n_tile * 4 : 0;
+    float* stage_tile = reinterpret_cast<float*>(smem + stage_off);
+    long long* row_off = reinterpret_cast<long long*>(smem + stage_off + 128 * (kMaxNTile + 4) * 4);
     const int ld = p.n_tile + 4;
     row_off[m] = valid ? (long long)(orow - p.out) : -1;
     bool do_store = true;
@@ -280,6 +314,59 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
           GG_FINISH4(o, c0 + i);
           *reinterpret_cast<float4*>(stage_tile + m * ld + c0 + i) = o;
+        }
+      }
+    } else if (cl) {
+      // split-K inside a thread-block cluster: each CTA parks its partial tile in its OWN shared memory ([n_tile/4][128]
+      // float4), signals every peer's mbarrier, and then sums its column slice straight out of the peers' shared memory
+      // (DSMEM) in split order — no global round trip, no atomics, no cooperative launch.
+      float4* ptile = reinterpret_cast<float4*>(smem);
+      for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
+        float v[32];
+        if (nkb > 0) tmem_ld_32x32(taddr + (uint32_t)c0, v);
+        else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) ptile[((c0 + i) >> 2) * 128 + m] = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
+      asm volatile("fence.acq_rel.cluster;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et < p.splits) mbar_arrive_remote(map_to_cta(smem_u32(&cl_bar), (uint32_t)et));
+      mbar_wait_cluster(&cl_bar, 0);
+      const int nc = p.n_tile / 4;
+      cbeg = (split * nc) / p.splits;
+      cend = ((split + 1) * nc) / p.splits;
+      const uint32_t my_ptile = smem_u32(ptile);
+      for (int c4 = cbeg; c4 < cend; c4 += 4) {
+        float4 acc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int sp = 0; sp < p.splits; sp += 2) {
+          float4 t[2][4];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const uint32_t peer = map_to_cta(my_ptile, (uint32_t)min(sp + q, p.splits - 1));
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              t[q][u] = (sp + q < p.splits && c4 + u < cend) ? ld_dsmem_f4(peer + (uint32_t)(((c4 + u) * 128 + m) * 16))
+                                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              acc[u].x += t[q][u].x; acc[u].y += t[q][u].y; acc[u].z += t[q][u].z; acc[u].w += t[q][u].w;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (c4 + u < cend) {
+            float4 o = acc[u];
+            GG_FINISH4(o, (c4 + u) * 4);
+            *reinterpret_cast<float4*>(stage_tile + m * ld + (c4 + u) * 4) = o;
+          }
         }
       }
     } else {
@@ -390,7 +477,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (p.dbg && threadIdx.x == 64) atomicMax(reinterpret_cast<unsigned long long*>(p.dbg + 200), (unsigned long long)gtime());
   // ---- teardown -----------------------------------------------------------------------------------------
   tc_fence_before();
-  __syncthreads();
+  __syncwarp();
+  if (cl) cluster_sync_all();                  // no CTA may exit (and free its shared memory) while a peer still reads it
+  else __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_d, tmem_cols);
 }
 
@@ -435,7 +524,8 @@ int pick_splits(int tiles, int kb_min) {
   int cap = kb_min / 3;                      // keep >= 3 k-blocks per CTA so the pipeline fills
   if (cap < 1) cap = 1;
   if (s > cap) s = cap;
-  if (s > 16) s = 16;
+  static int use_cluster = env_int("GG_TC_CLUSTER", 0);
+  if (s > (use_cluster ? 8 : 16)) s = use_cluster ? 8 : 16;   // 8 = portable thread-block-cluster size
   if (s < 1) s = 1;
   return s;
 }
@@ -537,7 +627,26 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, TcPlan& pl, void* ws,
     attr_set[MODE] = true;
   }
   dim3 grid(pl.grid_x, p.splits);
-  if (p.splits > 1) {
+  // Thread-block-cluster / DSMEM reduction (GG_TC_CLUSTER=1): correct (same tests pass) but measured no faster than the
+  // L2 workspace rendezvous on B200 (E.2 fwd 13.7 vs 14.2 us, E.3 fwd 26 vs 13 us: 8-CTA clusters of 197 KB CTAs place
+  // badly on 16-20-SM GPCs), so it is off by default.
+  p.cluster = (p.splits > 1 && p.splits <= 8 && env_int("GG_TC_CLUSTER", 0) != 0) ? 1 : 0;
+  if (p.cluster) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = (unsigned)p.splits;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<MODE>, tmA, tmB, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(GG_ERR_CUDA_BASE + (int)e, "conv_tc: cluster launch failed: %s", cudaGetErrorString(e)); }
+  } else if (p.splits > 1) {
     // the split-K rendezvous spins on a ticket: all CTAs of the grid must be co-resident -> cooperative launch
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;

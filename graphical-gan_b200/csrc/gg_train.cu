@@ -373,10 +373,30 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const gg_adam_entry* __
   // TensorFlow ApplyAdam: lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t), epsilon outside the bias correction
   float lr_t = (float)((double)lr * sqrt(1.0 - st->b2t) / (1.0 - st->b1t));
   long long end = min(e.n, ch.offset + (long long)GG_ADAM_CHUNK);
+  const float om1 = 1.f - b1, om2 = 1.f - b2;
+  const bool vec = ((reinterpret_cast<uintptr_t>(e.p) | reinterpret_cast<uintptr_t>(e.g) | reinterpret_cast<uintptr_t>(e.m) |
+                     reinterpret_cast<uintptr_t>(e.v)) & 15) == 0 && ((end - ch.offset) & 3) == 0;
+  if (vec) {   // 28 B/parameter of traffic: 128-bit accesses (chunk offsets are multiples of 4096 elements)
+    for (long long i = ch.offset + threadIdx.x * 4; i < end; i += blockDim.x * 4) {
+      float4 g = *reinterpret_cast<const float4*>(e.g + i);
+      float4 m = *reinterpret_cast<float4*>(e.m + i);
+      float4 v = *reinterpret_cast<float4*>(e.v + i);
+      float4 p = *reinterpret_cast<float4*>(e.p + i);
+      g.x *= gscale; g.y *= gscale; g.z *= gscale; g.w *= gscale;
+      m.x += (g.x - m.x) * om1; m.y += (g.y - m.y) * om1; m.z += (g.z - m.z) * om1; m.w += (g.w - m.w) * om1;
+      v.x += (g.x * g.x - v.x) * om2; v.y += (g.y * g.y - v.y) * om2; v.z += (g.z * g.z - v.z) * om2; v.w += (g.w * g.w - v.w) * om2;
+      p.x -= lr_t * m.x / (sqrtf(v.x) + eps); p.y -= lr_t * m.y / (sqrtf(v.y) + eps);
+      p.z -= lr_t * m.z / (sqrtf(v.z) + eps); p.w -= lr_t * m.w / (sqrtf(v.w) + eps);
+      *reinterpret_cast<float4*>(e.m + i) = m;
+      *reinterpret_cast<float4*>(e.v + i) = v;
+      *reinterpret_cast<float4*>(e.p + i) = p;
+    }
+    return;
+  }
   for (long long i = ch.offset + threadIdx.x; i < end; i += blockDim.x) {
     float g = e.g[i] * gscale;
-    float m = e.m[i] + (g - e.m[i]) * (1.f - b1);
-    float v = e.v[i] + (g * g - e.v[i]) * (1.f - b2);
+    float m = e.m[i] + (g - e.m[i]) * om1;
+    float v = e.v[i] + (g * g - e.v[i]) * om2;
     e.m[i] = m;
     e.v[i] = v;
     e.p[i] = e.p[i] - lr_t * m / (sqrtf(v) + eps);

@@ -165,7 +165,7 @@ class Plan(object):
         self.order = self._toposort(roots)
         # split-K of the tensor-core kernels is sized to half the GPU when the plan will run multi-stream (two launches can
         # then overlap); workspace sizes depend on it, so it is fixed before emission
-        self.n_streams = int(os.environ.get("GG_STREAMS", "6")) if (rt.use_cuda_graph and ggdist.world_size() == 1) else 1
+        self.n_streams = int(os.environ.get("GG_STREAMS", "6")) if rt.use_cuda_graph else 1
         cabi.call("gg_set_tc_max_ctas", int(os.environ.get("GG_TC_MAX_CTAS", "74" if self.n_streams > 1 else "148")))
         # scheduling metadata: one group per node that launches kernels; `owner` resolves views (reshape / aux / fed)
         # to the node whose kernels produce the storage
@@ -175,7 +175,7 @@ class Plan(object):
             self.has_random = True
             tick = rt.tick()
             self.steps.append(lambda st, tick=tick: cabi.call("gg_rng_tick", tick.data_ptr(), st))
-            self.groups.append(dict(start=0, end=1, reads=set(), writes="tick", barrier=False))
+            self.groups.append(dict(start=0, end=1, reads=set(), writes="tick", barrier=False, collective=False))
         for node in self.order:
             s0 = len(self.steps)
             self._emit(node)
@@ -185,7 +185,7 @@ class Plan(object):
                 s0 = len(self.steps)
                 self._emit_operation(f)
                 if len(self.steps) > s0:
-                    self.groups.append(dict(start=s0, end=len(self.steps), reads=set(), writes="op%d" % f.id, barrier=True))
+                    self._add_groups(s0, len(self.steps), set(), "op%d" % f.id, barrier=True)
         self.graph = None
         self.kernel_launches = 0   # libgg_b200 kernels per run (counted at capture / eager launch)
         self.runs = 0
@@ -201,7 +201,27 @@ class Plan(object):
         reads = set(self.owner.get(i.id, i.id) for i in node.inputs)
         if node.op == "random":
             reads.add("tick")
-        self.groups.append(dict(start=s0, end=len(self.steps), reads=reads, writes=node.id, barrier=False))
+        self._add_groups(s0, len(self.steps), reads, node.id, barrier=False)
+
+    def _add_groups(self, s0, end, reads, writes, barrier):
+        """one scheduling group per maximal run of kernel steps; a collective step inside a node (SyncBN statistics, the
+        gradient bucket all-reduce) becomes its own group so the launch list can be cut there"""
+        cuts = [i for i in range(s0, end) if getattr(self.steps[i], "is_collective", False)]
+        ranges, a = [], s0
+        for c in cuts:
+            if c > a:
+                ranges.append((a, c, False))
+            ranges.append((c, c + 1, True))
+            a = c + 1
+        if end > a:
+            ranges.append((a, end, False))
+        prev = None
+        for k, (a, b, coll) in enumerate(ranges):
+            last = k == len(ranges) - 1
+            w = writes if last else "%s#%d" % (writes, k)
+            r = set(reads) if prev is None else {prev}
+            self.groups.append(dict(start=a, end=b, reads=r, writes=w, barrier=barrier and prev is None, collective=coll))
+            prev = w
 
     # ---- graph walking ---------------------------------------------------------------------
     def _op_roots(self, op):
@@ -645,10 +665,14 @@ class Plan(object):
         stream; cross-stream dependencies become event waits.  Independent branches of the step (E(real) vs G(p_z),
         the two discriminator applications, every wgrad / bias-gradient leaf vs the dgrad chain) then overlap inside the
         captured CUDA graph — most kernels of this workload are latency-bound and fill a fraction of the 148 SMs."""
-        producer, assign, waits, need_event = {}, [], [], set()
+        return self._schedule_range(range(len(self.groups)), n_streams)
+
+    def _schedule_range(self, idxs, n_streams):
+        producer, assign, waits, need_event = {}, {}, {}, set()
         tail = [None] * n_streams
         last_barrier = None
-        for gi, g in enumerate(self.groups):
+        for gi in idxs:
+            g = self.groups[gi]
             deps = set(producer[o] for o in g["reads"] if o in producer)
             if last_barrier is not None:
                 deps.add(last_barrier)
@@ -662,21 +686,20 @@ class Plan(object):
                 s = free[0] if free else min(range(n_streams), key=lambda q: tail[q])
             w = sorted(d for d in deps if assign[d] != s)
             need_event.update(w)
-            assign.append(s)
-            waits.append(w)
+            assign[gi] = s
+            waits[gi] = w
             tail[s] = gi
             producer[g["writes"]] = gi
             if g["barrier"]:
                 last_barrier = gi
         return assign, waits, need_event
 
-    def _capture_multi_stream(self, n_streams):
+    def _capture_range(self, idxs, n_streams):
+        """capture the kernel groups `idxs` (no collectives among them) into one CUDA graph, spread over n_streams streams"""
         torch = _torch()
-        assign, waits, need_event = self._schedule(n_streams)
-        torch.cuda.synchronize()
-        before = cabi.lib.gg_launch_count()
+        assign, waits, need_event = self._schedule_range(idxs, n_streams)
         g = torch.cuda.CUDAGraph()
-        side = [torch.cuda.Stream() for _ in range(n_streams - 1)]
+        side = [torch.cuda.Stream() for _ in range(max(n_streams - 1, 0))]
         self.keep.append(side)
         with torch.cuda.graph(g):
             cs = torch.cuda.current_stream()
@@ -684,7 +707,8 @@ class Plan(object):
             for sd in side:
                 sd.wait_stream(cs)
             events = {}
-            for gi, grp in enumerate(self.groups):
+            for gi in idxs:
+                grp = self.groups[gi]
                 st = streams[assign[gi]]
                 for d in waits[gi]:
                     st.wait_event(events[d])
@@ -698,39 +722,26 @@ class Plan(object):
             for sd in side:
                 cs.wait_stream(sd)
             self.keep.append(events)
-        self.kernel_launches = cabi.lib.gg_launch_count() - before
-        self.streams_used = len(set(assign))
-        return [g]
+        return g
 
     def _capture_segments(self):
+        """launch list -> [CUDA graph | eager collective | CUDA graph | ...]: NCCL collectives stay outside stream capture
+        and run on the main stream between graph segments; every segment is scheduled over n_streams streams"""
         torch = _torch()
-        n_streams = self.n_streams
-        if n_streams > 1 and not any(getattr(f, "is_collective", False) for f in self.steps):
-            return self._capture_multi_stream(n_streams)
         segments, cur = [], []
-        for f in self.steps:
-            if getattr(f, "is_collective", False):
+        for gi, grp in enumerate(self.groups):
+            if grp["collective"]:
                 if cur:
                     segments.append(cur)
                     cur = []
-                segments.append(f)
+                segments.append(self.steps[grp["start"]])
             else:
-                cur.append(f)
+                cur.append(gi)
         if cur:
             segments.append(cur)
-        out = []
         torch.cuda.synchronize()
         before = cabi.lib.gg_launch_count()
-        for seg in segments:
-            if callable(seg):
-                out.append(seg)
-                continue
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                st = cabi.stream_ptr()
-                for f in seg:
-                    f(st)
-            out.append(g)
+        out = [seg if callable(seg) else self._capture_range(seg, self.n_streams) for seg in segments]
         self.kernel_launches = cabi.lib.gg_launch_count() - before
         return out
 
