@@ -81,6 +81,10 @@ SIGNATURES = {
     "gg_rng_uniform": (c_i, [c_p, c_ll, c_f, c_f, C.c_uint64, C.c_uint32, c_p, c_p]),
     "gg_rng_categorical": (c_i, [c_p, c_i, c_p, c_i, C.c_uint64, C.c_uint32, c_p, c_p]),
     "gg_debug_set_buffer": (c_i, [c_p]),
+    "gg_comm_buffer_bytes": (c_sz, [c_i]),
+    "gg_comm_alloc": (c_i, [c_i, C.POINTER(c_p), c_p]),
+    "gg_comm_open": (c_i, [c_p, C.POINTER(c_p)]),
+    "gg_allreduce_small": (c_i, [c_p, c_p, c_i, C.POINTER(c_p), c_i, c_i, c_i, c_p, c_p]),
     "gg_probe_tma_strided": (c_i, [c_p] + [c_i] * 11 + [c_p, c_p]),
     "gg_probe_umma_tf32": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
 }

@@ -58,6 +58,52 @@ def all_reduce_sum(t):
     return t
 
 
+class SmallAllReduce(object):
+    """One-kernel all-reduce of <= max_floats fp32 values through NVLink peer memory (csrc/gg_comm.cu).  Used for the
+    SyncBN statistic exchange: it is CUDA-graph capturable, so a data-parallel step is no longer cut into a graph segment
+    per batch-norm layer.  Single node only (CUDA IPC)."""
+    MAX_FLOATS = 16384
+
+    def __init__(self):
+        import ctypes as C
+        import torch
+        from . import cabi
+        self.cabi, self.C = cabi, C
+        self.rank, self.world = rank(), world_size()
+        buf = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        cabi.call("gg_comm_alloc", self.MAX_FLOATS, C.byref(buf), handle)
+        handles = [None] * self.world
+        _td().all_gather_object(handles, bytes(handle.raw))
+        ptrs = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                ptrs.append(buf.value)
+            else:
+                p = C.c_void_p()
+                cabi.call("gg_comm_open", C.create_string_buffer(h, 64), C.byref(p))
+                ptrs.append(p.value)
+        self.peers = (C.c_void_p * self.world)(*ptrs)
+        self.epoch = torch.zeros(1, dtype=torch.int32, device="cuda")
+        _td().barrier()
+
+    def __call__(self, src, dst, n, stream):
+        self.cabi.call("gg_allreduce_small", src.data_ptr(), dst.data_ptr(), int(n), self.peers, self.rank, self.world,
+                       self.MAX_FLOATS, self.epoch.data_ptr(), stream)
+
+
+_small = {}
+
+
+def small_all_reduce():
+    """process-wide SmallAllReduce, or None (single rank, or GG_SMALL_ALLREDUCE=0 -> NCCL for everything)"""
+    if world_size() <= 1 or os.environ.get("GG_SMALL_ALLREDUCE", "1") == "0":
+        return None
+    if "obj" not in _small:
+        _small["obj"] = SmallAllReduce()
+    return _small["obj"]
+
+
 def shard_bounds(n, r=None, w=None):
     """[lo, hi) of the contiguous dim-0 slice of an n-row batch owned by rank r of w (n must divide evenly:
     the mean-reduced losses only average correctly over equal shards)."""

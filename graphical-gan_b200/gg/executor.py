@@ -544,7 +544,7 @@ class Plan(object):
             self.keep.append(folded)
             fp = folded.data_ptr()
             self.steps.append(lambda st: cabi.call("gg_bn_fold_partials", pp, S, fp, Cc, st))
-            self.steps.append(self._collective(lambda st: ggdist.all_reduce_sum(folded)))
+            self._all_reduce_small(folded, 2 * Cc)
             cnt = float(R * world)
             self.steps.append(lambda st: cabi.call("gg_bn_apply", xp, fp, 1, cnt, gp, bp, eps, yp, mp, rp, R, Cc, act, alpha, st))
         else:
@@ -572,13 +572,22 @@ class Plan(object):
             self.keep.append(glob)
             glp = glob.data_ptr()
             self.steps.append(lambda st: cabi.call("gg_unary", cabi.UNARY["copy"], dgbp, glp, 2 * Cc, 0.0, 0.0, st))
-            self.steps.append(self._collective(lambda st: ggdist.all_reduce_sum(glob)))
+            self._all_reduce_small(glob, 2 * Cc)
             cnt = float(R * world)
             self.steps.append(lambda st: cabi.call("gg_bn_bwd_apply", gyp, xp, yp, mp, rp, gp, None, glp, 1, cnt, dxp, None, None,
                                                    R, Cc, act, alpha, st))
         else:
             self.steps.append(lambda st: cabi.call("gg_bn_bwd_apply", gyp, xp, yp, mp, rp, gp, None, dgbp, 1, float(R), dxp, None,
                                                    None, R, Cc, act, alpha, st))
+
+    def _all_reduce_small(self, t, n):
+        """in-place sum over ranks of the first n floats of t: one peer-memory kernel inside the graph when available,
+        else an eager NCCL all-reduce between graph segments"""
+        sar = ggdist.small_all_reduce()
+        if sar is not None and n <= sar.MAX_FLOATS:
+            self.steps.append(lambda st: sar(t, t, n, st))
+        else:
+            self.steps.append(self._collective(lambda st: ggdist.all_reduce_sum(t)))
 
     # ---- operations (train ops) ---------------------------------------------------------------
     def _emit_operation(self, op):

@@ -233,6 +233,18 @@ int gg_rng_uniform(float* out, long long n, float lo, float hi, uint64_t seed, u
 int gg_rng_categorical(int32_t* idx, int n, const float* probs, int K, uint64_t seed, uint32_t stream_id,
                        const void* tick_counter, void* stream);
 
+/* ---- small-message all-reduce over NVLink peer memory (SyncBN statistics; new functionality) ------ */
+/* Each rank allocates one exchange buffer (gg_comm_alloc -> device pointer + 64-byte CUDA IPC handle), the handles are
+ * exchanged by the host (torch.distributed all_gather), every rank maps its peers' buffers (gg_comm_open).
+ * gg_allreduce_small: dst[i] = sum over ranks of src[i], n <= max_floats, one kernel, CUDA-graph capturable;
+ * epoch_counter is a device uint32 owned by the caller (zero-initialised), peer_bufs_host a host array of `world` device
+ * pointers ordered by rank (entry `rank` = the local buffer).  All ranks must issue the same sequence of calls. */
+size_t gg_comm_buffer_bytes(int max_floats);
+int gg_comm_alloc(int max_floats, void** buf_out, void* ipc_handle_out_64);
+int gg_comm_open(const void* ipc_handle_64, void** buf_out);
+int gg_allreduce_small(const float* src, float* dst, int n, void* const* peer_bufs_host, int rank, int world,
+                       int max_floats, void* epoch_counter, void* stream);
+
 /* ---- hardware probes used by the tests (not part of the training path) ---------------- */
 /* TMA strided-box probe: loads x[b, h0 + 2*i, w0 + 2*j, c0..c0+32) for i<hb, j<wb into out[hb][wb][32] with a
  * tiled tensor map using elementStrides=(1,2,2,1), zero-filling out-of-range coordinates. `out` receives the raw shared-memory image
