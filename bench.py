@@ -220,6 +220,13 @@ def run_ours(args):
     barrier()
     hot_ms = e0.elapsed_time(e1)
 
+    if args.quick:
+        # experiment mode (tools/, env-knob sweeps): device-timed numbers only, not a bench line
+        if rank == 0:
+            print(json.dumps({"quick": True, "images_per_sec": BATCH * world * args.steps / (dev_ms / 1e3),
+                              "ms_per_step": dev_ms / args.steps, "ms_per_step_hot_l2": hot_ms / args.steps,
+                              "env": {k: v for k, v in os.environ.items() if k.startswith("GG_")}}))
+        return
     # ---- end to end through Session.run: host batches in, cost scalars out, every step ----
     for i in range(3):
         iteration_e2e(i)
@@ -282,6 +289,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--quick", action="store_true", help="device-timed throughput only (knob sweeps); prints a short JSON")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

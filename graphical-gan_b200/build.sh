@@ -23,3 +23,13 @@ done
 for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
 "$NVCC" -shared -gencode arch=compute_100a,code=sm_100a "${objs[@]}" -o "$OUT/libgg_b200.so" -cudart static
 echo "built $OUT/libgg_b200.so"
+if [ "${GG_BUILD_TIMELINE:-0}" = "1" ]; then
+  # instrumented twin for tools/timeline_conv.py (GG_LIB=.../libgg_b200_tl.so): per-stage globaltimer stamps in the conv kernel
+  "$NVCC" "${FLAGS[@]}" -DGG_TIMELINE -c "$HERE/csrc/gg_conv_tc.cu" -o "$OBJ/gg_conv_tc_tl.o"
+  tl_objs=()
+  for o in "${objs[@]}"; do
+    if [ "$(basename "$o")" = "gg_conv_tc.o" ]; then tl_objs+=("$OBJ/gg_conv_tc_tl.o"); else tl_objs+=("$o"); fi
+  done
+  "$NVCC" -shared -gencode arch=compute_100a,code=sm_100a "${tl_objs[@]}" -o "$OUT/libgg_b200_tl.so" -cudart static
+  echo "built $OUT/libgg_b200_tl.so"
+fi

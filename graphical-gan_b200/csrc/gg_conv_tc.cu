@@ -98,6 +98,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], accum_bar, cl_bar;
+  if (p.dbg && threadIdx.x == 0) {             // timeline (tools/timeline_conv.py): earliest CTA entry of the launch
+    const long long t_in = gtime();
+    atomicMin(reinterpret_cast<unsigned long long*>(p.dbg + 210), (unsigned long long)t_in);
+    if (blockIdx.x == 0 && blockIdx.y == 0) p.dbg[211] = t_in;
+  }
   const int kStages = p.stages;
   __shared__ uint32_t tmem_base_sh;
 
@@ -401,6 +406,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         } while (seen < (unsigned)p.splits);
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et == 0) GG_DBG(212);
       const int nc = p.n_tile / 4;
       cbeg = (split * nc) / p.splits;
       cend = ((split + 1) * nc) / p.splits;

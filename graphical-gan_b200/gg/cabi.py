@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libgg_b200.so")
+# GG_LIB selects an alternative build of the same library (e.g. the -DGG_TIMELINE instrumented one for tools/)
+LIB_PATH = os.environ.get("GG_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libgg_b200.so")
 
 
 class GGError(RuntimeError):
