@@ -1,0 +1,304 @@
+// gg_bn_fused.cu — training-mode batch normalisation (batch statistics, tflib/ops/batchnorm.py:30,77-84) and its gradient
+// as ONE kernel each.
+//
+// The two-/three-kernel form (gg_bn_stats -> gg_bn_apply; gg_bn_bwd_reduce -> gg_bn_fold_partials -> gg_bn_bwd_apply) sits on
+// the critical path of the training step five times forward and five times backward; every extra launch costs a
+// kernel-to-kernel dependency latency (~2 us) on tensors that are only 1-4 MB.  Per-channel statistics are independent
+// across channels, so the work is partitioned by CHANNEL GROUP: a thread-block cluster owns `cw` consecutive channels
+// (32-byte row segments for cw = 8), its CTAs split the rows, the per-CTA partial sums meet in distributed shared memory
+// (one cluster barrier), and every CTA then normalises its own row slice.  x is read twice (statistics, apply) — the
+// second read is an L1/L2 hit for these sizes — and y written once: 12*R*C bytes algorithmic, HBM/L2-bound.
+// No grid-wide synchronisation, no atomics, deterministic summation order.  The multi-kernel path remains for data
+// parallel runs, where the statistics are all-reduced across ranks between the two halves (SyncBN).
+#include "gg_common.cuh"
+
+using namespace gg;
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxCw = 32;
+
+struct BnPlan {
+  bool ok;
+  int cw;       // channels per cluster
+  int groups;   // channel groups (clusters)
+  int cs;       // CTAs per cluster (row split)
+};
+
+BnPlan bn_plan(int R, int C) {
+  BnPlan p{false, 0, 0, 1};
+  if (R <= 0 || C <= 0 || C % 4 != 0) return p;
+  p.cw = (C >= 32 && R <= 256) ? 32 : 8;
+  if (p.cw > C) p.cw = (C >= 8) ? 8 : 4;
+  p.groups = ceil_div(C, p.cw);
+  p.cs = 1;
+  while (p.cs < 8 && p.groups * p.cs < 64 && R / (p.cs * 2) >= 64) p.cs *= 2;
+  p.ok = true;
+  return p;
+}
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ double ld_dsmem_f64(const double* local_ptr, uint32_t cta_rank) {
+  uint32_t local = (uint32_t)__cvta_generic_to_shared(local_ptr), remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(cta_rank));
+  double v;
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(remote) : "memory");
+  return v;
+}
+
+// Reduce per-thread (a[4], b[4]) over all threads of the CTA that share a channel quad, then over the CTAs of the
+// cluster.  Thread t owns quad t % Q; on return threads 0..cw-1 hold the cluster totals of channel c0 + t in (ta, tb).
+template <int Q>
+__device__ __forceinline__ void reduce_channels(float (&a)[4], float (&b)[4], int cs, double& ta, double& tb,
+                                                float (*wred)[kMaxCw][2], double (*xch)[2]) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int o = 16; o >= Q; o >>= 1) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      a[e] += __shfl_xor_sync(0xffffffffu, a[e], o);
+      b[e] += __shfl_xor_sync(0xffffffffu, b[e], o);
+    }
+  }
+  if (lane < Q) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { wred[warp][lane * 4 + e][0] = a[e]; wred[warp][lane * 4 + e][1] = b[e]; }
+  }
+  __syncthreads();
+  const int cw = Q * 4;
+  ta = 0.0; tb = 0.0;
+  if (tid < cw) {
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) { ta += (double)wred[w][tid][0]; tb += (double)wred[w][tid][1]; }
+    xch[tid][0] = ta;
+    xch[tid][1] = tb;
+  }
+  if (cs > 1) {
+    cluster_sync_all();                       // every CTA's xch is written and visible cluster-wide
+    if (tid < cw) {
+      ta = 0.0; tb = 0.0;
+      for (int r = 0; r < cs; ++r) {          // rank order: identical, deterministic totals on every CTA
+        ta += ld_dsmem_f64(&xch[tid][0], (uint32_t)r);
+        tb += ld_dsmem_f64(&xch[tid][1], (uint32_t)r);
+      }
+    }
+    cluster_sync_all();                       // peers have finished reading this CTA's xch: it may exit / reuse
+  }
+}
+
+template <int Q>
+__global__ void __launch_bounds__(kThreads) bn_fwd_fused_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, float eps,
+                                                                float* __restrict__ y, float* __restrict__ mean_out,
+                                                                float* __restrict__ rstd_out, int R, int C, int cs, int act,
+                                                                float alpha) {
+  constexpr int cw = Q * 4, RL = kThreads / Q;
+  __shared__ float wred[kThreads / 32][kMaxCw][2];
+  __shared__ double xch[kMaxCw][2];
+  __shared__ float s_scale[kMaxCw], s_shift[kMaxCw];
+  const int tid = threadIdx.x;
+  const int rank = cs > 1 ? (int)cluster_ctarank() : 0;
+  const int group = blockIdx.x / cs;
+  const int c0 = group * cw;
+  const int quad = tid % Q, rl = tid / Q;
+  const int c = c0 + quad * 4;
+  const bool c_ok = c < C;                                   // C % 4 == 0: a quad is entirely inside or outside
+  const int rows_per = (R + cs - 1) / cs;
+  const int r_begin = rank * rows_per, r_end = min(R, r_begin + rows_per);
+
+  float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c_ok) {
+#pragma unroll 4
+    for (int r = r_begin + rl; r < r_end; r += RL) {
+      const float4 v = *reinterpret_cast<const float4*>(x + (size_t)r * C + c);
+      a[0] += v.x; a[1] += v.y; a[2] += v.z; a[3] += v.w;
+      b[0] += v.x * v.x; b[1] += v.y * v.y; b[2] += v.z * v.z; b[3] += v.w * v.w;
+    }
+  }
+  double ta, tb;
+  reduce_channels<Q>(a, b, cs, ta, tb, wred, xch);
+  if (tid < cw) {
+    const int ch = c0 + tid;
+    if (ch < C) {
+      const double mean = ta / (double)R;
+      double var = tb / (double)R - mean * mean;             // biased batch variance (fused_batch_norm, is_training)
+      if (var < 0.0) var = 0.0;
+      const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+      const float g = gamma ? gamma[ch] : 1.f, bt = beta ? beta[ch] : 0.f;
+      s_scale[tid] = rstd * g;
+      s_shift[tid] = bt - (float)mean * rstd * g;
+      if (rank == 0) {
+        if (mean_out) mean_out[ch] = (float)mean;
+        if (rstd_out) rstd_out[ch] = rstd;
+      }
+    }
+  }
+  __syncthreads();
+  if (!c_ok) return;
+  const float4 sc = *reinterpret_cast<const float4*>(&s_scale[quad * 4]);
+  const float4 sh = *reinterpret_cast<const float4*>(&s_shift[quad * 4]);
+#pragma unroll 4
+  for (int r = r_begin + rl; r < r_end; r += RL) {
+    const size_t i = (size_t)r * C + c;
+    const float4 v = *reinterpret_cast<const float4*>(x + i);
+    float4 o;
+    o.x = apply_act(v.x * sc.x + sh.x, act, alpha);
+    o.y = apply_act(v.y * sc.y + sh.y, act, alpha);
+    o.z = apply_act(v.z * sc.z + sh.z, act, alpha);
+    o.w = apply_act(v.w * sc.w + sh.w, act, alpha);
+    *reinterpret_cast<float4*>(y + i) = o;
+  }
+}
+
+template <int Q>
+__global__ void __launch_bounds__(kThreads) bn_bwd_fused_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                                const float* __restrict__ y, const float* __restrict__ mean,
+                                                                const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                                float* __restrict__ dx, float* __restrict__ dgamma,
+                                                                float* __restrict__ dbeta, int R, int C, int cs, int act,
+                                                                float alpha) {
+  constexpr int cw = Q * 4, RL = kThreads / Q;
+  __shared__ float wred[kThreads / 32][kMaxCw][2];
+  __shared__ double xch[kMaxCw][2];
+  __shared__ float s_mg[kMaxCw], s_mgx[kMaxCw];
+  const int tid = threadIdx.x;
+  const int rank = cs > 1 ? (int)cluster_ctarank() : 0;
+  const int group = blockIdx.x / cs;
+  const int c0 = group * cw;
+  const int quad = tid % Q, rl = tid / Q;
+  const int c = c0 + quad * 4;
+  const bool c_ok = c < C;
+  const int rows_per = (R + cs - 1) / cs;
+  const int r_begin = rank * rows_per, r_end = min(R, r_begin + rows_per);
+
+  float4 m4 = make_float4(0.f, 0.f, 0.f, 0.f), rs4 = m4;
+  if (c_ok) {
+    m4 = *reinterpret_cast<const float4*>(mean + c);
+    rs4 = *reinterpret_cast<const float4*>(rstd + c);
+  }
+  float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c_ok) {
+#pragma unroll 2
+    for (int r = r_begin + rl; r < r_end; r += RL) {
+      const size_t i = (size_t)r * C + c;
+      float4 g = *reinterpret_cast<const float4*>(dy + i);
+      const float4 xv = *reinterpret_cast<const float4*>(x + i);
+      if (act != GG_ACT_NONE) {
+        const float4 yv = *reinterpret_cast<const float4*>(y + i);
+        g.x = act_grad_from_out(yv.x, g.x, act, alpha); g.y = act_grad_from_out(yv.y, g.y, act, alpha);
+        g.z = act_grad_from_out(yv.z, g.z, act, alpha); g.w = act_grad_from_out(yv.w, g.w, act, alpha);
+      }
+      a[0] += g.x; a[1] += g.y; a[2] += g.z; a[3] += g.w;
+      b[0] += g.x * ((xv.x - m4.x) * rs4.x); b[1] += g.y * ((xv.y - m4.y) * rs4.y);
+      b[2] += g.z * ((xv.z - m4.z) * rs4.z); b[3] += g.w * ((xv.w - m4.w) * rs4.w);
+    }
+  }
+  double ta, tb;
+  reduce_channels<Q>(a, b, cs, ta, tb, wred, xch);
+  if (tid < cw) {
+    const int ch = c0 + tid;
+    if (ch < C) {
+      s_mg[tid] = (float)(ta / (double)R);
+      s_mgx[tid] = (float)(tb / (double)R);
+      if (rank == 0) {
+        if (dbeta) dbeta[ch] = (float)ta;
+        if (dgamma) dgamma[ch] = (float)tb;
+      }
+    }
+  }
+  __syncthreads();
+  if (!c_ok || dx == nullptr) return;
+  const float4 mg = *reinterpret_cast<const float4*>(&s_mg[quad * 4]);
+  const float4 mgx = *reinterpret_cast<const float4*>(&s_mgx[quad * 4]);
+  float4 k4 = rs4;
+  if (gamma) {
+    const float4 gm = *reinterpret_cast<const float4*>(gamma + c);
+    k4.x *= gm.x; k4.y *= gm.y; k4.z *= gm.z; k4.w *= gm.w;
+  }
+#pragma unroll 2
+  for (int r = r_begin + rl; r < r_end; r += RL) {
+    const size_t i = (size_t)r * C + c;
+    float4 g = *reinterpret_cast<const float4*>(dy + i);
+    const float4 xv = *reinterpret_cast<const float4*>(x + i);
+    if (act != GG_ACT_NONE) {
+      const float4 yv = *reinterpret_cast<const float4*>(y + i);
+      g.x = act_grad_from_out(yv.x, g.x, act, alpha); g.y = act_grad_from_out(yv.y, g.y, act, alpha);
+      g.z = act_grad_from_out(yv.z, g.z, act, alpha); g.w = act_grad_from_out(yv.w, g.w, act, alpha);
+    }
+    float4 o;
+    o.x = k4.x * (g.x - mg.x - (xv.x - m4.x) * rs4.x * mgx.x);
+    o.y = k4.y * (g.y - mg.y - (xv.y - m4.y) * rs4.y * mgx.y);
+    o.z = k4.z * (g.z - mg.z - (xv.z - m4.z) * rs4.z * mgx.z);
+    o.w = k4.w * (g.w - mg.w - (xv.w - m4.w) * rs4.w * mgx.w);
+    *reinterpret_cast<float4*>(dx + i) = o;
+  }
+}
+
+template <typename Kern, typename... Args>
+int launch_clustered(Kern kern, const BnPlan& pl, cudaStream_t st, const char* what, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(pl.groups * pl.cs));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)pl.cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pl.cs > 1 ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, args...);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(GG_ERR_CUDA_BASE + (int)e, "%s: launch failed", what);
+  }
+  return check_launch(what);
+}
+
+}  // namespace
+
+extern "C" int gg_bn_fused_supported(int R, int C) { return bn_plan(R, C).ok ? 1 : 0; }
+
+extern "C" int gg_bn_fwd_fused(const float* x, const float* gamma, const float* beta, float eps, float* y, float* mean_out,
+                               float* rstd_out, int R, int C, int act, float alpha, void* stream) {
+  if (R <= 0 || C <= 0) return GG_OK;
+  const BnPlan pl = bn_plan(R, C);
+  if (!pl.ok) return fail(GG_ERR_UNSUPPORTED, "gg_bn_fwd_fused: C must be a multiple of 4%s");
+  cudaStream_t st = as_stream(stream);
+  if (pl.cw == 32)
+    return launch_clustered(bn_fwd_fused_kernel<8>, pl, st, "gg_bn_fwd_fused", x, gamma, beta, eps, y, mean_out, rstd_out, R, C,
+                            pl.cs, act, alpha);
+  if (pl.cw == 8)
+    return launch_clustered(bn_fwd_fused_kernel<2>, pl, st, "gg_bn_fwd_fused", x, gamma, beta, eps, y, mean_out, rstd_out, R, C,
+                            pl.cs, act, alpha);
+  return launch_clustered(bn_fwd_fused_kernel<1>, pl, st, "gg_bn_fwd_fused", x, gamma, beta, eps, y, mean_out, rstd_out, R, C,
+                          pl.cs, act, alpha);
+}
+
+extern "C" int gg_bn_bwd_fused(const float* dy, const float* x, const float* y, const float* mean, const float* rstd,
+                               const float* gamma, float* dx, float* dgamma, float* dbeta, int R, int C, int act, float alpha,
+                               void* stream) {
+  if (R <= 0 || C <= 0) return GG_OK;
+  if (act != GG_ACT_NONE && y == nullptr) return fail(GG_ERR_BAD_ARG, "gg_bn_bwd_fused: y required when act is fused%s");
+  const BnPlan pl = bn_plan(R, C);
+  if (!pl.ok) return fail(GG_ERR_UNSUPPORTED, "gg_bn_bwd_fused: C must be a multiple of 4%s");
+  cudaStream_t st = as_stream(stream);
+  if (pl.cw == 32)
+    return launch_clustered(bn_bwd_fused_kernel<8>, pl, st, "gg_bn_bwd_fused", dy, x, y, mean, rstd, gamma, dx, dgamma, dbeta, R,
+                            C, pl.cs, act, alpha);
+  if (pl.cw == 8)
+    return launch_clustered(bn_bwd_fused_kernel<2>, pl, st, "gg_bn_bwd_fused", dy, x, y, mean, rstd, gamma, dx, dgamma, dbeta, R,
+                            C, pl.cs, act, alpha);
+  return launch_clustered(bn_bwd_fused_kernel<1>, pl, st, "gg_bn_bwd_fused", dy, x, y, mean, rstd, gamma, dx, dgamma, dbeta, R,
+                          C, pl.cs, act, alpha);
+}

@@ -284,7 +284,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // (cluster mode keeps this CTA's partial tile in the first 64 KB for its peers to read; staging goes behind it)
     const int stage_off = cl ? 128 * p.n_tile * 4 : 0;
     float* stage_tile = reinterpret_cast<float*>(smem + stage_off);
-    long long* row_off = reinterpret_cast<long long*>(smem + stage_off + 128 * (kMaxNTile + 4) * 4);
+    long long* row_off = reinterpret_cast<long long*>(smem + stage_off + 128 * (p.n_tile + 4) * 4);
     const int ld = p.n_tile + 4;
     row_off[m] = valid ? (long long)(orow - p.out) : -1;
     bool do_store = true;
@@ -624,7 +624,21 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, TcPlan& pl, void* ws,
     int fit = (int)((113 * 1024 - 1024) / (kABytes + p.n_tile * 128));
     p.stages = fit < 3 ? 3 : (fit > kMaxStages ? kMaxStages : fit);
   }
-  const size_t smem = (size_t)p.stages * (kABytes + p.n_tile * 128) + 1024;
+  {
+    // GG_TC_STAGES: cap the ring depth (3 stages = 97 KB: two CTAs — of the same or of two concurrent launches — share an SM)
+    static int forced = env_int("GG_TC_STAGES", 0);
+    if (forced >= 2 && forced < p.stages) p.stages = forced;
+  }
+  // Thread-block-cluster / DSMEM reduction (GG_TC_CLUSTER=1): correct (same tests pass) but measured no faster than the
+  // L2 workspace rendezvous on B200 (E.2 fwd 13.7 vs 14.2 us, E.3 fwd 26 vs 13 us: 8-CTA clusters of 197 KB CTAs place
+  // badly on 16-20-SM GPCs), so it is off by default.
+  p.cluster = (p.splits > 1 && p.splits <= 8 && env_int("GG_TC_CLUSTER", 0) != 0) ? 1 : 0;
+  if (p.cluster) p.stages = kMaxStages;        // the cluster epilogue parks a partial tile AND a staging tile in the ring
+  // the epilogue re-uses the ring as a [128][n_tile+4] staging tile + 128 row offsets
+  size_t ring = (size_t)p.stages * (kABytes + p.n_tile * 128);
+  const size_t staging = (size_t)128 * (p.n_tile + 4) * 4 + 128 * 8;
+  if (ring < staging) ring = staging;
+  const size_t smem = ring + 1024;
   static bool attr_set[3] = {false, false, false};
   if (!attr_set[MODE]) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -633,10 +647,6 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, TcPlan& pl, void* ws,
     attr_set[MODE] = true;
   }
   dim3 grid(pl.grid_x, p.splits);
-  // Thread-block-cluster / DSMEM reduction (GG_TC_CLUSTER=1): correct (same tests pass) but measured no faster than the
-  // L2 workspace rendezvous on B200 (E.2 fwd 13.7 vs 14.2 us, E.3 fwd 26 vs 13 us: 8-CTA clusters of 197 KB CTAs place
-  // badly on 16-20-SM GPCs), so it is off by default.
-  p.cluster = (p.splits > 1 && p.splits <= 8 && env_int("GG_TC_CLUSTER", 0) != 0) ? 1 : 0;
   if (p.cluster) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;

@@ -53,6 +53,9 @@ SIGNATURES = {
     "gg_bn_bwd_reduce": (c_i, [c_p] * 8 + [c_i, c_i, c_i, c_f, c_p]),
     "gg_bn_bwd_apply": (c_i, [c_p] * 8 + [c_i, c_f, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_p]),
     "gg_bn_fold_partials": (c_i, [c_p, c_i, c_p, c_i, c_p]),
+    "gg_bn_fused_supported": (c_i, [c_i, c_i]),
+    "gg_bn_fwd_fused": (c_i, [c_p, c_p, c_p, c_f, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_p]),
+    "gg_bn_bwd_fused": (c_i, [c_p] * 9 + [c_i, c_i, c_i, c_f, c_p]),
     "gg_unary": (c_i, [c_i, c_p, c_p, c_ll, c_f, c_f, c_p]),
     "gg_binary": (c_i, [c_i, c_p, c_p, c_p, C.POINTER(c_i), C.POINTER(c_i), C.POINTER(c_i), c_f, c_p]),
     "gg_reduce": (c_i, [c_i, c_p, c_p, c_i, c_i, c_i, c_p]),
@@ -86,6 +89,9 @@ SIGNATURES = {
     "gg_comm_alloc": (c_i, [c_i, C.POINTER(c_p), c_p]),
     "gg_comm_open": (c_i, [c_p, C.POINTER(c_p)]),
     "gg_allreduce_small": (c_i, [c_p, c_p, c_i, C.POINTER(c_p), c_i, c_i, c_i, c_p, c_p]),
+    "gg_trace_event_create": (c_i, [C.POINTER(c_p)]),
+    "gg_trace_event_record": (c_i, [c_p, c_p]),
+    "gg_trace_event_elapsed_us": (c_i, [c_p, c_p, C.POINTER(c_f)]),
     "gg_probe_tma_strided": (c_i, [c_p] + [c_i] * 11 + [c_p, c_p]),
     "gg_probe_umma_tf32": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
 }

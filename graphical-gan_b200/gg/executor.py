@@ -175,7 +175,8 @@ class Plan(object):
             self.has_random = True
             tick = rt.tick()
             self.steps.append(lambda st, tick=tick: cabi.call("gg_rng_tick", tick.data_ptr(), st))
-            self.groups.append(dict(start=0, end=1, reads=set(), writes="tick", barrier=False, collective=False))
+            self.groups.append(dict(start=0, end=1, reads=set(), writes="tick", barrier=False, collective=False, node=None,
+                                    part=(0, 1)))
         for node in self.order:
             s0 = len(self.steps)
             self._emit(node)
@@ -187,6 +188,7 @@ class Plan(object):
                 if len(self.steps) > s0:
                     self._add_groups(s0, len(self.steps), set(), "op%d" % f.id, barrier=True)
         self.graph = None
+        self.trace, self.trace_t0 = [], None
         self.kernel_launches = 0   # libgg_b200 kernels per run (counted at capture / eager launch)
         self.runs = 0
 
@@ -201,9 +203,9 @@ class Plan(object):
         reads = set(self.owner.get(i.id, i.id) for i in node.inputs)
         if node.op == "random":
             reads.add("tick")
-        self._add_groups(s0, len(self.steps), reads, node.id, barrier=False)
+        self._add_groups(s0, len(self.steps), reads, node.id, barrier=False, node=node)
 
-    def _add_groups(self, s0, end, reads, writes, barrier):
+    def _add_groups(self, s0, end, reads, writes, barrier, node=None):
         """one scheduling group per maximal run of kernel steps; a collective step inside a node (SyncBN statistics, the
         gradient bucket all-reduce) becomes its own group so the launch list can be cut there"""
         cuts = [i for i in range(s0, end) if getattr(self.steps[i], "is_collective", False)]
@@ -220,7 +222,8 @@ class Plan(object):
             last = k == len(ranges) - 1
             w = writes if last else "%s#%d" % (writes, k)
             r = set(reads) if prev is None else {prev}
-            self.groups.append(dict(start=a, end=b, reads=r, writes=w, barrier=barrier and prev is None, collective=coll))
+            self.groups.append(dict(start=a, end=b, reads=r, writes=w, barrier=barrier and prev is None, collective=coll,
+                                    node=node, part=(k, len(ranges))))
             prev = w
 
     # ---- graph walking ---------------------------------------------------------------------
@@ -530,15 +533,20 @@ class Plan(object):
         y = self._alloc(node)
         Cc = node.shape[-1]
         R = node.size // Cc
-        S = cabi.lib.gg_bn_slices(R, Cc)
-        part = self.rt.empty((S, 2, Cc))
         mean, rstd = self.rt.empty((Cc,)), self.rt.empty((Cc,))
         self.extra[(node.id, 1)], self.extra[(node.id, 2)] = mean, rstd
-        self.keep.append(part)
         act, alpha, eps = cabi.ACT[node.attrs["act"]], node.attrs["alpha"], node.attrs["eps"]
+        world = ggdist.world_size()
+        if self._bn_fused(R, Cc, world):
+            # statistics + normalise + activation in ONE launch (no cross-rank exchange needed)
+            xp, gp, bp, yp, mp, rp = (t.data_ptr() for t in (x, gamma, beta, y, mean, rstd))
+            self.steps.append(lambda st: cabi.call("gg_bn_fwd_fused", xp, gp, bp, eps, yp, mp, rp, R, Cc, act, alpha, st))
+            return
+        S = cabi.lib.gg_bn_slices(R, Cc)
+        part = self.rt.empty((S, 2, Cc))
+        self.keep.append(part)
         xp, pp, gp, bp, yp, mp, rp = (t.data_ptr() for t in (x, part, gamma, beta, y, mean, rstd))
         self.steps.append(lambda st: cabi.call("gg_bn_stats", xp, pp, R, Cc, st))
-        world = ggdist.world_size()
         if world > 1 and self.rt.sync_bn:
             folded = self.rt.empty((2, Cc))
             self.keep.append(folded)
@@ -550,18 +558,27 @@ class Plan(object):
         else:
             self.steps.append(lambda st: cabi.call("gg_bn_apply", xp, pp, S, float(R), gp, bp, eps, yp, mp, rp, R, Cc, act, alpha, st))
 
+    def _bn_fused(self, R, Cc, world):
+        return (world == 1 or not self.rt.sync_bn) and os.environ.get("GG_BN_FUSED", "1") != "0" and \
+            cabi.lib.gg_bn_fused_supported(R, Cc) == 1
+
     def _emit_bn_grad(self, node):
         gy, x, y, mean, rstd, gamma = (self._in(node, i) for i in range(6))
         dx = self._alloc(node)
         Cc = node.shape[-1]
         R = node.size // Cc
-        S = cabi.lib.gg_bn_slices(R, Cc)
-        part = self.rt.empty((S, 2, Cc))
         dgb = self.rt.empty((2, Cc))          # [dbeta ; dgamma]
-        self.keep.append(part)
         self.extra[(node.id, 1)] = dgb[Cc:]   # dgamma
         self.extra[(node.id, 2)] = dgb[:Cc]   # dbeta
         act, alpha = cabi.ACT[node.attrs["act"]], node.attrs["alpha"]
+        if self._bn_fused(R, Cc, ggdist.world_size()):
+            gyp, xp, yp, mp, rp, gp, dxp = (t.data_ptr() for t in (gy, x, y, mean, rstd, gamma, dx))
+            dgp, dbp = dgb.data_ptr() + 4 * Cc, dgb.data_ptr()
+            self.steps.append(lambda st: cabi.call("gg_bn_bwd_fused", gyp, xp, yp, mp, rp, gp, dxp, dgp, dbp, R, Cc, act, alpha, st))
+            return
+        S = cabi.lib.gg_bn_slices(R, Cc)
+        part = self.rt.empty((S, 2, Cc))
+        self.keep.append(part)
         gyp, xp, yp, mp, rp, gp, pp, dxp, dgbp = (t.data_ptr() for t in (gy, x, y, mean, rstd, gamma, part, dx, dgb))
         self.steps.append(lambda st: cabi.call("gg_bn_bwd_reduce", gyp, xp, yp, mp, rp, gp, None, pp, R, Cc, act, alpha, st))
         # local sums are the (local) parameter gradients; the data-parallel all-reduce of the gradient bucket sums them
@@ -676,54 +693,158 @@ class Plan(object):
         captured CUDA graph — most kernels of this workload are latency-bound and fill a fraction of the 148 SMs."""
         return self._schedule_range(range(len(self.groups)), n_streams)
 
+    def _group_cost(self, g):
+        """estimated duration (us) of a kernel group inside the graph, for the list scheduler; calibrated on CUPTI
+        timelines of the gmgan-CIFAR step (profiles/timeline_*): tensor-core conv / dense launches are dominated by a
+        fixed ~10 us of pipeline fill + split-K exchange, element-wise glue by the ~2 us dependent-launch latency"""
+        node = g.get("node")
+        n_k = g["end"] - g["start"]
+        if node is None:
+            return 16.0 if g["barrier"] else 2.0          # optimiser update / rng tick
+        mb = node.size * 4 / 1e6
+        op = node.op
+        if op == "conv":
+            a = node.attrs
+            gf = 2.0 * a["B"] * a["Ho"] * a["Wo"] * a["Co"] * a["Ci"] * a["k"] * a["k"] / 1e9
+            t = 10.0 + 3.0 * gf
+            if min(a["Ci"], a["Co"]) <= 4:
+                t += 10.0                                   # patch-matrix kernels around the GEMM
+            return t
+        if op == "matmul":
+            M, N = node.shape
+            K = node.inputs[0].shape[0] if node.attrs["ta"] else node.inputs[0].shape[1]
+            return 12.0 if (N % 32 == 0 and K % 32 == 0) else 8.0
+        if op == "bn":
+            return 4.0 + 1.5 * mb
+        if op == "bn_grad":
+            return 5.0 + 3.0 * mb
+        return 2.0 * n_k + 0.5 * mb
+
     def _schedule_range(self, idxs, n_streams):
-        producer, assign, waits, need_event = {}, {}, {}, set()
-        tail = [None] * n_streams
-        last_barrier = None
+        """Static list scheduling (HEFT-style) of the kernel groups `idxs` onto n_streams streams of one CUDA graph.
+
+        Groups become ready when all their producers are placed; among the ready ones the group with the longest
+        remaining dependency chain (bottom level, from the cost model above) goes first, onto the stream where it can
+        start earliest in a simulated timeline — preferring the stream of the producer it waits for, so that chains stay
+        on one stream and cross-stream edges (event waits) appear only where branches fork or join.  A stream runs its
+        groups in issue order, so a bad placement is a false dependency: the previous policy (continue the producer's
+        stream, else least-recently-used) left the Extractor's backward chain queued behind the Generator's although
+        the two are independent (CUPTI timeline, profiles/timeline_gen_r1_before.txt).
+        Returns (issue order, stream of each group, cross-stream waits, groups that need an event)."""
+        idxs = list(idxs)
+        pos = {gi: k for k, gi in enumerate(idxs)}
+        cost = {gi: self._group_cost(self.groups[gi]) for gi in idxs}
+        # dependencies: producers of what the group reads; an optimiser step (barrier) waits for everything before it and
+        # everything after it waits for the barrier
+        producer, deps, last_barrier, seen = {}, {}, None, []
         for gi in idxs:
             g = self.groups[gi]
-            deps = set(producer[o] for o in g["reads"] if o in producer)
+            d = set(producer[o] for o in g["reads"] if o in producer)
             if last_barrier is not None:
-                deps.add(last_barrier)
+                d.add(last_barrier)
             if g["barrier"]:
-                deps |= set(t for t in tail if t is not None)
-            cand = [s for s in range(n_streams) if tail[s] is not None and tail[s] in deps]
+                d |= set(seen)
+                last_barrier = gi
+            deps[gi] = d
+            producer[g["writes"]] = gi
+            seen.append(gi)
+        succ = {gi: [] for gi in idxs}
+        for gi in idxs:
+            for d in deps[gi]:
+                succ[d].append(gi)
+        bottom = {}
+        for gi in reversed(idxs):
+            bottom[gi] = cost[gi] + max([bottom[c] for c in succ[gi]] or [0.0])
+        if n_streams <= 1 or os.environ.get("GG_SCHED", "heft") == "order":
+            return self._schedule_in_order(idxs, deps, n_streams)
+        import heapq
+        indeg = {gi: len(deps[gi]) for gi in idxs}
+        ready = [(-bottom[gi], pos[gi], gi) for gi in idxs if indeg[gi] == 0]
+        heapq.heapify(ready)
+        free_at = [0.0] * n_streams
+        finish, assign, waits, need_event, order, issued = {}, {}, {}, set(), [], {}
+        sync_cost = 1.0                       # a cross-stream edge costs an event wait
+        while ready:
+            _, _, gi = heapq.heappop(ready)
+            best = None
+            for s in range(n_streams):
+                t = free_at[s]
+                for d in deps[gi]:
+                    t = max(t, finish[d] + (0.0 if assign[d] == s else sync_cost))
+                key = (t, 0 if any(assign[d] == s for d in deps[gi]) else 1, s)
+                if best is None or key < best[0]:
+                    best = (key, s, t)
+            _, s, t = best
+            assign[gi] = s
+            finish[gi] = t + cost[gi]
+            free_at[s] = finish[gi]
+            # only the latest cross-stream producers per foreign stream need a wait (stream order covers the earlier ones)
+            per_stream = {}
+            for d in deps[gi]:
+                q = assign[d]
+                if q != s and (q not in per_stream or issued[d] > issued[per_stream[q]]):
+                    per_stream[q] = d
+            w = sorted(per_stream.values(), key=lambda d: issued[d])
+            waits[gi] = w
+            need_event.update(w)
+            issued[gi] = len(order)
+            order.append(gi)
+            for c in succ[gi]:
+                indeg[c] -= 1
+                if indeg[c] == 0:
+                    heapq.heappush(ready, (-bottom[c], pos[c], c))
+        assert len(order) == len(idxs)
+        self.sched_estimate_us = max(finish.values()) if finish else 0.0
+        return order, assign, waits, need_event
+
+    def _schedule_in_order(self, idxs, deps, n_streams):
+        """the plan's own topological order; a group continues the stream of its most recent producer when that producer is
+        still the stream's tail, otherwise it takes the least recently used stream (GG_SCHED=order, and n_streams == 1)"""
+        assign, waits, need_event = {}, {}, set()
+        tail = [None] * n_streams
+        for gi in idxs:
+            d = deps[gi]
+            cand = [s for s in range(n_streams) if tail[s] is not None and tail[s] in d]
             if cand:
                 s = max(cand, key=lambda q: tail[q])
             else:
                 free = [q for q in range(n_streams) if tail[q] is None]
                 s = free[0] if free else min(range(n_streams), key=lambda q: tail[q])
-            w = sorted(d for d in deps if assign[d] != s)
+            w = sorted(x for x in d if assign[x] != s)
             need_event.update(w)
             assign[gi] = s
             waits[gi] = w
             tail[s] = gi
-            producer[g["writes"]] = gi
-            if g["barrier"]:
-                last_barrier = gi
-        return assign, waits, need_event
+        return list(idxs), assign, waits, need_event
 
     def _capture_range(self, idxs, n_streams):
         """capture the kernel groups `idxs` (no collectives among them) into one CUDA graph, spread over n_streams streams"""
         torch = _torch()
-        assign, waits, need_event = self._schedule_range(idxs, n_streams)
+        order, assign, waits, need_event = self._schedule_range(idxs, n_streams)
         g = torch.cuda.CUDAGraph()
         side = [torch.cuda.Stream() for _ in range(max(n_streams - 1, 0))]
         self.keep.append(side)
+        trace = os.environ.get("GG_TRACE", "0") == "1"      # tools/trace_step.py: timed event nodes around every group
         with torch.cuda.graph(g):
             cs = torch.cuda.current_stream()
             streams = [cs] + side
+            if trace:
+                self.trace_t0 = self._trace_event(cs.cuda_stream)
             for sd in side:
                 sd.wait_stream(cs)
             events = {}
-            for gi in idxs:
+            for gi in order:
                 grp = self.groups[gi]
                 st = streams[assign[gi]]
                 for d in waits[gi]:
                     st.wait_event(events[d])
                 sp = st.cuda_stream
+                if trace:
+                    ta = self._trace_event(sp)
                 for f in self.steps[grp["start"]:grp["end"]]:
                     f(sp)
+                if trace:
+                    self.trace.append((gi, assign[gi], ta, self._trace_event(sp), list(waits[gi])))
                 if gi in need_event:
                     ev = torch.cuda.Event()
                     ev.record(st)
@@ -732,6 +853,19 @@ class Plan(object):
                 cs.wait_stream(sd)
             self.keep.append(events)
         return g
+
+    @staticmethod
+    def _trace_event(stream_ptr):
+        ev = C.c_void_p()
+        cabi.call("gg_trace_event_create", C.byref(ev))
+        cabi.call("gg_trace_event_record", ev, stream_ptr)
+        return ev
+
+    @staticmethod
+    def trace_elapsed_us(a, b):
+        us = C.c_float()
+        cabi.call("gg_trace_event_elapsed_us", a, b, C.byref(us))
+        return us.value
 
     def _capture_segments(self):
         """launch list -> [CUDA graph | eager collective | CUDA graph | ...]: NCCL collectives stay outside stream capture

@@ -123,6 +123,16 @@ int gg_bn_bwd_apply(const float* dy, const float* x, const float* y, const float
                     int R, int C, int act, float alpha, void* stream);
 /* sum S partial slices [S,2,C] into out[2,C] (used before the SyncBN all-reduce) */
 int gg_bn_fold_partials(const float* partial, int S, float* out, int C, void* stream);
+/* Single-kernel forms of the same two operations (batch statistics computed inside; no partial buffers): one
+ * thread-block cluster per group of channels, rows split over the cluster's CTAs, partial sums exchanged through
+ * distributed shared memory.  Used whenever the statistics need no cross-rank exchange (single GPU, or SyncBN off).
+ * gg_bn_fused_supported: 1 when (R, C) is handled (C % 4 == 0), else use the multi-kernel entry points above. */
+int gg_bn_fused_supported(int R, int C);
+int gg_bn_fwd_fused(const float* x, const float* gamma, const float* beta, float eps,
+                    float* y, float* mean_out, float* rstd_out, int R, int C, int act, float alpha, void* stream);
+int gg_bn_bwd_fused(const float* dy, const float* x, const float* y, const float* mean, const float* rstd,
+                    const float* gamma, float* dx, float* dgamma, float* dbeta,
+                    int R, int C, int act, float alpha, void* stream);
 
 /* ---- elementwise / layout glue (script-level tf.* ops, SURVEY.md §8(a) a6,a7,a13) -------- */
 #define GG_U_COPY 0
@@ -260,6 +270,11 @@ int gg_probe_umma_tf32(const float* A, const float* Bm, float* D, int N, int K, 
  * %globaltimer timeline (slot 0 start, 1+i TMA issue of k-block i, 64+i operands landed, 128 accumulator ready,
  * 129 partial written, 131 epilogue done).  NULL disables it. */
 int gg_debug_set_buffer(void* device_buffer_256_int64);
+
+/* ---- tooling: timed event nodes inside a captured CUDA graph (tools/trace_step.py) ------ */
+int gg_trace_event_create(void** event_out);
+int gg_trace_event_record(void* event, void* stream);   /* cudaEventRecordExternal: an event-record node under capture */
+int gg_trace_event_elapsed_us(void* start, void* end, float* us_out);
 
 #ifdef __cplusplus
 }

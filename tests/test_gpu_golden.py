@@ -70,6 +70,17 @@ def test_batchnorm_golden(name):
     U.assert_close(back(dx), torch.from_numpy(d["out_dx"]), 1e-4, name + " dx")
     U.assert_close(dg, torch.from_numpy(d["out_dscale"]).reshape(-1), 1e-4, name + " dscale")
     U.assert_close(db, torch.from_numpy(d["out_doffset"]).reshape(-1), 1e-4, name + " doffset")
+    # single-kernel forms
+    y2, dx2 = torch.empty(R, Cc, device="cuda"), torch.empty(R, Cc, device="cuda")
+    mean2, rstd2, dg2, db2 = (torch.empty(Cc, device="cuda") for _ in range(4))
+    cabi.call("gg_bn_fwd_fused", xd.data_ptr(), gd.data_ptr(), bd.data_ptr(), 1e-5, y2.data_ptr(), mean2.data_ptr(),
+              rstd2.data_ptr(), R, Cc, 0, 0.0, st)
+    cabi.call("gg_bn_bwd_fused", gyd.data_ptr(), xd.data_ptr(), y2.data_ptr(), mean2.data_ptr(), rstd2.data_ptr(), gd.data_ptr(),
+              dx2.data_ptr(), dg2.data_ptr(), db2.data_ptr(), R, Cc, 0, 0.0, st)
+    U.assert_close(back(y2), torch.from_numpy(d["out_y"]), 1e-5, name + " fused y")
+    U.assert_close(back(dx2), torch.from_numpy(d["out_dx"]), 1e-4, name + " fused dx")
+    U.assert_close(dg2, torch.from_numpy(d["out_dscale"]).reshape(-1), 1e-4, name + " fused dscale")
+    U.assert_close(db2, torch.from_numpy(d["out_doffset"]).reshape(-1), 1e-4, name + " fused doffset")
 
 
 def test_adam_golden():

@@ -121,7 +121,8 @@ def test_gemm(case):
 
 
 @pytest.mark.parametrize("R,Cc,act", [(64, 4096, "relu"), (64 * 8 * 8, 128, "relu"), (64 * 16 * 16, 64, None),
-                                      (64 * 4 * 4, 256, "leaky"), (50, 7, None), (1000, 33, "relu")])
+                                      (64 * 4 * 4, 256, "leaky"), (50, 7, None), (1000, 33, "relu"),
+                                      (50 * 14 * 14, 64, "leaky"), (50 * 7 * 7, 128, None), (37, 12, "relu"), (3, 4, None)])
 def test_batchnorm_fwd_bwd(R, Cc, act):
     U, cabi = _mods()
     g = torch.Generator().manual_seed(5 + R)
@@ -159,6 +160,21 @@ def test_batchnorm_fwd_bwd(R, Cc, act):
     U.assert_close(dxd, dx, 1e-4, "bn dx")
     U.assert_close(dgd, dg, 1e-4, "bn dgamma")
     U.assert_close(dbd, db, 1e-4, "bn dbeta")
+    # the single-kernel (thread-block-cluster) forms used by the single-GPU plan: same contract, no partial buffers
+    assert cabi.lib.gg_bn_fused_supported(R, Cc) == (1 if Cc % 4 == 0 else 0)
+    if Cc % 4 == 0:
+        y2, mean2, rstd2 = torch.empty(R, Cc, device="cuda"), torch.empty(Cc, device="cuda"), torch.empty(Cc, device="cuda")
+        cabi.call("gg_bn_fwd_fused", cabi.ptr(xd), cabi.ptr(gd), cabi.ptr(bd), 1e-5, cabi.ptr(y2), cabi.ptr(mean2),
+                  cabi.ptr(rstd2), R, Cc, cabi.ACT[act], 0.2, st)
+        U.assert_close(y2, y, 1e-5, "bn fused fwd")
+        U.assert_close(mean2, mean, 1e-5, "bn fused mean")
+        U.assert_close(rstd2, rstd, 1e-5, "bn fused rstd")
+        dx2, dg2, db2 = torch.empty(R, Cc, device="cuda"), torch.empty(Cc, device="cuda"), torch.empty(Cc, device="cuda")
+        cabi.call("gg_bn_bwd_fused", cabi.ptr(gyd), cabi.ptr(xd), cabi.ptr(y2), cabi.ptr(mean2), cabi.ptr(rstd2), cabi.ptr(gd),
+                  cabi.ptr(dx2), cabi.ptr(dg2), cabi.ptr(db2), R, Cc, cabi.ACT[act], 0.2, st)
+        U.assert_close(dx2, dx, 1e-4, "bn fused dx")
+        U.assert_close(dg2, dg, 1e-4, "bn fused dgamma")
+        U.assert_close(db2, db, 1e-4, "bn fused dbeta")
 
 
 def test_unary_binary_reduce_softmax():
