@@ -410,6 +410,12 @@ extern "C" size_t gg_conv2d_wgrad_workspace(int B, int H, int W, int Ci, int Co,
   return direct > tc ? direct : tc;
 }
 
+namespace gg { void conv_tc_set_stage_cap(int n); }
+extern "C" int gg_set_tc_stages(int n) {
+  gg::conv_tc_set_stage_cap(n);
+  return GG_OK;
+}
+
 extern "C" int gg_set_tc_max_ctas(int n) {
   conv_tc_set_max_ctas(n);
   return GG_OK;

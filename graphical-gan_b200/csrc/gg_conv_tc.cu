@@ -516,6 +516,7 @@ int pick_n_tile(int n) {
 }
 
 int g_tc_max_ctas = kNumSMs;
+int g_tc_stage_cap = 0;
 
 int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
@@ -624,11 +625,9 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, TcPlan& pl, void* ws,
     int fit = (int)((113 * 1024 - 1024) / (kABytes + p.n_tile * 128));
     p.stages = fit < 3 ? 3 : (fit > kMaxStages ? kMaxStages : fit);
   }
-  {
-    // GG_TC_STAGES: cap the ring depth (3 stages = 97 KB: two CTAs — of the same or of two concurrent launches — share an SM)
-    static int forced = env_int("GG_TC_STAGES", 0);
-    if (forced >= 2 && forced < p.stages) p.stages = forced;
-  }
+  // ring-depth cap (gg_set_tc_stages): 3 stages = 97 KB, so two CTAs — of the same or of two concurrent launches on
+  // different streams — share an SM; the main loop is TMA-issue-bound, not latency-bound, and loses nothing
+  if (g_tc_stage_cap >= 2 && g_tc_stage_cap < p.stages) p.stages = g_tc_stage_cap;
   // Thread-block-cluster / DSMEM reduction (GG_TC_CLUSTER=1): correct (same tests pass) but measured no faster than the
   // L2 workspace rendezvous on B200 (E.2 fwd 13.7 vs 14.2 us, E.3 fwd 26 vs 13 us: 8-CTA clusters of 197 KB CTAs place
   // badly on 16-20-SM GPCs), so it is off by default.
@@ -771,6 +770,8 @@ int conv_tc_wgrad(const float* x, const float* dy, float* dw, int B, int H, int 
   *handled = true;
   return GG_OK;
 }
+
+void conv_tc_set_stage_cap(int n) { g_tc_stage_cap = n; }
 
 void conv_tc_set_max_ctas(int n) { g_tc_max_ctas = n < 1 ? 1 : (n > kNumSMs ? kNumSMs : n); }
 

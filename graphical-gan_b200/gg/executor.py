@@ -167,6 +167,7 @@ class Plan(object):
         # then overlap); workspace sizes depend on it, so it is fixed before emission
         self.n_streams = int(os.environ.get("GG_STREAMS", "6")) if rt.use_cuda_graph else 1
         cabi.call("gg_set_tc_max_ctas", int(os.environ.get("GG_TC_MAX_CTAS", "74" if self.n_streams > 1 else "148")))
+        cabi.call("gg_set_tc_stages", int(os.environ.get("GG_TC_STAGES", "3" if self.n_streams > 1 else "0")))
         # scheduling metadata: one group per node that launches kernels; `owner` resolves views (reshape / aux / fed)
         # to the node whose kernels produce the storage
         self.groups = []     # dicts: start, end, reads (owner ids), writes (owner id), barrier
@@ -177,6 +178,7 @@ class Plan(object):
             self.steps.append(lambda st, tick=tick: cabi.call("gg_rng_tick", tick.data_ptr(), st))
             self.groups.append(dict(start=0, end=1, reads=set(), writes="tick", barrier=False, collective=False, node=None,
                                     part=(0, 1)))
+        self._plan_inplace_concats()
         for node in self.order:
             s0 = len(self.steps)
             self._emit(node)
@@ -192,15 +194,23 @@ class Plan(object):
         self.kernel_launches = 0   # libgg_b200 kernels per run (counted at capture / eager launch)
         self.runs = 0
 
+    def _owners(self, t):
+        return self.owner.get(t.id, frozenset([t.id]))
+
     def _note_group(self, node, s0):
-        if len(self.steps) == s0:        # no kernels: a view or a leaf
-            if node.inputs and node.op in ALIAS_OPS and node.id not in self.fed:
-                self.owner[node.id] = self.owner.get(node.inputs[0].id, node.inputs[0].id)
+        if len(self.steps) == s0:        # no kernels: a leaf, or a view (reshape, axis-0 slice, in-place concat, ...)
+            if node.inputs and node.id not in self.fed:
+                own = frozenset()
+                for i in node.inputs:
+                    own |= self._owners(i)
+                self.owner[node.id] = own
             else:
-                self.owner[node.id] = node.id
+                self.owner[node.id] = frozenset([node.id])
             return
-        self.owner[node.id] = node.id
-        reads = set(self.owner.get(i.id, i.id) for i in node.inputs)
+        self.owner[node.id] = frozenset([node.id])
+        reads = set()
+        for i in node.inputs:
+            reads |= self._owners(i)
         if node.op == "random":
             reads.add("tick")
         self._add_groups(s0, len(self.steps), reads, node.id, barrier=False, node=node)
@@ -255,9 +265,57 @@ class Plan(object):
 
     # ---- emission ---------------------------------------------------------------------------
     def _alloc(self, node):
-        t = self.rt.empty(node.shape, node.dtype)
+        if node.id in self.placed:       # this node's output lives inside the buffer of an axis-0 concat (zero-copy concat)
+            cid, off = self.placed[node.id]
+            t = self._concat_storage(cid)[off:off + max(node.size, 1)]
+        else:
+            t = self.rt.empty(node.shape, node.dtype)
         self.buf[node.id] = t
         return t
+
+    # ---- zero-copy row concatenation / row slices --------------------------------------------------------------------
+    # The sibling-batching rewrite (gg/rewrite.py) joins the inputs of the two discriminator towers along axis 0 and
+    # splits the batched result again.  Both are free here: the producers of a concat's pieces write straight into the
+    # concat's buffer, and an axis-0 slice of a contiguous tensor is a pointer offset.
+    OWN_OUTPUT_OPS = ("unary", "binary", "broadcast", "add_n", "cast", "reduce", "softmax", "softmax_grad", "one_hot", "random",
+                      "transpose", "pad", "tile", "matmul", "conv", "bn", "bn_grad")
+
+    @staticmethod
+    def _is_row_concat(node):
+        return node.op == "concat" and node.dtype == float32 and prod(node.shape[:node.attrs["axis"]]) == 1
+
+    @staticmethod
+    def _slice_is_view(node):
+        a = node.attrs
+        shp = node.inputs[0].shape
+        inner = prod(shp[a["axis"] + 1:])
+        return prod(shp[:a["axis"]]) == 1 and (a["start"] * inner) % 64 == 0 and node.dtype == float32
+
+    def _plan_inplace_concats(self):
+        self.placed, self.inplace_concat, self._concat_bufs = {}, set(), {}
+        if os.environ.get("GG_INPLACE_CONCAT", "1") == "0":
+            return
+        for node in self.order:
+            if not self._is_row_concat(node) or node.id in self.fed:
+                continue
+            off, plan, ok = 0, [], True
+            for inp in node.inputs:
+                if inp.op not in self.OWN_OUTPUT_OPS or inp.id in self.fed or inp.id in self.placed or inp.dtype != float32 \
+                        or off % 64 != 0 or any(inp is q for q, _ in plan) or (inp.op == "slice" and self._slice_is_view(inp)):
+                    ok = False
+                    break
+                plan.append((inp, off))
+                off += inp.size
+            if ok:
+                for inp, o in plan:
+                    self.placed[inp.id] = (node.id, o)
+                self.inplace_concat.add(node.id)
+
+    def _concat_storage(self, cid):
+        if cid not in self._concat_bufs:
+            node = next(n for n in self.order if n.id == cid)
+            self._concat_bufs[cid] = self.rt.empty(node.shape, node.dtype)
+        return self._concat_bufs[cid]
 
     def _ws(self, nbytes):
         torch = _torch()
@@ -445,6 +503,9 @@ class Plan(object):
         self.steps.append(lambda st: cabi.call("gg_transpose4", xp, yp, dims, p4, st))
 
     def _emit_concat(self, node):
+        if node.id in self.inplace_concat:
+            self.buf[node.id] = self._concat_storage(node.id)      # the pieces were written in place by their producers
+            return
         out = self._alloc(node)
         axis = node.attrs["axis"]
         outer = prod(node.shape[:axis])
@@ -460,9 +521,13 @@ class Plan(object):
             off += cols
 
     def _emit_slice(self, node):
-        x, out = self._in(node, 0), self._alloc(node)
         axis, start, size = node.attrs["axis"], node.attrs["start"], node.attrs["size"]
         shp = node.inputs[0].shape
+        if self._slice_is_view(node) and node.id not in self.placed and os.environ.get("GG_INPLACE_CONCAT", "1") != "0":
+            inner = prod(shp[axis + 1:])
+            self.buf[node.id] = self._in(node, 0)[start * inner:(start + size) * inner]   # rows of a contiguous tensor: a view
+            return
+        x, out = self._in(node, 0), self._alloc(node)
         outer, inner = prod(shp[:axis]), prod(shp[axis + 1:])
         src_ld, cols = shp[axis] * inner, size * inner
         sp, dp = x.data_ptr() + start * inner * 4, out.data_ptr()

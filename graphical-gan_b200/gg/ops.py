@@ -299,6 +299,19 @@ def add_n(ts):
         return ts[0]
     if all(t.op == "transpose" and t.attrs["perm"] == ts[0].attrs["perm"] for t in ts):
         return transpose(add_n([t.inputs[0] for t in ts]), ts[0].attrs["perm"])
+    if all(t.op == "pad" and t.attrs["axis"] == ts[0].attrs["axis"] and t.attrs["total"] == ts[0].attrs["total"] for t in ts):
+        # gradients of the slices that tile a tensor (the two halves of a sibling-batched tower, gg/rewrite.py): the sum of
+        # zero-padded pieces with disjoint, covering extents IS their concatenation — no zero fill, no add
+        axis, total = ts[0].attrs["axis"], ts[0].attrs["total"]
+        parts = sorted(ts, key=lambda t: t.attrs["start"])
+        pos = 0
+        for t in parts:
+            if t.attrs["start"] != pos:
+                break
+            pos += t.inputs[0].shape[axis]
+        else:
+            if pos == total:
+                return concat([t.inputs[0] for t in parts], axis)
     shape = ts[0].shape
     for t in ts:
         if tuple(t.shape) != tuple(shape):
@@ -648,10 +661,34 @@ def _grad_bn_grad(n, g, need):
 def _grad_concat(n, g, need):
     axis = n.attrs["axis"]
     out, start = [], 0
-    for inp in n.inputs:
-        out.append(slice_axis(g, axis, start, inp.shape[axis]))
-        start += inp.shape[axis]
+    # Row-concatenated inputs of a sibling-batched tower where only SOME pieces need a gradient (D(fake_x) vs D(real_x):
+    # real_x is data): do not compute the producing conv-dgrad / dense-dgrad for rows nobody reads — run it on the row
+    # slice of ITS input instead (an axis-0 slice is a zero-copy view).
+    partial_rows = axis == 0 and not all(need) and g.op in ("conv", "matmul") and \
+        (g.attrs.get("mode", "fwd") in ("fwd", "dgrad")) and not g.attrs.get("ta", False)
+    for inp, nd in zip(n.inputs, need):
+        size = inp.shape[axis]
+        if not nd:
+            out.append(None)
+        elif partial_rows:
+            out.append(_rows_of(g, start, size))
+        else:
+            out.append(slice_axis(g, axis, start, size))
+        start += size
     return out
+
+
+def _rows_of(g, start, size):
+    """rows [start, start+size) of a conv / dense node, computed from the same rows of its activation input"""
+    x = slice_axis(g.inputs[0], 0, start, size)
+    if g.op == "conv":
+        geom = _geom(g)
+        geom["B"] = size
+        t = conv(g.attrs["mode"], x, g.inputs[1], geom, g.inputs[2] if len(g.inputs) == 3 else None)
+    else:
+        t = matmul(x, g.inputs[1], False, g.attrs["tb"], g.inputs[2] if len(g.inputs) == 3 else None)
+    t.attrs["act"], t.attrs["alpha"] = g.attrs["act"], g.attrs["alpha"]
+    return t
 
 
 def _grad_tile(n, g, need):

@@ -9,6 +9,7 @@ vegan :194-223, vegan_wgan_gp :225-244, local_ep_dynamic :246-304, weighted_loca
 import tensorflow as tf
 
 import tflib as lib
+from gg.rewrite import batch_pairs as _siblings   # D(fake) and D(real) share weights: one batched application (gg/rewrite.py)
 
 
 def _bce(logits, label):
@@ -32,6 +33,7 @@ def _adam_ops(gen_cost, disc_cost, gen_params, disc_params, **kw):
 
 
 def wali(disc_fake, disc_real, gen_params, disc_params, lr=5e-5):
+    disc_fake, disc_real = _siblings(disc_fake, disc_real)
     gen_cost = -tf.reduce_mean(disc_fake) - tf.reduce_mean(disc_real)     # sic: the reference negates both (:5)
     disc_cost = tf.reduce_mean(disc_fake) - tf.reduce_mean(disc_real)
     gen_train_op = tf.train.RMSPropOptimizer(learning_rate=lr).minimize(gen_cost, var_list=gen_params)
@@ -42,6 +44,7 @@ def wali(disc_fake, disc_real, gen_params, disc_params, lr=5e-5):
 
 
 def wali_gp(disc_fake, disc_real, gradient_penalty, gen_params, disc_params, lr=1e-4):
+    disc_fake, disc_real = _siblings(disc_fake, disc_real)
     gen_cost = -tf.reduce_mean(disc_fake) + tf.reduce_mean(disc_real)
     disc_cost = tf.reduce_mean(disc_fake) - tf.reduce_mean(disc_real)
     disc_cost += gradient_penalty
@@ -50,6 +53,7 @@ def wali_gp(disc_fake, disc_real, gradient_penalty, gen_params, disc_params, lr=
 
 
 def ali(disc_fake, disc_real, gen_params, disc_params, lr=2e-4, beta1=0.5, beta2=0.999, s_f=None):
+    disc_fake, disc_real = _siblings(disc_fake, disc_real)
     gen_cost = _gen_term(disc_fake, disc_real)
     disc_cost = _disc_term(disc_fake, disc_real)
     if s_f is not None:
@@ -72,6 +76,7 @@ def _local_sums(disc_fake_list, disc_real_list, ratio_list=None):
 
 def local_ep(disc_fake_list, disc_real_list, gen_params, disc_params, lr=2e-4, beta1=0.5, beta2=.999, s_f=None):
     """the north-star objective: one (fake, real) logit pair per local discriminator, costs averaged over the list"""
+    disc_fake_list, disc_real_list = _siblings(disc_fake_list, disc_real_list)
     gen_cost, disc_cost, _, _ = _local_sums(disc_fake_list, disc_real_list)
     if s_f is not None:
         gen_cost += s_f
@@ -82,6 +87,7 @@ def local_ep(disc_fake_list, disc_real_list, gen_params, disc_params, lr=2e-4, b
 
 
 def local_epce(disc_fake_list, disc_real_list, rec_penalty, gen_params, disc_params, lr=2e-4, beta1=0.5, s_f=None):
+    disc_fake_list, disc_real_list = _siblings(disc_fake_list, disc_real_list)
     gen_cost, disc_cost, _, _ = _local_sums(disc_fake_list, disc_real_list)
     if s_f is not None:
         gen_cost += s_f
@@ -93,6 +99,7 @@ def local_epce(disc_fake_list, disc_real_list, rec_penalty, gen_params, disc_par
 
 
 def alice(disc_fake, disc_real, rec_penalty, gen_params, disc_params, lr=2e-4, beta1=0.5, s_f=None):
+    disc_fake, disc_real = _siblings(disc_fake, disc_real)
     gen_cost = _gen_term(disc_fake, disc_real)
     if s_f is not None:
         gen_cost += s_f
@@ -103,6 +110,7 @@ def alice(disc_fake, disc_real, rec_penalty, gen_params, disc_params, lr=2e-4, b
 
 
 def vegan(disc_fake, disc_real, rec_penalty, gen_params, disc_params, lamb, lr=2e-4, beta1=.5, s_f=None):
+    disc_fake, disc_real = _siblings(disc_fake, disc_real)
     gen_cost = _bce(disc_fake, 1)
     if s_f is not None:
         gen_cost += s_f
@@ -115,6 +123,7 @@ def vegan(disc_fake, disc_real, rec_penalty, gen_params, disc_params, lamb, lr=2
 
 
 def vegan_wgan_gp(disc_fake, disc_real, rec_penalty, gradient_penalty, gen_params, disc_params, lamb, lr=2e-4, beta1=.5):
+    disc_fake, disc_real = _siblings(disc_fake, disc_real)
     gen_cost = -tf.reduce_mean(disc_fake) + tf.reduce_mean(disc_real)
     gen_cost *= lamb
     gen_cost += rec_penalty
@@ -127,6 +136,8 @@ def vegan_wgan_gp(disc_fake, disc_real, rec_penalty, gradient_penalty, gen_param
 
 def local_ep_dynamic(disc_fake_zz, disc_real_zz, disc_fake_xz, disc_real_xz, gen_params, disc_params, lr=2e-4, beta1=0.5,
                      beta2=.999, rec_penalty=None):
+    disc_fake_zz, disc_real_zz = _siblings(disc_fake_zz, disc_real_zz)
+    disc_fake_xz, disc_real_xz = _siblings(disc_fake_xz, disc_real_xz)
     gen_cost, disc_cost, _, _ = _local_sums(disc_fake_zz, disc_real_zz)
     if len(disc_fake_zz) > 0:
         gen_cost /= (len(disc_fake_zz) + 1)
@@ -142,6 +153,7 @@ def local_ep_dynamic(disc_fake_zz, disc_real_zz, disc_fake_xz, disc_real_xz, gen
 def weighted_local_epce(disc_fake_list, disc_real_list, ratio_list, gen_params, disc_params, lr=2e-4, beta1=0.5,
                         rec_penalty=None):
     """SSGAN objective (ssgan_inference_moving_mnist.py:547): entries weighted by ratio_list, no division"""
+    disc_fake_list, disc_real_list = _siblings(disc_fake_list, disc_real_list)
     assert len(disc_fake_list) == ratio_list.shape[0]
     gen_cost, disc_cost, gen_debug_list, disc_debug_list = _local_sums(disc_fake_list, disc_real_list, ratio_list)
     if rec_penalty is not None:

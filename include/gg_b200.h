@@ -56,6 +56,8 @@ int gg_last_backend(void);
 /* upper bound on the CTAs one tensor-core conv / dense launch may occupy (split-K is sized to it).  148 = the whole
  * GPU (default, best for a kernel running alone); the multi-stream executor sets 74 so two launches can overlap. */
 int gg_set_tc_max_ctas(int n);
+/* cap the operand-ring depth of the tensor-core kernels (0 = as deep as fits; 3 lets two CTAs share an SM) */
+int gg_set_tc_stages(int n);
 
 /* ---- activation codes ------------------------------------------------------------ */
 #define GG_ACT_NONE 0

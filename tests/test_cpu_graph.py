@@ -46,3 +46,74 @@ def test_gmgan_graph_gradients_match_oracle_autograd(batch):
             scale = np.abs(ref).max() + 1e-30
             # (a bias in front of batch norm has an exactly-zero gradient: absolute floor)
             assert np.abs(got - ref.reshape(got.shape)).max() <= 1e-8 * scale + 1e-13, name
+
+
+# ---- sibling batching (gg/rewrite.py): the rewritten graph computes the same costs and parameter gradients ------------
+def _all_nodes(roots):
+    from gg.ops import toposort
+    return toposort([r for r in roots if r is not None])
+
+
+def _eval_family(build, batching, seed):
+    """build the family's graph with sibling batching on/off; evaluate costs + every parameter gradient of both train ops
+    with all placeholders and random draws fed from one seeded stream (in creation order, identical for both builds)"""
+    import os
+    import tensorflow as tf
+    import tflib as lib
+    os.environ["GG_BATCH_SIBLINGS"] = "1" if batching else "0"
+    try:
+        tf.reset_default_graph()
+        lib.delete_all_params()
+        np.random.seed(seed)
+        g = build()
+    finally:
+        os.environ.pop("GG_BATCH_SIBLINGS", None)
+    grads = {}
+    for tag, op in (("gen", g.gen_train_op), ("disc", g.disc_train_op)):
+        for v, d in zip(op.attrs["vars"], op.deps):
+            if d is not None:
+                grads[(tag, v.name)] = d
+    roots = [g.gen_cost, g.disc_cost] + list(grads.values())
+    nodes = _all_nodes(roots)
+    rs = np.random.RandomState(99)
+    feeds = {}
+    for n in sorted(nodes, key=lambda n: n.id):
+        if n.op == "placeholder" or (n.op == "random" and n.attrs["kind"] != "categorical"):
+            if n.dtype.name == "int32":
+                feeds[n] = rs.randint(0, 10 if n.size < 4096 else 256, size=tuple(n.shape))
+            elif n.op == "placeholder" or n.attrs["kind"] == "uniform":
+                feeds[n] = rs.uniform(0.05, 0.95, size=tuple(n.shape))
+            else:
+                feeds[n] = rs.randn(*n.shape)
+        elif n.op == "random":
+            feeds[n] = rs.randint(0, n.inputs[0].size, size=tuple(n.shape))
+    it = Interp(feeds)
+    n_heavy = sum(1 for n in nodes if n.op in ("conv", "matmul"))
+    vals = {k: it.run(v) for k, v in grads.items()}
+    return float(it.run(g.gen_cost)), float(it.run(g.disc_cost)), vals, n_heavy
+
+
+def _families():
+    import gmgan_inference_cifar10 as C
+    import gan_inference_svhn as V
+    import gan_inference_face as F
+    import ssgan_inference_moving_mnist as M
+    return {
+        "gmgan_cifar10_local_ep": lambda: C.build_graph(BATCH_SIZE=4),
+        "gan_svhn_wali_gp": lambda: V.build_graph(MODE='wali-gp', BATCH_SIZE=4),
+        "gan_face_ali": lambda: F.build_graph(BATCH_SIZE=2),
+        "ssgan_moving_mnist": lambda: M.build_graph(BATCH_SIZE=2, LEN=3),
+    }
+
+
+@pytest.mark.parametrize("family", ["gmgan_cifar10_local_ep", "gan_svhn_wali_gp", "gan_face_ali", "ssgan_moving_mnist"])
+def test_sibling_batching_preserves_costs_and_gradients(family):
+    build = _families()[family]
+    g0, d0, v0, h0 = _eval_family(build, False, 7)
+    g1, d1, v1, h1 = _eval_family(build, True, 7)
+    assert h1 < h0, "batching should remove conv/dense launches (%d -> %d)" % (h0, h1)
+    assert abs(g0 - g1) < 1e-9 * max(1, abs(g0)) and abs(d0 - d1) < 1e-9 * max(1, abs(d0))
+    assert set(v0) == set(v1)
+    for k in v0:
+        scale = np.abs(v0[k]).max() + 1e-30
+        assert np.abs(v0[k] - v1[k]).max() <= 1e-8 * scale + 1e-13, k
