@@ -16,7 +16,7 @@ using namespace gg;
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;
 constexpr int kMaxCw = 32;
 
 struct BnPlan {
@@ -33,7 +33,7 @@ BnPlan bn_plan(int R, int C) {
   if (p.cw > C) p.cw = (C >= 8) ? 8 : 4;
   p.groups = ceil_div(C, p.cw);
   p.cs = 1;
-  while (p.cs < 8 && p.groups * p.cs < 64 && R / (p.cs * 2) >= 64) p.cs *= 2;
+  while (p.cs < 8 && p.groups * p.cs < 128 && R / (p.cs * 2) >= 128) p.cs *= 2;
   p.ok = true;
   return p;
 }

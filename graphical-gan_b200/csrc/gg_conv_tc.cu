@@ -42,6 +42,7 @@ struct TcParams {
   int splits;
   int stages;                 // depth of the operand ring (as many as fit)
   int cluster;                // 1: the `splits` CTAs of a tile form a thread-block cluster and reduce through DSMEM
+  int bulk;                   // 1: split-K slices come back through cp.async.bulk (copy engine) instead of per-thread L2 loads
   int act;
   float alpha;
   float* out;
@@ -86,6 +87,13 @@ __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t addr) {
   return v;
 }
 
+// 1-D bulk copy global -> shared through the async proxy (copy engine), completion counted on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 #ifdef GG_TIMELINE
 #define GG_DBG(slot) do { if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0) p.dbg[slot] = gtime(); } while (0)
 #else
@@ -105,6 +113,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   const int kStages = p.stages;
   __shared__ uint32_t tmem_base_sh;
+  __shared__ long long s_row_off[128];                  // element offset of each accumulator row's output row (-1: masked)
+  __shared__ __align__(16) float s_bias[kMaxNTile];   // bias slice of this n-tile (read from HBM/L2 once, before the accumulator is ready)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int stage_bytes = kABytes + p.n_tile * 128;
@@ -259,6 +269,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
     const int m = quad * 32 + lane;               // accumulator row
     const int et = threadIdx.x - 64;              // 0..127
+    // While the main loop runs these warps are idle: fetch the bias slice now.  (Loading it from global memory inside the
+    // read-out loop cost one exposed L2 round trip per 32-column chunk — the tcgen05.ld asm is a compiler barrier —
+    // ~2 us of a ~3.4 us epilogue on the timeline.)
+    const bool has_bias = (MODE != 2) && p.bias != nullptr;
+    if (has_bias && et < p.n_tile) s_bias[et] = p.bias[nt * p.n_tile + et];
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     mbar_wait(&accum_bar, 0);
     tc_fence_after();
     if (et == 0) GG_DBG(128);
@@ -284,19 +300,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // (cluster mode keeps this CTA's partial tile in the first 64 KB for its peers to read; staging goes behind it)
     const int stage_off = cl ? 128 * p.n_tile * 4 : 0;
     float* stage_tile = reinterpret_cast<float*>(smem + stage_off);
-    long long* row_off = reinterpret_cast<long long*>(smem + stage_off + 128 * (p.n_tile + 4) * 4);
-    const int ld = p.n_tile + 4;
+    long long* row_off = s_row_off;
+    int ld = p.n_tile + 4;                        // staging row pitch (floats)
+    int col0 = 0;                                 // float4 column of the tile held in staging column 0
     row_off[m] = valid ? (long long)(orow - p.out) : -1;
     bool do_store = true;
     // activation / bias parameters hoisted into registers: none / relu / leaky are max(a*v, v) with a = 1 / 0 / alpha
     const float a_eff = act_slope(p.act, p.alpha);
     const bool slow_act = (MODE != 2) && p.act >= GG_ACT_TANH;
     const int act_code = p.act;
-    const float* bias_n0 = (MODE != 2 && p.bias != nullptr) ? p.bias + n0 : nullptr;
 #define GG_FINISH4(o, col)                                                                        \
     do {                                                                                          \
-      if (bias_n0) {                                                                              \
-        const float4 bb = *reinterpret_cast<const float4*>(bias_n0 + (col));                      \
+      if (has_bias) {                                                                             \
+        const float4 bb = *reinterpret_cast<const float4*>(s_bias + (col));                       \
         o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;                                       \
       }                                                                                           \
       if (MODE != 2) {                                                                            \
@@ -397,7 +413,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __threadfence();
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (et == 0) {
-        atomicAdd(&p.counters[blockIdx.x], 1u);
+        // arrival needs no return value: a reduction (fire and forget) instead of an atomic round trip before the poll
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.counters + blockIdx.x) : "memory");
         unsigned seen;
         unsigned spins = 0;
         do {
@@ -410,7 +427,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int nc = p.n_tile / 4;
       cbeg = (split * nc) / p.splits;
       cend = ((split + 1) * nc) / p.splits;
-      {
+      if (p.bulk) {
+        // The slice [cbeg, cend) x 128 rows of one split's partial tile is CONTIGUOUS in the [n_tile/4][128] float4 layout:
+        // one elected thread asks the copy engine for the `splits` slices (cp.async.bulk -> the idle operand ring) and
+        // the 128 epilogue threads then sum them out of shared memory in split order.  Replaces two dependent rounds of
+        // 16 L2 loads per thread (2.8 us on the timeline) by one bulk transfer of <= 64 KB.
+        const int ncols = cend - cbeg;
+        const int ncols_max = (nc + p.splits - 1) / p.splits;
+        const uint32_t chunk = (uint32_t)ncols * 2048u;
+        if (ncols > 0) {
+          if (et == 0) {
+            fence_proxy_async_all();               // partials were written through the generic proxy (by other CTAs)
+            mbar_expect_tx(&accum_bar, chunk * (uint32_t)p.splits);
+            const uint8_t* src0 = reinterpret_cast<const uint8_t*>(p.partial + (size_t)blockIdx.x * tile_elems) + (size_t)cbeg * 2048;
+            const size_t split_stride_bytes = ntiles_all * tile_elems * sizeof(float);
+            for (int sp = 0; sp < p.splits; ++sp) bulk_g2s(smem + (size_t)sp * chunk, src0 + (size_t)sp * split_stride_bytes, chunk, &accum_bar);
+          }
+          mbar_wait(&accum_bar, 1);
+        }
+        stage_tile = reinterpret_cast<float*>(smem + (size_t)p.splits * ncols_max * 2048);
+        ld = ncols * 4 + 4;
+        col0 = cbeg;
+        const float4* land = reinterpret_cast<const float4*>(smem) + m;
+        for (int c = 0; c < ncols; ++c) {
+          float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+          for (int sp = 0; sp < p.splits; ++sp) {
+            const float4 t = land[((size_t)sp * ncols + c) * 128];
+            o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+          }
+          GG_FINISH4(o, (cbeg + c) * 4);
+          *reinterpret_cast<float4*>(stage_tile + m * ld + c * 4) = o;
+        }
+      } else {
         const float4* pbase = reinterpret_cast<const float4*>(p.partial + (size_t)blockIdx.x * tile_elems) + m;
         const size_t split_stride4 = ntiles_all * tile_elems / 4;
         // up to 16 independent L2 loads in flight per thread (4 column groups x 4 splits)
@@ -457,24 +506,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (p.dbg && et == 0) p.dbg[140] = gtime();
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (p.dbg && et == 0) p.dbg[141] = gtime();
-      // coalesced write-out of columns [cbeg, cend): consecutive threads take consecutive float4 of a row
+      // coalesced write-out of columns [cbeg, cend): `ncol` consecutive threads take the consecutive float4 of one row
+      // (a warp stores whole 128..512-byte row segments); the row/column split is computed once, not per element
       const int ncol = cend - cbeg;
-      const int total = 128 * ncol;
-      for (int base = et; base < total; base += 4 * 128) {
-        float4 val[4];
-        long long off[4];
-        int cc[4];
+      if (ncol > 0) {
+        const int rpp = 128 / ncol;                 // rows per pass of the 128 threads
+        const int my_c = et % ncol, my_r = et / ncol;
+        if (my_r < rpp) {
+          const float* sp_ = stage_tile + (cbeg - col0 + my_c) * 4;
+          float* gp_ = p.out + (size_t)(cbeg + my_c) * 4;
+          for (int r = my_r; r < 128; r += 4 * rpp) {
+            float4 val[4];
+            long long off[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int idx = base + u * 128;
-          const int r = (idx < total) ? idx / ncol : 0;
-          cc[u] = cbeg + ((idx < total) ? idx - r * ncol : 0);
-          off[u] = (idx < total) ? row_off[r] : -1;
-          val[u] = *reinterpret_cast<const float4*>(stage_tile + r * ld + cc[u] * 4);
+            for (int u = 0; u < 4; ++u) {
+              const int rr = r + u * rpp;
+              off[u] = rr < 128 ? row_off[rr] : -1;
+              val[u] = *reinterpret_cast<const float4*>(sp_ + (rr < 128 ? rr : 0) * ld);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (off[u] >= 0) *reinterpret_cast<float4*>(gp_ + off[u]) = val[u];
+          }
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (off[u] >= 0) *reinterpret_cast<float4*>(p.out + off[u] + cc[u] * 4) = val[u];
       }
       if (p.dbg && et == 0) p.dbg[203] = gtime();
     }
@@ -633,9 +687,18 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, TcPlan& pl, void* ws,
   // badly on 16-20-SM GPCs), so it is off by default.
   p.cluster = (p.splits > 1 && p.splits <= 8 && env_int("GG_TC_CLUSTER", 0) != 0) ? 1 : 0;
   if (p.cluster) p.stages = kMaxStages;        // the cluster epilogue parks a partial tile AND a staging tile in the ring
-  // the epilogue re-uses the ring as a [128][n_tile+4] staging tile + 128 row offsets
+  // the epilogue re-uses the ring as a [128][n_tile+4] staging tile; split-K with the bulk-copy reduction lands the
+  // `splits` slices ([splits][ncols][128] float4, <= 64 KB + rounding) in front of a compact [128][4*ncols+4] staging tile
+  // (GG_TC_BULK=1, opt-in: measured SLOWER than the per-thread L2 loads on B200 — rendezvous -> staged 3.7 us vs 2.8 us for
+  // the E.2 forward conv, profiles/timeline_conv_r1.txt — the 1-D bulk copies of 16 KB slices do not beat 16 loads in flight
+  // per thread here; kept as a documented negative result.)
+  p.bulk = (p.splits > 1 && !p.cluster && env_int("GG_TC_BULK", 0) != 0) ? 1 : 0;
   size_t ring = (size_t)p.stages * (kABytes + p.n_tile * 128);
-  const size_t staging = (size_t)128 * (p.n_tile + 4) * 4 + 128 * 8;
+  size_t staging = (size_t)128 * (p.n_tile + 4) * 4;
+  if (p.bulk) {
+    const int nc = p.n_tile / 4, ncols_max = (nc + p.splits - 1) / p.splits;
+    staging = (size_t)p.splits * ncols_max * 2048 + (size_t)128 * (ncols_max * 4 + 4) * 4;
+  }
   if (ring < staging) ring = staging;
   const size_t smem = ring + 1024;
   static bool attr_set[3] = {false, false, false};
