@@ -124,32 +124,57 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def time_dominant_kernel(torch, cabi, flush):
-    """live CUDA-event timing of the dominant tensor kernel: conv2d fwd at the Extractor.2/Discriminator.2 shape
-    (64x16x16x64 -> 64x8x8x128, 5x5 stride 2; 1.678 GFLOP per launch)"""
-    B, H, W, Ci, Co, k = BATCH, 16, 16, 64, 128, 5
+def time_dominant_kernel(torch, cabi, flush_buf):
+    """live CUDA-event timing of the dominant tensor kernel: the tcgen05 conv2d forward at the Discriminator.2 shape of the
+    step (fake and real towers batched: 128x16x16x64 -> 128x8x8x128, 5x5 stride 2; 3.355 GFLOP per launch, 2x SURVEY.md
+    §8(d)'s 1.678 GF per 64 images).  N launches are replayed from a CUDA graph between two events, so the number is the
+    kernel's device time (launch gap included), not the host's launch overhead; `cold` puts a 256 MiB memset between
+    launches (its own time, measured the same way, subtracted)."""
+    import numpy as np
+    B, H, W, Ci, Co, k = 2 * BATCH, 16, 16, 64, 128, 5
     x = torch.randn(B, H, W, Ci, device="cuda")
     w = torch.randn(k, k, Ci, Co, device="cuda") * 0.05
     b = torch.zeros(Co, device="cuda")
     y = torch.empty(B, 8, 8, Co, device="cuda")
-    ws = torch.empty(1 << 20, dtype=torch.uint8, device="cuda")
-    st = cabi.stream_ptr()
+    ws = torch.zeros(max(int(cabi.lib.gg_conv2d_workspace(0, B, H, W, Ci, Co, k, 2, 8, 8)), 256), dtype=torch.uint8, device="cuda")
+    N = 20
 
-    def launch():
+    def launch(st):
         cabi.call("gg_conv2d_fwd", x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), B, H, W, Ci, Co, k, 2, 1, 1, 8, 8,
                   2, 0.2, ws.data_ptr(), ws.numel(), st)
-    for _ in range(5):
-        launch()
-    times = []
-    for _ in range(20):
-        flush()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); launch(); e1.record()
-        e1.synchronize()
-        times.append(e0.elapsed_time(e1))
-    ms = float(np.mean(times))
+
+    def graph_us(with_kernel, with_flush):
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            launch(s.cuda_stream)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=s):
+                for _ in range(N):
+                    if with_flush:
+                        flush_buf.zero_()
+                    if with_kernel:
+                        launch(torch.cuda.current_stream().cuda_stream)
+            ts = []
+            for _ in range(8):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(s); g.replay(); e1.record(s); e1.synchronize()
+                ts.append(e0.elapsed_time(e1) * 1e3 / N)
+        return float(np.mean(ts[2:]))
+    hot = graph_us(True, False)
+    cold = graph_us(True, True) - graph_us(False, True)
     flops = 2.0 * B * 8 * 8 * Co * Ci * k * k
-    return ms, flops, cabi.lib.gg_last_backend()
+    return hot * 1e-3, cold * 1e-3, flops, cabi.lib.gg_last_backend()
+
+
+def load_ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
+    capture (profiles/ncu_dominant_kernel.json, written by tools/summarize_ncu.py); None when no capture is committed"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_dominant_kernel.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
 
 
 def run_ours(args):
@@ -252,8 +277,9 @@ def run_ours(args):
     images = BATCH * world * args.steps
     value = images / (dev_ms / 1e3)
     hbm_peak, tf_peak, peak_kind = load_peaks()
-    k_ms, k_flops, k_backend = time_dominant_kernel(torch, cabi, flush)
+    k_ms_hot, k_ms, k_flops, k_backend = time_dominant_kernel(torch, cabi, flush_buf)
     achieved = k_flops / (k_ms * 1e-3) / 1e12
+    ncu = load_ncu_traffic()
     cpu = None
     if world == 1:
         ips, _, threads = cpu_oracle_ips(8, 2)
@@ -274,8 +300,13 @@ def run_ours(args):
                 "h2d_bytes_per_step": 2 * BATCH * 3072 * 4, "d2h_bytes_per_step": 8},
         "gpu_launches": launches_per_iter * args.steps,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
-                     "traffic": None, "kernel": "gg_conv2d_fwd 64x16x16x64->128 5x5 s2 (%s)" % ("tcgen05 tf32" if k_backend else "direct fp32"),
-                     "kernel_ms": k_ms, "peak_kind": peak_kind + " dense bf16 (kind::tf32 peaks at half of it)"},
+                     "traffic": (ncu or {}).get("dram_bytes_per_launch"),
+                     "kernel": "gg_conv2d_fwd 128x16x16x64->128 5x5 s2, Discriminator.2 on the batched fake+real towers (%s)" %
+                               ("tcgen05 tf32" if k_backend else "direct fp32"),
+                     "algorithmic_flop_per_launch": k_flops, "kernel_ms": k_ms, "kernel_ms_hot_l2": k_ms_hot,
+                     "timing": "CUDA graph of 20 launches between two events, 256 MiB memset between launches (subtracted)",
+                     "peak_kind": peak_kind + " dense bf16 burst (kind::tf32 peaks at half of it)",
+                     "ncu": (ncu or {}).get("source")},
         "clocks": clocks,
     }
     if cpu is not None:

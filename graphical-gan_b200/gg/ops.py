@@ -120,6 +120,11 @@ def slice_axis(x, axis, start, size):
         axis += len(x.shape)
     if start == 0 and size == x.shape[axis]:
         return x
+    if x.op == "transpose":
+        # crop in the producer's own layout (gmgan_inference_mnist.py:179 crops the NCHW view `output[:, :, :7, :7]` between
+        # two deconvolutions: the data stays NHWC and no layout kernel is materialised)
+        perm = x.attrs["perm"]
+        return transpose(slice_axis(x.inputs[0], perm[axis], start, size), perm)
     shape = list(x.shape)
     shape[axis] = size
     return Tensor("slice", (x,), {"axis": axis, "start": int(start), "size": int(size)}, shape, x.dtype)

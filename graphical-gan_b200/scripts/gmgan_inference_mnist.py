@@ -1,12 +1,13 @@
-"""GMGAN on CIFAR-10 — Python-3 port of the reference's gmgan_inference_cifar10.py driving the B200 kernels.
+"""GMGAN on MNIST — Python-3 port of the reference's gmgan_inference_mnist.py driving the B200 kernels
+(BASELINE.json configs[0]: MODE='local_ep', BATCH_SIZE=50, 28x28x1 — SURVEY.md D2).
 
 The constants block, the model functions (Generator / Extractor / HyperGenerator / HyperExtractor /
 HyperDiscriminator / Discriminator) and the `session.run` training loop keep the reference's structure and
-names (line references below are to /root/reference/gmgan_inference_cifar10.py).  Differences, all mechanical:
+names (line references below are to /root/reference/gmgan_inference_mnist.py).  Differences, all mechanical:
   * the graph is built inside build_graph() so that tests and bench.py can import it (the reference builds it at
     module import); random tensors are also returned so parity tests can FEED them (TF lets you feed any tensor);
   * Python 3 syntax; matplotlib / inception-score / image-grid side outputs are optional and skipped when their
-    dependencies or datasets are absent; `--synthetic` trains on uniform random int images (no dataset needed).
+    dependencies or datasets are absent; `--synthetic` trains on uniform random [0,1] images (no dataset needed).
 """
 import os
 import sys
@@ -31,8 +32,8 @@ import tflib.utils.distance
 import tflib.plot
 
 
-def build_graph(MODE='local_ep', BATCH_SIZE=64, DIM=64, N_COMS=30, LR=2e-4, MODE_K='CONCRETE', N_VIS=None, BN_FLAG=None):
-    """Lines 39-410 of the reference script.  Returns a namespace with every tensor / op the train loop uses."""
+def build_graph(MODE='local_ep', BATCH_SIZE=50, DIM=64, N_COMS=30, LR=2e-4, MODE_K='CONCRETE', N_VIS=None):
+    """Lines 31-394 of the reference script.  Returns a namespace with every tensor / op the train loop uses."""
     # ---- hyperparameters (:39-87) ----
     if MODE in ['vegan-kl', 'vegan-ikl', 'vegan-jsd', 'vae', 'vegan-mmd']:
         raise NotImplementedError("MODE %s has no discriminator; not on the adversarial hot path" % MODE)
@@ -41,14 +42,11 @@ def build_graph(MODE='local_ep', BATCH_SIZE=64, DIM=64, N_COMS=30, LR=2e-4, MODE
     CRITIC_ITERS = 5 if MODE in ['vegan', 'vegan-wgan-gp', 'wali', 'wali-gp'] else 1
     LAMBDA = 1.
     BETA1 = .5
-    OUTPUT_DIM = 3072
-    bn_override = BN_FLAG                     # gmgan_inference_svhn.py:70 runs the same networks with BN_FLAG = False
+    OUTPUT_DIM = 784
     if MODE in ['vegan', 'vegan-wgan-gp']:
         BN_FLAG, DIM_LATENT = False, 8
     else:
         BN_FLAG, DIM_LATENT = True, 128
-    if bn_override is not None:
-        BN_FLAG = bool(bn_override)
     if N_VIS is None:
         N_VIS = N_COMS * 10
     assert N_VIS % N_COMS == 0
@@ -108,18 +106,20 @@ def build_graph(MODE='local_ep', BATCH_SIZE=64, DIM=64, N_COMS=30, LR=2e-4, MODE
             output = lib.ops.batchnorm.Batchnorm('Generator.BN2', [0, 2, 3], output)
         output = tf.nn.relu(output)
 
+        output = output[:, :, :7, :7]                                            # (:179) 8x8 -> 7x7 so that 7 -> 14 -> 28
+
         output = lib.ops.deconv2d.Deconv2D('Generator.3', 2 * DIM, DIM, 5, output)
         if BN_FLAG:
             output = lib.ops.batchnorm.Batchnorm('Generator.BN3', [0, 2, 3], output)
         output = tf.nn.relu(output)
 
-        output = lib.ops.deconv2d.Deconv2D('Generator.5', DIM, 3, 5, output)
-        output = tf.tanh(output)
+        output = lib.ops.deconv2d.Deconv2D('Generator.5', DIM, 1, 5, output)
+        output = tf.nn.sigmoid(output)                                            # (:187)
         return tf.reshape(output, [-1, OUTPUT_DIM]), None, None
 
     def Extractor(inputs):
-        output = tf.reshape(inputs, [-1, 3, 32, 32])
-        output = lib.ops.conv2d.Conv2D('Extractor.1', 3, DIM, 5, output, stride=2)
+        output = tf.reshape(inputs, [-1, 1, 28, 28])
+        output = lib.ops.conv2d.Conv2D('Extractor.1', 1, DIM, 5, output, stride=2)
         output = LeakyReLU(output)
 
         output = lib.ops.conv2d.Conv2D('Extractor.2', DIM, 2 * DIM, 5, output, stride=2)
@@ -151,8 +151,8 @@ def build_graph(MODE='local_ep', BATCH_SIZE=64, DIM=64, N_COMS=30, LR=2e-4, MODE
         return tf.reshape(output, [-1])
 
     def _conv_trunk(prefix, x):
-        output = tf.reshape(x, [-1, 3, 32, 32])
-        output = lib.ops.conv2d.Conv2D('Discriminator.%s1' % prefix, 3, DIM, 5, output, stride=2)
+        output = tf.reshape(x, [-1, 1, 28, 28])
+        output = lib.ops.conv2d.Conv2D('Discriminator.%s1' % prefix, 1, DIM, 5, output, stride=2)
         output = LeakyReLU(output)
         output = tf.layers.dropout(output, rate=DR_RATE)
         output = lib.ops.conv2d.Conv2D('Discriminator.%s2' % prefix, DIM, 2 * DIM, 5, output, stride=2)
@@ -194,8 +194,7 @@ def build_graph(MODE='local_ep', BATCH_SIZE=64, DIM=64, N_COMS=30, LR=2e-4, MODE
             return tf.reshape(output, [-1])
 
     # ---- losses (:341-410) ----
-    real_x_int = tf.placeholder(tf.int32, shape=[BATCH_SIZE, OUTPUT_DIM])
-    real_x = 2 * ((tf.cast(real_x_int, tf.float32) / 255.) - .5)
+    real_x = tf.placeholder(tf.float32, shape=[BATCH_SIZE, OUTPUT_DIM])      # MNIST feeds float [0,1] directly (:335)
     q_z, _, _ = Extractor(real_x)
     q_k_logits, q_k = HyperExtractor(q_z)
     q_k_probs = tf.nn.softmax(q_k_logits)
@@ -259,7 +258,7 @@ def build_graph(MODE='local_ep', BATCH_SIZE=64, DIM=64, N_COMS=30, LR=2e-4, MODE
     fixed_noise = HyperGenerator(tf.constant(np_fixed_k), tf.constant(np_fixed_noise))
     fixed_noise_samples, _, _ = Generator(fixed_noise)
 
-    ns.__dict__.update(real_x_int=real_x_int, real_x=real_x, q_z=q_z, q_k=q_k, q_k_logits=q_k_logits, rec_x=rec_x,
+    ns.__dict__.update(real_x=real_x, q_z=q_z, q_k=q_k, q_k_logits=q_k_logits, rec_x=rec_x,
                        hyper_p_z=hyper_p_z, hyper_p_k_idx=hyper_p_k_idx, hyper_p_k=hyper_p_k, p_z=p_z, fake_x=fake_x,
                        rec_z=rec_z, disc_fake=disc_fake, disc_real=disc_real, gen_params=gen_params, ext_params=ext_params,
                        disc_params=disc_params, rec_penalty=rec_penalty, gen_cost=gen_cost, disc_cost=disc_cost,
@@ -268,10 +267,10 @@ def build_graph(MODE='local_ep', BATCH_SIZE=64, DIM=64, N_COMS=30, LR=2e-4, MODE
     return ns
 
 
-def synthetic_batches(batch_size, output_dim=3072, n=8, seed=0):
-    """a ring of pre-generated uniform 0..255 int32 batches"""
+def synthetic_batches(batch_size, output_dim=784, n=8, seed=0):
+    """a ring of pre-generated uniform [0,1] float32 batches"""
     rs = np.random.RandomState(seed)
-    ring = [rs.randint(0, 256, size=(batch_size, output_dim)).astype('int32') for _ in range(n)]
+    ring = [rs.uniform(0, 1, size=(batch_size, output_dim)).astype('float32') for _ in range(n)]
     while True:
         for b in ring:
             yield b
@@ -282,29 +281,34 @@ def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument('--mode', default='local_ep')
     ap.add_argument('--iters', type=int, default=200000)
-    ap.add_argument('--batch-size', type=int, default=64)
-    ap.add_argument('--data-dir', default='./dataset/cifar10/cifar-10-batches-py')
+    ap.add_argument('--batch-size', type=int, default=50)
+    ap.add_argument('--data-dir', default='/tmp/mnist.pkl.gz')
     ap.add_argument('--synthetic', action='store_true', help='train on uniform random images (no dataset needed)')
     ap.add_argument('--out', default=None)
     args = ap.parse_args(argv)
 
     MODE, BATCH_SIZE, ITERS = args.mode, args.batch_size, args.iters
-    outf = args.out or os.path.join("result", "gmgan_inference_cifar10.MODE-%s.N_COMS-30.%d" % (MODE, int(time.time())))
+    outf = args.out or os.path.join("result", "gmgan_inference_mnist.MODE-%s.N_COMS-30.%d" % (MODE, int(time.time())))
     os.makedirs(outf, exist_ok=True)
     logfile = os.path.join(outf, 'logfile.txt')
     lib.print_model_settings_to_file(dict(MODE=MODE, BATCH_SIZE=BATCH_SIZE, ITERS=ITERS), logfile)
 
     g = build_graph(MODE=MODE, BATCH_SIZE=BATCH_SIZE)
-    if args.synthetic or not os.path.isdir(args.data_dir):
+    if args.synthetic or not os.path.exists(args.data_dir):
         gen = synthetic_batches(BATCH_SIZE)
     else:
-        import tflib.cifar10
-        train_gen, _ = lib.cifar10.load(BATCH_SIZE, data_dir=args.data_dir)
+        import gzip
+        import pickle
+        with gzip.open(args.data_dir, 'rb') as f:                               # tflib/mnist.py:53-57 (mnist.pkl.gz)
+            train_data, _, _ = pickle.load(f, encoding='latin1')
+        images = train_data[0].astype('float32')
 
         def inf_train_gen():
+            rs = np.random.RandomState(1)
             while True:
-                for images, _ in train_gen():
-                    yield images
+                rs.shuffle(images)
+                for i in range(len(images) // BATCH_SIZE):
+                    yield images[i * BATCH_SIZE:(i + 1) * BATCH_SIZE]
         gen = inf_train_gen()
 
     saver = tf.train.Saver()
@@ -316,10 +320,10 @@ def main(argv=None):
             start_time = time.time()
             if iteration > 0:
                 _data = next(gen)
-                _gen_cost, _ = session.run([g.gen_cost, g.gen_train_op], feed_dict={g.real_x_int: _data})
+                _gen_cost, _ = session.run([g.gen_cost, g.gen_train_op], feed_dict={g.real_x: _data})
             for i in range(g.CRITIC_ITERS):
                 _data = next(gen)
-                _disc_cost, _ = session.run([g.disc_cost, g.disc_train_op], feed_dict={g.real_x_int: _data})
+                _disc_cost, _ = session.run([g.disc_cost, g.disc_train_op], feed_dict={g.real_x: _data})
             lib.plot.plot('train disc cost', _disc_cost)
             lib.plot.plot('time', time.time() - start_time)
             if (iteration < 5) or (iteration % 100 == 99):
@@ -328,7 +332,7 @@ def main(argv=None):
             if iteration % 5000 == 4999:
                 samples = session.run(g.fixed_noise_samples)
                 np.save(os.path.join(outf, '%d_samples_%s.npy' % (iteration, MODE)),
-                        ((samples + 1.) * (255. / 2)).astype('int32').reshape((-1, 3, 32, 32)))
+                        samples.reshape((-1, 28, 28)))
             if iteration == ITERS - 1:
                 saver.save(session, os.path.join(outf, '{}_model_{}.ckpt'.format(iteration, MODE)))
 

@@ -98,7 +98,10 @@ def _families():
     import gan_inference_svhn as V
     import gan_inference_face as F
     import ssgan_inference_moving_mnist as M
+    import gmgan_inference_mnist as N
     return {
+        "gmgan_mnist_local_ep": lambda: N.build_graph(BATCH_SIZE=3),
+        "gmgan_svhn_local_epce": lambda: __import__("gmgan_inference_svhn").build_graph(MODE='local_epce', BATCH_SIZE=2),
         "gmgan_cifar10_local_ep": lambda: C.build_graph(BATCH_SIZE=4),
         "gan_svhn_wali_gp": lambda: V.build_graph(MODE='wali-gp', BATCH_SIZE=4),
         "gan_face_ali": lambda: F.build_graph(BATCH_SIZE=2),
@@ -106,7 +109,8 @@ def _families():
     }
 
 
-@pytest.mark.parametrize("family", ["gmgan_cifar10_local_ep", "gan_svhn_wali_gp", "gan_face_ali", "ssgan_moving_mnist"])
+@pytest.mark.parametrize("family", ["gmgan_cifar10_local_ep", "gmgan_mnist_local_ep", "gmgan_svhn_local_epce", "gan_svhn_wali_gp", "gan_face_ali",
+                                    "ssgan_moving_mnist"])
 def test_sibling_batching_preserves_costs_and_gradients(family):
     build = _families()[family]
     g0, d0, v0, h0 = _eval_family(build, False, 7)
@@ -117,3 +121,27 @@ def test_sibling_batching_preserves_costs_and_gradients(family):
     for k in v0:
         scale = np.abs(v0[k]).max() + 1e-30
         assert np.abs(v0[k] - v1[k]).max() <= 1e-8 * scale + 1e-13, k
+
+
+def test_gmgan_mnist_graph_matches_oracle_autograd():
+    """configs[0] on the CPU: the compiled MNIST graph (crop between deconvolutions sunk into NHWC, 7 -> 4 conv with (2,2)
+    padding, single-channel first / last layers) against oracle/gmgan_mnist.py, costs and all gradients, batch 5"""
+    import tensorflow as tf
+    import tflib as lib
+    import gmgan_inference_mnist as S
+    from oracle import gmgan_mnist as OM
+    tf.reset_default_graph()
+    lib.delete_all_params()
+    np.random.seed(5)
+    g = S.build_graph(BATCH_SIZE=5)
+    params = {n: p.attrs["init"] for n, p in lib._params.items()}
+    model = OM.GMGANMnist(params, dtype=torch.float64)
+    inp = OM.synthetic_inputs(5, 0)
+    it = Interp({g.real_x: inp["real_x"], g.hyper_p_z: inp["hyper_p_z"], g.hyper_p_k_idx: inp["k_idx"],
+                 g.gumbel_uniforms[0]: inp["U"]})
+    for cost, op, fn in ((g.gen_cost, g.gen_train_op, model.gen_step), (g.disc_cost, g.disc_train_op, model.disc_step)):
+        ref_cost, ref_grads = fn(apply=False, **inp)
+        assert abs(float(it.run(cost)) - ref_cost) < 1e-9 * max(1.0, abs(ref_cost))
+        for name, node in _grads_of(op).items():
+            got, ref = it.run(node), ref_grads[name].numpy()
+            assert np.abs(got - ref.reshape(got.shape)).max() <= 1e-8 * (np.abs(ref).max() + 1e-30) + 1e-13, name

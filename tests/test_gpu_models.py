@@ -101,3 +101,62 @@ def test_checkpoint_save_restore_roundtrip(tmp_path):
     assert np.array_equal(before, RT.get_param(w))
     c2, _ = sess.run([g.disc_cost, g.disc_train_op], feed_dict=feeds)     # same params AND same Adam state -> same step
     assert c1 == c2
+
+
+def test_gmgan_mnist_local_ep_bs50_matches_oracle():
+    """BASELINE.json configs[0] (gmgan_inference_mnist.py MODE='local_ep', BATCH_SIZE=50, 1x28x28): costs and
+    every parameter gradient of the D step and the G step against the fp64 oracle (oracle/gmgan_mnist.py) — exercises the
+    28 -> 14 -> 7 -> 4 convolutions (pad (2,2) on the last), the 8x8 -> 7x7 crop between deconvolutions, Cin = Cout = 1
+    layers and a batch of 50 (no power of two anywhere) — then two training iterations."""
+    import tensorflow as tf
+    import tflib as lib
+    import gmgan_inference_mnist as S
+    from gg import cabi
+    from gg.executor import RT
+    from oracle import gmgan_mnist as OM
+    tf.reset_default_graph()
+    lib.delete_all_params()
+    np.random.seed(21)
+    B = 50
+    g = S.build_graph(BATCH_SIZE=B)
+    sess = tf.Session()
+    params = {name: RT.get_param(p).copy() for name, p in lib._params.items()}
+    oracle = OM.GMGANMnist(params, dtype=torch.float64)
+    inp = OM.synthetic_inputs(B, 0)
+    feeds = {g.real_x: inp["real_x"], g.hyper_p_z: inp["hyper_p_z"], g.hyper_p_k_idx: inp["k_idx"], g.gumbel_uniforms[0]: inp["U"]}
+    cabi.call("gg_set_conv_backend", 1)           # fp32 kernels: the tight end-to-end bound (see test_gpu_gmgan_step.py)
+    try:
+        for which, cost, plist, fn in (("disc", g.disc_cost, g.disc_params, oracle.disc_step),
+                                       ("gen", g.gen_cost, g.gen_params + g.ext_params, oracle.gen_step)):
+            plist = [p for p in plist if 'moving_' not in p.name]
+            grads = tf.gradients(cost, plist)
+            keep = [(p, gr) for p, gr in zip(plist, grads) if gr is not None]
+            out = sess.run([cost] + [gr for _, gr in keep], feed_dict=feeds)
+            ref_cost, ref_grads = fn(apply=False, **inp)
+            assert abs(float(out[0]) - ref_cost) <= 1e-4 * max(1.0, abs(ref_cost)), (which, float(out[0]), ref_cost)
+            gmax = max(float(v.abs().max()) for v in ref_grads.values() if v is not None)
+            for (p, _), got in zip(keep, out[1:]):
+                ref = ref_grads[p.name].numpy()
+                assert got.shape == ref.shape
+                if np.abs(ref).max() < 1e-7 * gmax:
+                    assert np.abs(got).max() < 1e-4 * gmax, p.name
+                    continue
+                l2 = float(np.linalg.norm(got.astype(np.float64) - ref) / (np.linalg.norm(ref) + 1e-30))
+                assert l2 < 5e-3, "%s grad of %s: rel-L2 %.3e" % (which, p.name, l2)
+    finally:
+        cabi.call("gg_set_conv_backend", 0)
+    # default (tensor-core) path: two training iterations against the oracle's costs
+    step = 0
+    for it in range(2):
+        i2 = OM.synthetic_inputs(B, 10 + step); step += 1
+        f2 = {g.real_x: i2["real_x"], g.hyper_p_z: i2["hyper_p_z"], g.hyper_p_k_idx: i2["k_idx"], g.gumbel_uniforms[0]: i2["U"]}
+        dc, _ = sess.run([g.disc_cost, g.disc_train_op], feed_dict=f2)
+        rc, _ = oracle.disc_step(**i2)
+        assert abs(float(dc) - rc) <= 5e-3 * max(1.0, abs(rc)), (it, float(dc), rc)
+        i3 = OM.synthetic_inputs(B, 10 + step); step += 1
+        f3 = {g.real_x: i3["real_x"], g.hyper_p_z: i3["hyper_p_z"], g.hyper_p_k_idx: i3["k_idx"], g.gumbel_uniforms[0]: i3["U"]}
+        gc, _ = sess.run([g.gen_cost, g.gen_train_op], feed_dict=f3)
+        rg, _ = oracle.gen_step(**i3)
+        assert abs(float(gc) - rg) <= 5e-3 * max(1.0, abs(rg)), (it, float(gc), rg)
+    s = sess.run(g.fake_x, feed_dict=f3)
+    assert s.shape == (B, 784) and s.min() >= 0.0 and s.max() <= 1.0

@@ -1,15 +1,19 @@
 #!/usr/bin/env bash
-# One GPU-box visit that produces everything a round needs: test results, the bench line, the ncu launch list of one
-# iteration and a full capture of the tensor-core conv kernels.  Outputs land in gpurun_out/.
+# One GPU-box visit that produces everything a round needs: test results, the bench lines (ours + reference arm), the ncu
+# launch list of one iteration, a full ncu capture of the tensor-core conv kernels, CUPTI timelines.  Outputs -> gpurun_out/.
 set -u
 tag="${1:-r1}"
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -q --no-header 2>&1 | tail -25 | cut -c1-250 > gpurun_out/pytest_${tag}.log
 tail -3 gpurun_out/pytest_${tag}.log
 python bench.py --steps 100 --warmup 10 2>&1 | tail -1 > gpurun_out/bench_${tag}.json
-python -c "import json;d=json.load(open('gpurun_out/bench_${tag}.json'));print('bench',d['value'],d['ms_per_step'],'e2e',d['e2e']['value'],'launches/iter',d['gpu_launches']/d['steps'],'kernel_ms',d['roofline']['kernel_ms'],'cpu',d.get('cpu_baseline',{}).get('value'))"
+python -c "import json;d=json.load(open('gpurun_out/bench_${tag}.json'));print('bench',d['value'],d['ms_per_step'],'e2e',d['e2e']['value'],'launches/iter',d['gpu_launches']/d['steps'],'kernel_ms',d['roofline']['kernel_ms'],'frac',d['roofline']['frac'],'cpu',d.get('cpu_baseline',{}).get('value'))"
 python bench.py --impl reference --steps 10 --warmup 2 2>&1 | tail -1 > gpurun_out/bench_ref_${tag}.json
-timeout 300 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_${tag}.csv python tools/profile_step.py 2>&1 | tail -1
-timeout 400 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:conv_tc -c 10 -o gpurun_out/prof_conv_${tag} python tools/profile_step.py 2>&1 | tail -1
+GG_CUDA_GRAPH=1 timeout 300 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_${tag}.csv python tools/profile_step.py 2>&1 | tail -1
+grep -c conv_tc gpurun_out/launches_${tag}.csv
+GG_CUDA_GRAPH=1 timeout 400 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:conv_tc -c 14 -o gpurun_out/prof_conv_${tag} python tools/profile_step.py 2>&1 | tail -1
 timeout 200 python tools/time_conv.py 2>&1 | tail -20 > gpurun_out/time_conv_${tag}.txt
-ls -la gpurun_out | tail -12
+python tools/profile_timeline.py gen > gpurun_out/timeline_gen_${tag}.txt 2>&1
+python tools/profile_timeline.py disc > gpurun_out/timeline_disc_${tag}.txt 2>&1
+head -3 gpurun_out/timeline_gen_${tag}.txt; head -3 gpurun_out/timeline_disc_${tag}.txt
+ls -la gpurun_out | tail -14

@@ -11,7 +11,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "graphical-gan_b200"), os.path.join(ROOT, "graphical-gan_b200", "scripts")):
     sys.path.insert(0, p)
-os.environ.setdefault("GG_CUDA_GRAPH", "0")     # eager launches: one profiler record per kernel
+os.environ.setdefault("GG_CUDA_GRAPH", "0")     # eager by default; GG_CUDA_GRAPH=1 profiles the kernel nodes of the captured graphs
 
 import numpy as np
 import torch
