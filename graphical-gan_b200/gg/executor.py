@@ -163,10 +163,10 @@ class Plan(object):
             elif isinstance(f, Tensor):
                 roots.append(f)
         self.order = self._toposort(roots)
-        # split-K of the tensor-core kernels is sized to half the GPU when the plan will run multi-stream (two launches can
-        # then overlap); workspace sizes depend on it, so it is fixed before emission
+        # split-K of the tensor-core kernels may use every SM (GG_TC_MAX_CTAS caps it); with the 3-stage ring two CTAs share an
+        # SM, so two launches on different streams still overlap.  Workspace sizes depend on both: fixed before emission
         self.n_streams = int(os.environ.get("GG_STREAMS", "6")) if rt.use_cuda_graph else 1
-        cabi.call("gg_set_tc_max_ctas", int(os.environ.get("GG_TC_MAX_CTAS", "74" if self.n_streams > 1 else "148")))
+        cabi.call("gg_set_tc_max_ctas", int(os.environ.get("GG_TC_MAX_CTAS", "148")))
         cabi.call("gg_set_tc_stages", int(os.environ.get("GG_TC_STAGES", "3" if self.n_streams > 1 else "0")))
         # scheduling metadata: one group per node that launches kernels; `owner` resolves views (reshape / aux / fed)
         # to the node whose kernels produce the storage
@@ -177,7 +177,7 @@ class Plan(object):
             tick = rt.tick()
             self.steps.append(lambda st, tick=tick: cabi.call("gg_rng_tick", tick.data_ptr(), st))
             self.groups.append(dict(start=0, end=1, reads=set(), writes="tick", barrier=False, collective=False, node=None,
-                                    part=(0, 1)))
+                                    part=(0, 1), ordered=False))
         self._plan_inplace_concats()
         for node in self.order:
             s0 = len(self.steps)
@@ -232,8 +232,11 @@ class Plan(object):
             last = k == len(ranges) - 1
             w = writes if last else "%s#%d" % (writes, k)
             r = set(reads) if prev is None else {prev}
+            # peer-memory all-reduce kernels share one exchange buffer and an epoch counter per rank: they must run one at
+            # a time and in the same order on every rank, so the scheduler chains the groups that contain one
+            ordered = any(getattr(self.steps[i], "is_small_allreduce", False) for i in range(a, b))
             self.groups.append(dict(start=a, end=b, reads=r, writes=w, barrier=barrier and prev is None, collective=coll,
-                                    node=node, part=(k, len(ranges))))
+                                    node=node, part=(k, len(ranges)), ordered=ordered))
             prev = w
 
     # ---- graph walking ---------------------------------------------------------------------
@@ -667,7 +670,9 @@ class Plan(object):
         else an eager NCCL all-reduce between graph segments"""
         sar = ggdist.small_all_reduce()
         if sar is not None and n <= sar.MAX_FLOATS:
-            self.steps.append(lambda st: sar(t, t, n, st))
+            fn = lambda st: sar(t, t, n, st)
+            fn.is_small_allreduce = True
+            self.steps.append(fn)
         else:
             self.steps.append(self._collective(lambda st: ggdist.all_reduce_sum(t)))
 
@@ -801,12 +806,16 @@ class Plan(object):
         cost = {gi: self._group_cost(self.groups[gi]) for gi in idxs}
         # dependencies: producers of what the group reads; an optimiser step (barrier) waits for everything before it and
         # everything after it waits for the barrier
-        producer, deps, last_barrier, seen = {}, {}, None, []
+        producer, deps, last_barrier, last_ordered, seen = {}, {}, None, None, []
         for gi in idxs:
             g = self.groups[gi]
             d = set(producer[o] for o in g["reads"] if o in producer)
             if last_barrier is not None:
                 d.add(last_barrier)
+            if g.get("ordered"):
+                if last_ordered is not None:
+                    d.add(last_ordered)
+                last_ordered = gi
             if g["barrier"]:
                 d |= set(seen)
                 last_barrier = gi
