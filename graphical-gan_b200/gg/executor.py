@@ -234,7 +234,7 @@ class Plan(object):
             r = set(reads) if prev is None else {prev}
             # peer-memory all-reduce kernels share one exchange buffer and an epoch counter per rank: they must run one at
             # a time and in the same order on every rank, so the scheduler chains the groups that contain one
-            ordered = any(getattr(self.steps[i], "is_small_allreduce", False) for i in range(a, b))
+            ordered = coll or any(getattr(self.steps[i], "is_small_allreduce", False) for i in range(a, b))
             self.groups.append(dict(start=a, end=b, reads=r, writes=w, barrier=barrier and prev is None, collective=coll,
                                     node=node, part=(k, len(ranges)), ordered=ordered))
             prev = w
@@ -915,8 +915,13 @@ class Plan(object):
                 sp = st.cuda_stream
                 if trace:
                     ta = self._trace_event(sp)
-                for f in self.steps[grp["start"]:grp["end"]]:
-                    f(sp)
+                if grp["collective"]:
+                    with torch.cuda.stream(st):        # NCCL (torch.distributed) issues on torch's current stream
+                        for f in self.steps[grp["start"]:grp["end"]]:
+                            f(sp)
+                else:
+                    for f in self.steps[grp["start"]:grp["end"]]:
+                        f(sp)
                 if trace:
                     self.trace.append((gi, assign[gi], ta, self._trace_event(sp), list(waits[gi])))
                 if gi in need_event:
@@ -946,8 +951,11 @@ class Plan(object):
         and run on the main stream between graph segments; every segment is scheduled over n_streams streams"""
         torch = _torch()
         segments, cur = [], []
+        # GG_NCCL_IN_GRAPH=1: capture the NCCL all-reduce as a node of the step's graph (one graph launch per step, and the
+        # scheduler can run independent kernels beside the exchange) instead of cutting the launch list around it
+        in_graph = os.environ.get("GG_NCCL_IN_GRAPH", "0") == "1"
         for gi, grp in enumerate(self.groups):
-            if grp["collective"]:
+            if grp["collective"] and not in_graph:
                 if cur:
                     segments.append(cur)
                     cur = []
