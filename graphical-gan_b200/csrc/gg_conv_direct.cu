@@ -20,6 +20,11 @@ size_t conv_tc_wgrad_workspace(int B, int H, int W, int Ci, int Co, int k, int s
 size_t conv_tc_workspace(int mode, int B, int H, int W, int Ci, int Co, int k, int stride, int Ho, int Wo);
 void conv_tc_set_debug(void* p);
 void conv_tc_set_max_ctas(int n);
+// gg_conv_small.cu: one-launch shared-memory kernels for the 1-/3-channel first conv and last deconv of every network
+int conv_small_fwd(const float* x, const float* w, const float* bias, float* y, int B, int H, int W, int Ci, int Co, int k,
+                   int stride, int pad_t, int pad_l, int Ho, int Wo, int act, float alpha, cudaStream_t st, bool* handled);
+int conv_small_dgrad(const float* dy, const float* w, const float* bias, float* dx, int B, int H, int W, int Ci, int Co, int k,
+                     int stride, int pad_t, int pad_l, int Ho, int Wo, int act, float alpha, cudaStream_t st, bool* handled);
 }  // namespace gg
 
 namespace {
@@ -325,6 +330,12 @@ extern "C" int gg_conv2d_fwd(const float* x, const float* w, const float* bias, 
   int rc = check_geom(p, "gg_conv2d_fwd");
   if (rc) return rc;
   cudaStream_t st = as_stream(stream);
+  if (g_conv_backend != 1) {
+    bool handled = false;
+    rc = conv_small_fwd(x, w, bias, y, B, H, W, Ci, Co, k, stride, pad_t, pad_l, Ho, Wo, act, alpha, st, &handled);
+    if (rc) return rc;
+    if (handled) { g_last_backend = 0; return GG_OK; }
+  }
   {
     SmallCi sc = smallci_plan(0, p);
     if (sc.ok && workspace != nullptr && workspace_bytes >= sc.tc_bytes + sc.p_bytes) {
@@ -366,6 +377,12 @@ extern "C" int gg_conv2d_dgrad(const float* dy, const float* w, const float* bia
   int rc = check_geom(p, "gg_conv2d_dgrad");
   if (rc) return rc;
   cudaStream_t st = as_stream(stream);
+  if (g_conv_backend != 1) {
+    bool handled = false;
+    rc = conv_small_dgrad(dy, w, bias, dx, B, H, W, Ci, Co, k, stride, pad_t, pad_l, Ho, Wo, act, alpha, st, &handled);
+    if (rc) return rc;
+    if (handled) { g_last_backend = 0; return GG_OK; }
+  }
   {
     SmallCi sc = smallci_plan(1, p);
     if (sc.ok && workspace != nullptr && workspace_bytes >= sc.tc_bytes + sc.p_bytes) {

