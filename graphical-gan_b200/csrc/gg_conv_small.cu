@@ -45,21 +45,41 @@ __global__ void __launch_bounds__(256) conv_small_fwd_kernel(const float* __rest
   const int tid = threadIdx.x;
 
   // filter slab: rows kk = (r*k+s)*CI+c of Co contiguous floats -> sw[kk][0..nco)
-  for (int i = tid; i < K * (kChunk / 4); i += 256) {
-    const int kk = i / (kChunk / 4), q = i % (kChunk / 4);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (q * 4 < nco) v = *reinterpret_cast<const float4*>(w + (size_t)kk * p.Co + co0 + q * 4);
-    *reinterpret_cast<float4*>(sw + kk * kChunk + q * 4) = v;
+  // (the fill loops keep 4 independent global loads in flight per thread: one load per iteration exposed an L2 round trip
+  //  per iteration, ~5 us of a 10 us kernel)
+  for (int base = tid; base < K * (kChunk / 4); base += 4 * 256) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + u * 256;
+      const int kk = i / (kChunk / 4), q = i % (kChunk / 4);
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < K * (kChunk / 4) && q * 4 < nco) v[u] = *reinterpret_cast<const float4*>(w + (size_t)kk * p.Co + co0 + q * 4);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + u * 256;
+      if (i < K * (kChunk / 4)) *reinterpret_cast<float4*>(sw + (i / (kChunk / 4)) * kChunk + (i % (kChunk / 4)) * 4) = v[u];
+    }
   }
   // input patch with TF SAME padding as zeros
   const int hi0 = ho0 * p.stride - p.pad_t, wi0 = wo0 * p.stride - p.pad_l;
   const float* xb = x + (size_t)b * p.H * p.W * CI;
-  for (int i = tid; i < IW * IW * CI; i += 256) {
-    const int c = i % CI, iw = (i / CI) % IW, ih = i / (CI * IW);
-    const int hi = hi0 + ih, wi = wi0 + iw;
-    float v = 0.f;
-    if (hi >= 0 && hi < p.H && wi >= 0 && wi < p.W) v = xb[((size_t)hi * p.W + wi) * CI + c];
-    sx[i] = v;
+  for (int base = tid; base < IW * IW * CI; base += 4 * 256) {
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + u * 256;
+      const int c = i % CI, iw = (i / CI) % IW, ih = i / (CI * IW);
+      const int hi = hi0 + ih, wi = wi0 + iw;
+      v[u] = 0.f;
+      if (i < IW * IW * CI && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W) v[u] = xb[((size_t)hi * p.W + wi) * CI + c];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + u * 256;
+      if (i < IW * IW * CI) sx[i] = v[u];
+    }
   }
   __syncthreads();
 
@@ -136,17 +156,58 @@ __global__ void __launch_bounds__(128) conv_small_dgrad_kernel(const float* __re
   const int hy_min = floor_div(h0 + p.pad_t - (p.k - 1), s), wx_min = floor_div(w0 + p.pad_l - (p.k - 1), s);
   const int cq = p.Co / 4;
 
-  for (int i = tid; i < KK * cq; i += 128) {
-    const int row = i / cq, q = i % cq;
-    *reinterpret_cast<float4*>(sw + row * pitch + q * 4) = *reinterpret_cast<const float4*>(w + (size_t)row * p.Co + q * 4);
-  }
   const float* dyb = dy + (size_t)b * p.Ho * p.Wo * p.Co;
-  for (int i = tid; i < PH * PW * cq; i += 128) {
-    const int q = i % cq, pix = i / cq, pw_ = pix % PW, ph_ = pix / PW;
-    const int hy = hy_min + ph_, wx = wx_min + pw_;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (hy >= 0 && hy < p.Ho && wx >= 0 && wx < p.Wo) v = *reinterpret_cast<const float4*>(dyb + ((size_t)hy * p.Wo + wx) * p.Co + q * 4);
-    *reinterpret_cast<float4*>(sdy + pix * pitch + q * 4) = v;
+  if (128 % cq == 0) {
+    // division-free fills: a thread keeps one float4 column q and walks rows / patch pixels with a fixed step (the generic
+    // form below spends 4 integer divisions per element — as many instructions as the FMA loop itself)
+    const int q4 = (tid % cq) * 4, first = tid / cq, step = 128 / cq;
+    for (int row = first; row < KK; row += 4 * step) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int rr = row + u * step;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rr < KK) v[u] = *reinterpret_cast<const float4*>(w + (size_t)rr * p.Co + q4);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int rr = row + u * step;
+        if (rr < KK) *reinterpret_cast<float4*>(sw + rr * pitch + q4) = v[u];
+      }
+    }
+    const int npix = PH * PW;
+    int ph_ = first / PW, pw_ = first % PW;
+    for (int pix = first; pix < npix; pix += 4 * step) {
+      float4 v[4];
+      int pp = pix, hh = ph_, ww = pw_;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int hy = hy_min + hh, wx = wx_min + ww;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pp < npix && hy >= 0 && hy < p.Ho && wx >= 0 && wx < p.Wo)
+          v[u] = *reinterpret_cast<const float4*>(dyb + ((size_t)hy * p.Wo + wx) * p.Co + q4);
+        pp += step; ww += step;
+        while (ww >= PW) { ww -= PW; ++hh; }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int pu = pix + u * step;
+        if (pu < npix) *reinterpret_cast<float4*>(sdy + pu * pitch + q4) = v[u];
+      }
+      ph_ = hh; pw_ = ww;
+    }
+  } else {
+    for (int i = tid; i < KK * cq; i += 128) {
+      const int row = i / cq, q = i % cq;
+      *reinterpret_cast<float4*>(sw + row * pitch + q * 4) = *reinterpret_cast<const float4*>(w + (size_t)row * p.Co + q * 4);
+    }
+    for (int i = tid; i < PH * PW * cq; i += 128) {
+      const int q = i % cq, pix = i / cq, pw_ = pix % PW, ph_ = pix / PW;
+      const int hy = hy_min + ph_, wx = wx_min + pw_;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (hy >= 0 && hy < p.Ho && wx >= 0 && wx < p.Wo) v = *reinterpret_cast<const float4*>(dyb + ((size_t)hy * p.Wo + wx) * p.Co + q * 4);
+      *reinterpret_cast<float4*>(sdy + pix * pitch + q * 4) = v;
+    }
   }
   __syncthreads();
 
@@ -166,6 +227,7 @@ __global__ void __launch_bounds__(128) conv_small_dgrad_kernel(const float* __re
       const int wx = (wv + p.pad_l - ss) / s - wx_min;
       const float* dp = sdy + (hy * PW + wx) * pitch;
       const float* wp = sw + ((r * p.k + ss) * CI) * pitch;
+#pragma unroll 4
       for (int q = 0; q < cq; ++q) {
         const float4 d = *reinterpret_cast<const float4*>(dp + q * 4);
 #pragma unroll
