@@ -11,7 +11,7 @@ python -c "import json;d=json.load(open('gpurun_out/bench_${tag}.json'));print('
 python bench.py --impl reference --steps 10 --warmup 2 2>&1 | tail -1 > gpurun_out/bench_ref_${tag}.json
 GG_CUDA_GRAPH=1 timeout 300 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_${tag}.csv python tools/profile_step.py 2>&1 | tail -1
 grep -c conv_tc gpurun_out/launches_${tag}.csv
-GG_CUDA_GRAPH=1 timeout 400 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:conv_tc -c 10 -o gpurun_out/prof_conv_${tag} python tools/profile_step.py 2>&1 | tail -1
+GG_CUDA_GRAPH=1 timeout 400 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:conv_tc -c 12 -o gpurun_out/prof_conv_${tag} python tools/profile_step.py 2>&1 | tail -1
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 python tools/profile_timeline.py gen > gpurun_out/timeline_gen_${tag}.txt 2>&1
 python tools/profile_timeline.py disc > gpurun_out/timeline_disc_${tag}.txt 2>&1
