@@ -1,0 +1,163 @@
+"""CPU: the plan compiler of gg/executor.py run against a host "device" (buffers are host tensors, launches are recorded,
+nothing executes): launch-list structure, the static multi-stream schedule, zero-copy row concat / row slices, the
+data-parallel launch-list cuts.  No kernel runs here; the numbers are checked on the GPU by tests/test_gpu_*.py."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "graphical-gan_b200", "scripts"))
+
+
+@pytest.fixture()
+def cpu_device(monkeypatch):
+    from gg import cabi, executor
+    monkeypatch.setattr(executor.Runtime, "dev", lambda self: torch.device("cpu"))
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    record = []
+    real = cabi.call
+
+    def fake(name, *args):
+        if name in ("gg_set_tc_max_ctas", "gg_set_tc_stages"):
+            return real(name, *args)
+        record.append((name, args))
+    monkeypatch.setattr(cabi, "call", fake)
+    executor.reset_runtime()
+    yield record
+    executor.reset_runtime()
+
+
+def _gmgan(batch=64):
+    import tensorflow as tf
+    import tflib as lib
+    import gmgan_inference_cifar10 as S
+    tf.reset_default_graph()
+    lib.delete_all_params()
+    np.random.seed(1234)
+    return S.build_graph(BATCH_SIZE=batch)
+
+
+def _plans(g):
+    from gg.executor import RT, Plan
+    return (Plan(RT, [g.gen_cost, g.gen_train_op], [g.real_x_int]), Plan(RT, [g.disc_cost, g.disc_train_op], [g.real_x_int]))
+
+
+def _group_deps(plan):
+    producer, deps, last_barrier, seen = {}, {}, None, []
+    for gi, g in enumerate(plan.groups):
+        d = set(producer[o] for o in g["reads"] if o in producer)
+        if last_barrier is not None:
+            d.add(last_barrier)
+        if g["barrier"]:
+            d |= set(seen)
+            last_barrier = gi
+        deps[gi] = d
+        producer[g["writes"]] = gi
+        seen.append(gi)
+    return deps
+
+
+@pytest.mark.parametrize("n_streams", [1, 2, 6, 12])
+def test_schedule_respects_every_dependency(cpu_device, n_streams):
+    """issue order is topological; every producer of a group is either earlier on the SAME stream or covered by an event wait
+    on a group at or after it on ITS stream; waited events are recorded before the wait is issued"""
+    for plan in _plans(_gmgan()):
+        order, assign, waits, need_event = plan._schedule_range(range(len(plan.groups)), n_streams)
+        assert sorted(order) == list(range(len(plan.groups)))
+        pos = {gi: i for i, gi in enumerate(order)}
+        deps = _group_deps(plan)
+        assert all(0 <= assign[g] < n_streams for g in order)
+        for gi in order:
+            for w in waits[gi]:
+                assert pos[w] < pos[gi] and w in need_event and assign[w] != assign[gi]
+            for d in deps[gi]:
+                assert pos[d] < pos[gi], "group %d issued before its producer %d" % (gi, d)
+                if assign[d] == assign[gi]:
+                    continue                                   # stream order
+                covered = any(assign[w] == assign[d] and pos[w] >= pos[d] for w in waits[gi])
+                # ... or transitively: an earlier group on MY stream already waited for it
+                if not covered:
+                    mine = [x for x in order[:pos[gi]] if assign[x] == assign[gi]]
+                    covered = any(assign[w] == assign[d] and pos[w] >= pos[d] for x in mine for w in waits[x])
+                assert covered, "dependency %d -> %d crosses streams without an event" % (d, gi)
+        if n_streams > 1:
+            assert 200.0 < plan.sched_estimate_us < 2000.0
+
+
+def test_heft_schedule_is_shorter_than_plan_order(cpu_device, monkeypatch):
+    """the simulated makespan of the list schedule is close to the critical path and well below the serial sum"""
+    gplan, dplan = _plans(_gmgan())
+    for plan in (gplan, dplan):
+        plan._schedule_range(range(len(plan.groups)), 6)
+        serial = sum(plan._group_cost(g) for g in plan.groups)
+        assert plan.sched_estimate_us < 0.6 * serial
+
+
+def test_sibling_batching_halves_discriminator_launches_and_concat_is_zero_copy(cpu_device, monkeypatch):
+    g = _gmgan()
+    gplan, dplan = _plans(g)
+
+    def heavy(plan):
+        return [n for n in plan.order if n.op in ("conv", "matmul")]
+    monkeypatch.setenv("GG_BATCH_SIBLINGS", "0")
+    g0 = _gmgan()
+    gplan0, dplan0 = _plans(g0)
+    assert len(heavy(dplan)) <= len(heavy(dplan0)) - 20 and len(heavy(gplan)) <= len(heavy(gplan0)) - 12
+    monkeypatch.delenv("GG_BATCH_SIBLINGS")
+    # every batched conv runs on 2x the rows; row concats of the towers' inputs own no copy kernels
+    assert any(n.op == "conv" and n.attrs["B"] == 128 for n in dplan.order)
+    for plan in (gplan, dplan):
+        assert plan.inplace_concat, "no zero-copy concat in the plan"
+        for node in plan.order:
+            if node.id in plan.inplace_concat:
+                base = plan.buf[node.id]
+                off = 0
+                for inp in node.inputs:
+                    piece = plan.buf[inp.id]
+                    assert piece.data_ptr() == base.data_ptr() + 4 * off, "concat piece is not placed inside the concat buffer"
+                    off += inp.size
+            if node.op == "slice" and plan._slice_is_view(node) and node.id not in plan.placed:
+                src = plan.buf[node.inputs[0].id]
+                inner = int(np.prod(node.inputs[0].shape[node.attrs["axis"] + 1:], dtype=np.int64))
+                assert plan.buf[node.id].data_ptr() == src.data_ptr() + 4 * node.attrs["start"] * inner
+
+
+def test_launch_list_uses_single_launch_batchnorm_and_fused_epilogues(cpu_device):
+    record = cpu_device
+    gplan, _ = _plans(_gmgan())
+    del record[:]
+    for f in gplan.steps:
+        f(0)
+    names = [n for n, _ in record]
+    assert "gg_bn_fwd_fused" in names and "gg_bn_bwd_fused" in names and "gg_bn_stats" not in names
+    assert names.count("gg_adam_multi") == 1 and names.count("gg_rng_tick") == 1
+    assert len(names) < 170, "G-step launch list grew to %d C-ABI calls" % len(names)
+    # LeakyReLU / ReLU / tanh never appear as their own launches: they ride conv / dense / BN epilogues
+    from gg import cabi
+    act_codes = {cabi.UNARY[k] for k in ("relu", "leaky", "tanh", "sigmoid")}
+    assert not [a for n, a in record if n == "gg_unary" and a[0] in act_codes]
+
+
+def test_data_parallel_plan_cuts_at_the_gradient_exchange_and_chains_statistic_exchanges(cpu_device, monkeypatch):
+    from gg import dist as ggdist
+
+    class FakeSmall(object):
+        MAX_FLOATS = 16384
+
+        def __call__(self, *a):
+            pass
+    monkeypatch.setattr(ggdist, "world_size", lambda: 2)
+    monkeypatch.setattr(ggdist, "small_all_reduce", lambda: FakeSmall())
+    gplan, dplan = _plans(_gmgan(32))
+    for plan in (gplan, dplan):
+        coll = [g for g in plan.groups if g["collective"]]
+        assert len(coll) == 1, "exactly ONE gradient all-reduce per optimiser step"
+        ordered = [i for i, g in enumerate(plan.groups) if g.get("ordered")]
+        assert len(ordered) >= 6                       # SyncBN statistic exchanges (+ the gradient exchange)
+        order, assign, waits, _ = plan._schedule_range([i for i, g in enumerate(plan.groups) if not g["collective"]], 6)
+        pos = {gi: i for i, gi in enumerate(order)}
+        seq = [gi for gi in order if plan.groups[gi].get("ordered")]
+        assert seq == sorted(seq, key=lambda gi: pos[gi]) and all(pos[a] < pos[b] for a, b in zip(seq, seq[1:]))
