@@ -147,3 +147,31 @@ def test_gmgan_mnist_graph_matches_oracle_autograd():
         for name, node in _grads_of(op).items():
             got, ref = it.run(node), ref_grads[name].numpy()
             assert np.abs(got - ref.reshape(got.shape)).max() <= 1e-8 * (np.abs(ref).max() + 1e-30) + 1e-13, name
+
+
+def test_objs_kl_matches_closed_forms_and_autograd():
+    """tflib/objs/kl.py:5-14 through the graph IR: values and gradients w.r.t. the posterior parameters vs torch"""
+    import tensorflow as tf
+    import tflib as lib
+    import tflib.objs.kl
+    from gg import ops as O
+    tf.reset_default_graph()
+    lib.delete_all_params()
+    rs = np.random.RandomState(3)
+    B, D = 6, 5
+    arrs = {k: rs.randn(B, D) for k in ("qm", "pm", "x", "mu")}
+    arrs.update({k: rs.uniform(0.5, 1.5, size=(B, D)) for k in ("qs", "ps", "std")})
+    ph = {k: tf.placeholder(tf.float32, shape=[B, D]) for k in arrs}
+    kl = lib.objs.kl.kl_q_p_diagonal_gaussian(ph["qm"], ph["qs"], ph["pm"], ph["ps"])
+    nll = lib.objs.kl.neg_log_likelihood_diagnoal_gaussian(ph["x"], ph["mu"], ph["std"])
+    g_qm, g_qs = O.gradients(kl, [ph["qm"], ph["qs"]])
+    g_mu, = O.gradients(nll, [ph["mu"]])
+    it = Interp({ph[k]: v for k, v in arrs.items()})
+    t = {k: torch.tensor(v, requires_grad=True) for k, v in arrs.items()}
+    ref_kl = (0.5 * (torch.log(t["ps"] ** 2 / t["qs"] ** 2) + ((t["pm"] - t["qm"]) ** 2 + t["qs"] ** 2) / t["ps"] ** 2 - 1)).sum(1).mean()
+    ref_nll = (0.5 * (((t["x"] - t["mu"]) / t["std"]) ** 2 + np.log(2 * np.pi) + 2 * torch.log(t["std"]))).sum(1).mean()
+    r_qm, r_qs = torch.autograd.grad(ref_kl, [t["qm"], t["qs"]])
+    r_mu, = torch.autograd.grad(ref_nll, [t["mu"]])
+    assert abs(float(it.run(kl)) - float(ref_kl.detach())) < 1e-12 and abs(float(it.run(nll)) - float(ref_nll.detach())) < 1e-12
+    for got, ref in ((g_qm, r_qm), (g_qs, r_qs), (g_mu, r_mu)):
+        assert np.abs(it.run(got) - ref.numpy()).max() < 1e-12
