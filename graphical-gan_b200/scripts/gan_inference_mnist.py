@@ -1,11 +1,13 @@
-"""ALI / ALICE / VEGAN / WALI(-GP) on SVHN — Python-3 port of the reference's gan_inference_svhn.py on the B200 kernels.
+"""ALI / ALICE / VEGAN / WALI(-GP) on MNIST — Python-3 port of the reference's gan_inference_mnist.py on the B200 kernels
+(this is the script BASELINE.json configs[0] names; its LOCAL_EP variant is gmgan_inference_mnist.py).
 
-This is the script that carries the WGAN-GP rows of the hot path:
-  * MODE='wali-gp'       critic on (x, z), conv; penalty on d D/d x_hat only ([0] of tf.gradients) — :342-357
-  * MODE='vegan-wgan-gp' critic on z, MLP with Gaussian noise layers — :302-316
-Both differentiate THROUGH tf.gradients when disc_cost is minimised (second-order backward through conv dgrad, dense
-layers and LeakyReLU masks).  Model functions and the graph section keep the reference's structure (line numbers refer to
-/root/reference/gan_inference_svhn.py); the graph is built inside build_graph() so tests can import it.
+1x28x28 images fed as float [0,1] (:248), sigmoid output (:142), the 8x8 -> 7x7 crop between the first two deconvolutions
+(:134), 28 -> 14 -> 7 -> 4 strided convolutions, BN_FLAG = True for the non-vegan modes (:66-71) — here also INSIDE the
+(x, z) critic (Discriminator.BN2 / BN3, :229-236), which also has two extra dense layers (Discriminator.2 on the z branch,
+zx2; :241-254).  Consequences: sibling batching of D(fake) / D(real) stops at the critic's batch norms (rows are coupled
+there: each tower keeps its own statistics, as in the reference), and MODE='wali-gp' would need the second-order gradient
+of batch norm, which no kernel provides — it raises NotImplementedError at graph construction (the reference's default MODE
+is 'ali').  Line numbers refer to /root/reference/gan_inference_mnist.py.
 """
 import os
 import sys
@@ -31,15 +33,14 @@ import tflib.plot
 SUPPORTED = ['ali', 'alice', 'alice-z', 'alice-x', 'vegan', 'vegan-wgan-gp', 'wali', 'wali-gp']
 
 
-def build_graph(MODE='ali', BATCH_SIZE=64, DIM=64, LR=2e-4, BN_FLAG=None):
+def build_graph(MODE='ali', BATCH_SIZE=50, DIM=64, LR=2e-4, BN_FLAG=None):
     if MODE not in SUPPORTED:
         raise NotImplementedError("MODE %r has no discriminator (VAE / MMD / KL baselines are off the adversarial hot path)" % MODE)
     DISTANCE_X = 'l2'
     CRITIC_ITERS = 5 if MODE in ['vegan', 'vegan-wgan-gp', 'wali', 'wali-gp'] else 1        # :46-51
-    LAMBDA, BETA1, OUTPUT_DIM = 1., .5, 3072
-    # :64-69: False in every branch of gan_inference_svhn.py; gan_inference_cifar10.py (same networks) passes True for the
-    # non-vegan modes (its :72-77).  The critics themselves carry no batch norm when BN_FLAG is off.
-    BN_FLAG = bool(BN_FLAG) if BN_FLAG is not None else False
+    LAMBDA, BETA1, OUTPUT_DIM = 1., .5, 784
+    if BN_FLAG is None:                                                                      # :66-71
+        BN_FLAG = MODE not in ('vegan', 'vegan-wgan-gp')
     DIM_LATENT = 8 if MODE in ['vegan', 'vegan-wgan-gp'] else 128
     N_VIS = BATCH_SIZE * 2
     DR_RATE = .2
@@ -63,17 +64,18 @@ def build_graph(MODE='ali', BATCH_SIZE=64, DIM=64, LR=2e-4, BN_FLAG=None):
         if BN_FLAG:
             output = lib.ops.batchnorm.Batchnorm('Generator.BN2', [0, 2, 3], output)
         output = tf.nn.relu(output)
+        output = output[:, :, :7, :7]                                                        # :134
         output = lib.ops.deconv2d.Deconv2D('Generator.3', 2 * DIM, DIM, 5, output)
         if BN_FLAG:
             output = lib.ops.batchnorm.Batchnorm('Generator.BN3', [0, 2, 3], output)
         output = tf.nn.relu(output)
-        output = lib.ops.deconv2d.Deconv2D('Generator.5', DIM, 3, 5, output)
-        output = tf.tanh(output)
+        output = lib.ops.deconv2d.Deconv2D('Generator.5', DIM, 1, 5, output)
+        output = tf.nn.sigmoid(output)
         return tf.reshape(output, [-1, OUTPUT_DIM]), None, None
 
     def Extractor(inputs):                                                                  # :151-180
-        output = tf.reshape(inputs, [-1, 3, 32, 32])
-        output = lib.ops.conv2d.Conv2D('Extractor.1', 3, DIM, 5, output, stride=2)
+        output = tf.reshape(inputs, [-1, 1, 28, 28])
+        output = lib.ops.conv2d.Conv2D('Extractor.1', 1, DIM, 5, output, stride=2)
         output = LeakyReLU(output)
         output = lib.ops.conv2d.Conv2D('Extractor.2', DIM, 2 * DIM, 5, output, stride=2)
         if BN_FLAG:
@@ -112,31 +114,37 @@ def build_graph(MODE='ali', BATCH_SIZE=64, DIM=64, LR=2e-4, BN_FLAG=None):
             output = lib.ops.linear.Linear('Discriminator.Output', 256, 1, output)
             return tf.reshape(output, [-1])
     else:
-        def Discriminator(x, z):                                                            # :216-240 critic on (x, z)
-            output = tf.reshape(x, [-1, 3, 32, 32])
-            output = lib.ops.conv2d.Conv2D('Discriminator.1', 3, DIM, 5, output, stride=2)
+        def Discriminator(x, z):                                                            # :221-256 critic on (x, z)
+            output = tf.reshape(x, [-1, 1, 28, 28])
+            output = lib.ops.conv2d.Conv2D('Discriminator.1', 1, DIM, 5, output, stride=2)
             output = LeakyReLU(output)
-            output = tf.layers.dropout(output, rate=DR_RATE)
             output = lib.ops.conv2d.Conv2D('Discriminator.2', DIM, 2 * DIM, 5, output, stride=2)
+            if BN_FLAG:
+                output = lib.ops.batchnorm.Batchnorm('Discriminator.BN2', [0, 2, 3], output)
             output = LeakyReLU(output)
-            output = tf.layers.dropout(output, rate=DR_RATE)
             output = lib.ops.conv2d.Conv2D('Discriminator.3', 2 * DIM, 4 * DIM, 5, output, stride=2)
+            if BN_FLAG:
+                output = lib.ops.batchnorm.Batchnorm('Discriminator.BN3', [0, 2, 3], output)
             output = LeakyReLU(output)
-            output = tf.layers.dropout(output, rate=DR_RATE)
             output = tf.reshape(output, [-1, 4 * 4 * 4 * DIM])
             z_output = lib.ops.linear.Linear('Discriminator.z1', DIM_LATENT, 512, z)
+            z_output = LeakyReLU(z_output)
+            z_output = tf.layers.dropout(z_output, rate=DR_RATE)
+            z_output = lib.ops.linear.Linear('Discriminator.2', 512, 512, z_output)       # (sic) shares the prefix of the conv
             z_output = LeakyReLU(z_output)
             z_output = tf.layers.dropout(z_output, rate=DR_RATE)
             output = tf.concat([output, z_output], 1)
             output = lib.ops.linear.Linear('Discriminator.zx1', 4 * 4 * 4 * DIM + 512, 512, output)
             output = LeakyReLU(output)
             output = tf.layers.dropout(output, rate=DR_RATE)
+            output = lib.ops.linear.Linear('Discriminator.zx2', 512, 512, output)
+            output = LeakyReLU(output)
+            output = tf.layers.dropout(output, rate=DR_RATE)
             output = lib.ops.linear.Linear('Discriminator.Output', 512, 1, output)
             return tf.reshape(output, [-1])
 
     # ---- losses (:246-360) ----
-    real_x_int = tf.placeholder(tf.int32, shape=[BATCH_SIZE, OUTPUT_DIM])
-    real_x = 2 * ((tf.cast(real_x_int, tf.float32) / 255.) - .5)
+    real_x = tf.placeholder(tf.float32, shape=[BATCH_SIZE, OUTPUT_DIM])                      # :248: float [0,1] images
     q_z, _, _ = Extractor(real_x)
     rec_x, _, _ = Generator(q_z)
     p_z = tf.random_normal([BATCH_SIZE, DIM_LATENT])
@@ -194,7 +202,7 @@ def build_graph(MODE='ali', BATCH_SIZE=64, DIM=64, LR=2e-4, BN_FLAG=None):
 
     np_fixed = np.random.normal(size=(N_VIS, DIM_LATENT)).astype('float32')
     fixed_noise_samples, _, _ = Generator(tf.constant(np_fixed))
-    ns.__dict__.update(real_x_int=real_x_int, real_x=real_x, q_z=q_z, p_z=p_z, fake_x=fake_x, rec_x=rec_x, rec_z=rec_z, alpha=alpha,
+    ns.__dict__.update(real_x=real_x, q_z=q_z, p_z=p_z, fake_x=fake_x, rec_x=rec_x, rec_z=rec_z, alpha=alpha,
                        disc_fake=disc_fake, disc_real=disc_real, gradient_penalty=gradient_penalty, rec_penalty=rec_penalty,
                        gen_params=gen_params, ext_params=ext_params, disc_params=disc_params, gen_cost=gen_cost, disc_cost=disc_cost,
                        gen_train_op=gen_train_op, disc_train_op=disc_train_op, clip_disc_weights=clip_disc_weights,
@@ -204,32 +212,40 @@ def build_graph(MODE='ali', BATCH_SIZE=64, DIM=64, LR=2e-4, BN_FLAG=None):
 
 def main(argv=None):
     import argparse
-    from gmgan_inference_cifar10 import synthetic_batches
+    from gmgan_inference_mnist import synthetic_batches
     ap = argparse.ArgumentParser()
     ap.add_argument('--mode', default='ali', choices=SUPPORTED)
     ap.add_argument('--iters', type=int, default=200000)
-    ap.add_argument('--batch-size', type=int, default=64)
-    ap.add_argument('--out', default=None)
+    ap.add_argument('--batch-size', type=int, default=50)
+    ap.add_argument('--synthetic', action='store_true')
     args = ap.parse_args(argv)
-    outf = args.out or os.path.join("result", "gan_inference_svhn.MODE-%s.%d" % (args.mode, int(time.time())))
-    os.makedirs(outf, exist_ok=True)
-    logfile = os.path.join(outf, 'logfile.txt')
     g = build_graph(MODE=args.mode, BATCH_SIZE=args.batch_size)
-    gen = synthetic_batches(args.batch_size)        # the SVHN .mat loader (tflib/svhn.py) needs scipy.io + the dataset on disk
+    gen = None
+    if not args.synthetic and os.path.isfile('/tmp/mnist.pkl.gz'):
+        import tflib.mnist
+        train_gen, _, _ = lib.mnist.load(args.batch_size, args.batch_size)
+
+        def inf_train_gen():
+            while True:
+                for images, _ in train_gen():
+                    yield images
+        gen = inf_train_gen()
+    if gen is None:
+        gen = synthetic_batches(args.batch_size)
     with tf.Session() as session:
         session.run(tf.global_variables_initializer())
-        for iteration in range(args.iters):
+        for iteration in range(args.iters):                                                  # :400-430
             start_time = time.time()
             if iteration > 0:
-                _gen_cost, _ = session.run([g.gen_cost, g.gen_train_op], feed_dict={g.real_x_int: next(gen)})
+                session.run([g.gen_cost, g.gen_train_op], feed_dict={g.real_x: next(gen)})
             for i in range(g.CRITIC_ITERS):
-                _disc_cost, _ = session.run([g.disc_cost, g.disc_train_op], feed_dict={g.real_x_int: next(gen)})
-                if args.mode == 'wali':
+                dc, _ = session.run([g.disc_cost, g.disc_train_op], feed_dict={g.real_x: next(gen)})
+                if g.clip_disc_weights is not None:
                     session.run(g.clip_disc_weights)
-            lib.plot.plot('train disc cost', _disc_cost)
+            lib.plot.plot('train disc cost', dc)
             lib.plot.plot('time', time.time() - start_time)
             if (iteration < 5) or (iteration % 100 == 99):
-                lib.plot.flush(outf, logfile)
+                lib.plot.flush()
             lib.plot.tick()
 
 

@@ -101,6 +101,9 @@ def _families():
     import gmgan_inference_mnist as N
     return {
         "gmgan_mnist_local_ep": lambda: N.build_graph(BATCH_SIZE=3),
+        "gan_mnist_ali_bn_in_critic": lambda: __import__("gan_inference_mnist").build_graph(MODE='ali', BATCH_SIZE=3),
+        "gan_cifar10_wali_gp": lambda: __import__("gan_inference_cifar10").build_graph(MODE='wali-gp', BATCH_SIZE=2, DIM=16),
+        "ssgan_chairs": lambda: __import__("ssgan_inference_chairs").build_graph(BATCH_SIZE=2, LEN=3, DIM=8),
         "gmgan_face_local_ep": lambda: __import__("gmgan_inference_face").build_graph(BATCH_SIZE=2, N_COMS=5, DIM_G=8, DIM_D=8),
         "gmgan_svhn_local_epce": lambda: __import__("gmgan_inference_svhn").build_graph(MODE='local_epce', BATCH_SIZE=2),
         "gmgan_cifar10_local_ep": lambda: C.build_graph(BATCH_SIZE=4),
@@ -111,7 +114,7 @@ def _families():
 
 
 @pytest.mark.parametrize("family", ["gmgan_cifar10_local_ep", "gmgan_mnist_local_ep", "gmgan_svhn_local_epce", "gmgan_face_local_ep",
-                                    "gan_svhn_wali_gp", "gan_face_ali",
+                                    "gan_svhn_wali_gp", "gan_face_ali", "gan_mnist_ali_bn_in_critic", "gan_cifar10_wali_gp", "ssgan_chairs",
                                     "ssgan_moving_mnist"])
 def test_sibling_batching_preserves_costs_and_gradients(family):
     build = _families()[family]
