@@ -132,6 +132,117 @@ __global__ void __launch_bounds__(256) conv_small_fwd_kernel(const float* __rest
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// forward, variant 2 (GG_CONV_SMALL_V2=1; NOT yet validated on a GPU — written after the round's GPU budget was spent, index
+// arithmetic pinned by tests/test_cpu_small_conv.py): 4 pixels x 8 channels per thread (32 accumulators) and the k x k tap
+// loop unrolled for k = 5, i.e. 2 weight LDS.128 + 4 input LDS.32 per 32 FMAs (73 % FMA density instead of 46 %).
+// Block = 128 threads = 8 channel octets x 16 pixel lanes over the same 8x8-pixel x 64-channel tile and smem layout.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int CI, int KS>
+__global__ void __launch_bounds__(128) conv_small_fwd_v2_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                const float* __restrict__ bias, float* __restrict__ y, SmallP p,
+                                                                int act, float alpha) {
+  extern __shared__ __align__(16) float smem_f[];
+  const int k = KS > 0 ? KS : p.k;
+  const int K = k * k * CI;
+  const int IW = (kTile - 1) * p.stride + k;
+  float* sw = smem_f;                                   // [K][64]
+  float* sx = smem_f + K * kChunk;                      // [IW][IW][CI]
+  const int tiles_w = (p.Wo + kTile - 1) / kTile;
+  const int ho0 = (blockIdx.x / tiles_w) * kTile, wo0 = (blockIdx.x % tiles_w) * kTile;
+  const int b = blockIdx.y;
+  const int co0 = blockIdx.z * kChunk;
+  const int nco = min(kChunk, p.Co - co0);
+  const int tid = threadIdx.x;
+  for (int base = tid; base < K * (kChunk / 4); base += 4 * 128) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + u * 128;
+      const int kk = i / (kChunk / 4), q = i % (kChunk / 4);
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < K * (kChunk / 4) && q * 4 < nco) v[u] = *reinterpret_cast<const float4*>(w + (size_t)kk * p.Co + co0 + q * 4);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + u * 128;
+      if (i < K * (kChunk / 4)) *reinterpret_cast<float4*>(sw + (i / (kChunk / 4)) * kChunk + (i % (kChunk / 4)) * 4) = v[u];
+    }
+  }
+  const int hi0 = ho0 * p.stride - p.pad_t, wi0 = wo0 * p.stride - p.pad_l;
+  const float* xb = x + (size_t)b * p.H * p.W * CI;
+  for (int i = tid; i < IW * IW * CI; i += 128) {
+    const int c = i % CI, iw = (i / CI) % IW, ih = i / (CI * IW);
+    const int hi = hi0 + ih, wi = wi0 + iw;
+    float v = 0.f;
+    if (hi >= 0 && hi < p.H && wi >= 0 && wi < p.W) v = xb[((size_t)hi * p.W + wi) * CI + c];
+    sx[i] = v;
+  }
+  __syncthreads();
+
+  const int co8 = (tid & 7) * 8, pl = tid >> 3;         // channel octet, pixel lane (pixels pl, pl+16, pl+32, pl+48)
+  int xo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int pix = pl + 16 * j, py = pix / kTile, px = pix % kTile;
+    xo[j] = ((py * p.stride) * IW + px * p.stride) * CI;
+  }
+  float acc[4][8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
+  const float* swq = sw + co8;
+#pragma unroll
+  for (int r = 0; r < (KS > 0 ? KS : 1); ++r) {
+    for (int rr = (KS > 0 ? r : 0); rr < (KS > 0 ? r + 1 : k); ++rr) {        // KS == 0: runtime loop over all rows
+#pragma unroll
+      for (int s = 0; s < (KS > 0 ? KS : 1); ++s) {
+        for (int ss = (KS > 0 ? s : 0); ss < (KS > 0 ? s + 1 : k); ++ss) {
+          const int xoff = (rr * IW + ss) * CI;
+          const int kk0 = (rr * k + ss) * CI;
+#pragma unroll
+          for (int c = 0; c < CI; ++c) {
+            const float4 w0 = *reinterpret_cast<const float4*>(swq + (kk0 + c) * kChunk);
+            const float4 w1 = *reinterpret_cast<const float4*>(swq + (kk0 + c) * kChunk + 4);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float xv = sx[xo[j] + xoff + c];
+              acc[j][0] = fmaf(xv, w0.x, acc[j][0]); acc[j][1] = fmaf(xv, w0.y, acc[j][1]);
+              acc[j][2] = fmaf(xv, w0.z, acc[j][2]); acc[j][3] = fmaf(xv, w0.w, acc[j][3]);
+              acc[j][4] = fmaf(xv, w1.x, acc[j][4]); acc[j][5] = fmaf(xv, w1.y, acc[j][5]);
+              acc[j][6] = fmaf(xv, w1.z, acc[j][6]); acc[j][7] = fmaf(xv, w1.w, acc[j][7]);
+            }
+          }
+        }
+      }
+    }
+  }
+  if (co8 >= nco) return;                               // nco is a multiple of 4: the second quad of an octet may be outside
+  const bool hi_ok = co8 + 4 < nco;
+  float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+  if (bias) {
+    b0 = *reinterpret_cast<const float4*>(bias + co0 + co8);
+    if (hi_ok) b1 = *reinterpret_cast<const float4*>(bias + co0 + co8 + 4);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int pix = pl + 16 * j, ho = ho0 + pix / kTile, wo = wo0 + pix % kTile;
+    if (ho < p.Ho && wo < p.Wo) {
+      float* o = y + (((size_t)b * p.Ho + ho) * p.Wo + wo) * p.Co + co0 + co8;
+      float4 v0, v1;
+      v0.x = apply_act(acc[j][0] + b0.x, act, alpha); v0.y = apply_act(acc[j][1] + b0.y, act, alpha);
+      v0.z = apply_act(acc[j][2] + b0.z, act, alpha); v0.w = apply_act(acc[j][3] + b0.w, act, alpha);
+      *reinterpret_cast<float4*>(o) = v0;
+      if (hi_ok) {
+        v1.x = apply_act(acc[j][4] + b1.x, act, alpha); v1.y = apply_act(acc[j][5] + b1.y, act, alpha);
+        v1.z = apply_act(acc[j][6] + b1.z, act, alpha); v1.w = apply_act(acc[j][7] + b1.w, act, alpha);
+        *reinterpret_cast<float4*>(o + 4) = v1;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // dgrad (and Deconv2D forward) towards CI <= 4 channels
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kDH = 8, kDW = 16;   // output pixels per block: 8 rows x 16 columns = 128 threads
@@ -271,6 +382,22 @@ int conv_small_fwd(const float* x, const float* w, const float* bias, float* y, 
   const size_t smem = ((size_t)k * k * Ci * kChunk + (size_t)IW * IW * Ci) * sizeof(float);
   if (smem > 48 * 1024 || B > 65535) return GG_OK;
   dim3 grid(ceil_div(Ho, kTile) * ceil_div(Wo, kTile), B, ceil_div(Co, kChunk));
+  static int v2 = -1;
+  if (v2 < 0) { const char* e = getenv("GG_CONV_SMALL_V2"); v2 = (e && e[0] == '1') ? 1 : 0; }
+  if (v2) {
+#define GG_V2(CI_)                                                                                                        \
+    if (k == 5) conv_small_fwd_v2_kernel<CI_, 5><<<grid, 128, smem, st>>>(x, w, bias, y, p, act, alpha);                    \
+    else conv_small_fwd_v2_kernel<CI_, 0><<<grid, 128, smem, st>>>(x, w, bias, y, p, act, alpha)
+    switch (Ci) {
+      case 1: GG_V2(1); break;
+      case 2: GG_V2(2); break;
+      case 3: GG_V2(3); break;
+      default: GG_V2(4); break;
+    }
+#undef GG_V2
+    *handled = true;
+    return check_launch("gg_conv2d_fwd(small-channel v2)");
+  }
   switch (Ci) {
     case 1: conv_small_fwd_kernel<1><<<grid, 256, smem, st>>>(x, w, bias, y, p, act, alpha); break;
     case 2: conv_small_fwd_kernel<2><<<grid, 256, smem, st>>>(x, w, bias, y, p, act, alpha); break;

@@ -92,6 +92,17 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     conv_case(64, 16, 16, 64, 128)
     conv_case(64, 8, 8, 128, 256)
+    if which in ("all", "batched"):
+        # the shapes the step actually launches after sibling batching (fake + real towers: 128 rows)
+        conv_case(128, 32, 32, 3, 64)
+        conv_case(128, 16, 16, 64, 128)
+        conv_case(128, 8, 8, 128, 256)
+    if which in ("all", "3x3"):
+        # 3x3 stride 1 / 2 at the same channel counts: a SYNTHETIC extra for BASELINE.json's "conv3x3" wording — the
+        # reference has no 3x3 convolution anywhere; filter_size is a free argument of the op
+        conv_case(64, 16, 16, 64, 128, k=3, s=1)
+        conv_case(64, 16, 16, 64, 128, k=3, s=2)
+        conv_case(64, 8, 8, 128, 256, k=3, s=1)
     if which == "all":
         conv_case(64, 32, 32, 3, 64)
         conv_case(128, 32, 32, 32, 64)
