@@ -234,7 +234,9 @@ def run_ours(args):
         e1.record()
         evs.append((e0, e1))
     barrier()
-    dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+    per_step = [e0.elapsed_time(e1) for e0, e1 in evs]
+    dev_ms = sum(per_step)
+    pct = [float(np.percentile(per_step, q)) for q in (10, 50, 90)]
     # hot-L2 variant (no flush), back-to-back, one event pair around all K steps
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -293,7 +295,8 @@ def run_ours(args):
         "config": {"workload": "gmgan_inference_cifar10.py MODE=local_ep bs=64 per GPU, 32x32x3 (BASELINE.json configs[1])",
                    "global_batch": BATCH * world, "parallelism": "dp%d" % world,
                    "l2": "256 MiB memset between timed steps, outside the per-step CUDA-event brackets",
-                   "ms_per_step_hot_l2": hot_ms / args.steps, "cuda_graph": bool(RT.use_cuda_graph),
+                   "ms_per_step_hot_l2": hot_ms / args.steps, "ms_per_step_p10_p50_p90_rank0": pct,
+                   "cuda_graph": bool(RT.use_cuda_graph),
                    "algorithmic_gflop_per_iteration": GF_PER_ITER,
                    "last_costs": [float(last[0]), float(last[1])]},
         "e2e": {"value": images / (e2e_ms / 1e3), "unit": "images/sec",
