@@ -223,8 +223,10 @@ def build_graph(MODE='local_ep', BATCH_SIZE=64, DIM=64, N_COMS=30, LR=2e-4, MODE
     else:
         disc_real = Discriminator(real_x, q_z, q_k)
         disc_fake = Discriminator(fake_x, p_z, hyper_p_k)
-    if MODE_K == 'REINFORCE':
-        raise NotImplementedError("MODE_K='REINFORCE' (tflib/objs/discrete_variables.py) is a non-default estimator")
+    if MODE_K == 'REINFORCE':                                                    # score-function estimator for the hard k
+        import tflib.objs.discrete_variables
+        critic_on_real = disc_real[0] if MODE in ['local_ep', 'local_epce'] else disc_real
+        score_function = lib.objs.discrete_variables.score_function(critic_on_real, q_k_prob_max, CONTROL_VARIATE)
 
     gen_params = lib.params_with_name('Generator')
     ext_params = lib.params_with_name('Extractor')

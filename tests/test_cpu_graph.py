@@ -90,7 +90,8 @@ def _eval_family(build, batching, seed):
     it = Interp(feeds)
     n_heavy = sum(1 for n in nodes if n.op in ("conv", "matmul"))
     vals = {k: it.run(v) for k, v in grads.items()}
-    return float(it.run(g.gen_cost)), float(it.run(g.disc_cost)), vals, n_heavy
+    # (gen_cost is a [B] vector in REINFORCE mode — scalar + per-sample score function, as in the reference; minimise sums it)
+    return float(np.sum(it.run(g.gen_cost))), float(np.sum(it.run(g.disc_cost))), vals, n_heavy
 
 
 def _families():
@@ -101,6 +102,7 @@ def _families():
     import gmgan_inference_mnist as N
     return {
         "gmgan_mnist_local_ep": lambda: N.build_graph(BATCH_SIZE=3),
+        "gmgan_cifar10_reinforce": lambda: C.build_graph(BATCH_SIZE=3, MODE_K='REINFORCE'),
         "gan_mnist_ali_bn_in_critic": lambda: __import__("gan_inference_mnist").build_graph(MODE='ali', BATCH_SIZE=3),
         "gan_cifar10_wali_gp": lambda: __import__("gan_inference_cifar10").build_graph(MODE='wali-gp', BATCH_SIZE=2, DIM=16),
         "ssgan_chairs": lambda: __import__("ssgan_inference_chairs").build_graph(BATCH_SIZE=2, LEN=3, DIM=8),
@@ -115,6 +117,7 @@ def _families():
 
 @pytest.mark.parametrize("family", ["gmgan_cifar10_local_ep", "gmgan_mnist_local_ep", "gmgan_svhn_local_epce", "gmgan_face_local_ep",
                                     "gan_svhn_wali_gp", "gan_face_ali", "gan_mnist_ali_bn_in_critic", "gan_cifar10_wali_gp", "ssgan_chairs",
+                                    "gmgan_cifar10_reinforce",
                                     "ssgan_moving_mnist"])
 def test_sibling_batching_preserves_costs_and_gradients(family):
     build = _families()[family]
