@@ -189,6 +189,30 @@ def clip_by_value(x, lo, hi):
     return O.unary("clip", x, float(lo), float(hi))
 
 
+def scalar_mul(scalar, x):
+    return O.mul(x, float(scalar))
+
+
+def ones(shape, dtype=None, name=None):
+    return O.constant(np.ones([int(v) for v in shape], np.float32))
+
+
+def zeros(shape, dtype=None, name=None):
+    return O.constant(np.zeros([int(v) for v in shape], np.float32))
+
+
+def diag_part(x):
+    """diagonal of a square matrix (tflib/objs/mmd.py:28-29): a masked row sum — no gather kernel needed"""
+    n = x.shape[0]
+    if len(x.shape) != 2 or x.shape[1] != n:
+        raise ValueError("diag_part expects a square matrix, got %s" % (tuple(x.shape),))
+    return O.reduce("sum", O.mul(x, O.constant(np.eye(n, dtype=np.float32))), [1], False)
+
+
+def trace(x):
+    return O.reduce("sum", diag_part(x), [0], False)
+
+
 def matmul(a, b, transpose_a=False, transpose_b=False):
     return O.matmul(a, b, transpose_a, transpose_b)
 

@@ -181,3 +181,67 @@ def test_objs_kl_matches_closed_forms_and_autograd():
     assert abs(float(it.run(kl)) - float(ref_kl.detach())) < 1e-12 and abs(float(it.run(nll)) - float(ref_nll.detach())) < 1e-12
     for got, ref in ((g_qm, r_qm), (g_qs, r_qs), (g_mu, r_mu)):
         assert np.abs(it.run(got) - ref.numpy()).max() < 1e-12
+
+
+def test_objs_kl_aggregated_matches_numpy_estimators():
+    """tflib/objs/kl_aggregated.py:17-72 through the graph IR with the Monte-Carlo draws injected: ikl and the two
+    mixture log-likelihoods against direct NumPy evaluations (logsumexp form)"""
+    import tensorflow as tf
+    import tflib as lib
+    import tflib.objs.kl_aggregated as KA
+    from gg.ops import toposort
+    tf.reset_default_graph()
+    lib.delete_all_params()
+    rs = np.random.RandomState(8)
+    nx, nz, dz = 5, 7, 3
+    mu, std = rs.randn(nx, dz), rs.uniform(0.5, 1.5, size=(nx, dz))
+    pm, ps = np.zeros((nz, dz)), np.ones((nz, dz))
+    z = rs.randn(nz, dz)
+    t = {k: tf.placeholder(tf.float32, shape=list(v.shape)) for k, v in (("mu", mu), ("std", std), ("pm", pm), ("ps", ps), ("z", z))}
+    lq = KA.log_likelihood_mixture_gaussian(t["z"], t["mu"], t["std"])
+    lm = KA.log_likelihood_mixture_mixture_gaussian(t["z"], t["mu"], t["std"], t["pm"], t["ps"], nx)
+    ikl = KA.ikl_q_aggregated_p_diagonal_gaussian(t["mu"], t["std"], t["pm"], t["ps"], nz, dz)
+    feeds = {t["mu"]: mu, t["std"]: std, t["pm"]: pm, t["ps"]: ps, t["z"]: z}
+    for n in toposort([ikl]):
+        if n.op == "random":
+            feeds[n] = z                                  # the estimator's own z ~ p draw
+    it = Interp(feeds)
+
+    def ll(x, m, s):
+        return (-.5 * (((x - m) / s) ** 2 + np.log(2 * np.pi) + 2 * np.log(s))).sum(-1)
+    mat = ll(z[:, None, :], mu[None], std[None])                                           # [nz, nx]
+    ref_lq = np.log(np.exp(mat).mean(1))
+    ref_lp = ll(z, pm, ps)
+    ref_lm = np.log(np.concatenate([np.exp(mat), np.tile(np.exp(ref_lp)[:, None], (1, nx))], 1).mean(1))
+    assert np.abs(it.run(lq) - ref_lq).max() < 1e-10 and np.abs(it.run(lm) - ref_lm).max() < 1e-10
+    assert abs(float(it.run(ikl)) - float((ref_lp - ref_lq).mean())) < 1e-10
+
+
+def test_objs_mmd_matches_numpy_and_autograd():
+    """tflib/objs/mmd.py through the graph IR: biased and unbiased mixed-RBF MMD^2 and d/dX vs torch"""
+    import tensorflow as tf
+    import tflib as lib
+    import tflib.objs.mmd as MM
+    from gg import ops as O
+    tf.reset_default_graph()
+    lib.delete_all_params()
+    rs = np.random.RandomState(4)
+    X, Y = rs.randn(6, 3), rs.randn(5, 3) * 1.3
+    tx, ty = tf.placeholder(tf.float32, shape=[6, 3]), tf.placeholder(tf.float32, shape=[5, 3])
+    biased = MM.mix_rbf_mmd2(tx, ty)
+    unbiased = MM.mix_rbf_mmd2(tx, ty, biased=False)
+    gx, = O.gradients(biased, [tx])
+    it = Interp({tx: X, ty: Y})
+    a, b = torch.tensor(X, requires_grad=True), torch.tensor(Y)
+
+    def kern(u, v):
+        d2 = ((u[:, None, :] - v[None, :, :]) ** 2).sum(-1)
+        return sum(torch.exp(-d2 / (2 * s ** 2)) for s in MM.SIGMAS)
+    kxx, kxy, kyy = kern(a, a), kern(a, b), kern(b, b)
+    ref_b = kxx.sum() / 36 + kyy.sum() / 25 - 2 * kxy.sum() / 30
+    d = float(len(MM.SIGMAS))
+    ref_u = (kxx.sum() - 6 * d) / 30 + (kyy.sum() - 5 * d) / 20 - 2 * kxy.sum() / 30
+    rg, = torch.autograd.grad(ref_b, [a])
+    assert abs(float(it.run(biased)) - float(ref_b.detach())) < 1e-10
+    assert abs(float(it.run(unbiased)) - float(ref_u.detach())) < 1e-10
+    assert np.abs(it.run(gx) - rg.numpy()).max() < 1e-10
