@@ -26,12 +26,12 @@ def main(path, which):
         elif cur is not None and cur["hdr"] is not None:
             cur["rows"].append(row)
     # group consecutive blocks by kernel launch: a new launch starts when the same file repeats for the same function
-    launches, seen = [], None
+    launches, seen, func = [], None, None
     for b in blocks:
         key = (b["func"], b["file"])
-        if seen is None or key in seen:
+        if seen is None or key in seen or b["func"] != func:
             launches.append([])
-            seen = set()
+            seen, func = set(), b["func"]
         seen.add(key)
         launches[-1].append(b)
     print("# %s: %d kernel launches with source pages; showing launch %d" % (path, len(launches), which))
