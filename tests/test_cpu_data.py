@@ -71,3 +71,26 @@ def test_save_images_grid(tmp_path):
     V.save_images(x, str(tmp_path / "grid.png"), size=(2, 3))
     assert Image.open(str(tmp_path / "grid.png")).size == (15, 8)
     assert V.large_image(np.zeros((9, 784), np.float32)).shape == (84, 84)
+
+
+def test_moving_mnist_sequences(tmp_path):
+    import tflib.simple_moving_mnist as MM
+    np.random.seed(3)
+    sy, sx = MM.GetRandomTrajectory(0.1, 40, 50, 64, 28)
+    assert sy.shape == (40, 50) and sy.min() >= 0 and sy.max() <= 36 and sx.min() >= 0 and sx.max() <= 36
+    step = np.hypot(np.diff(sy, axis=0), np.diff(sx, axis=0))
+    assert step.max() <= 0.1 * 36 * np.sqrt(2) + 2                 # unit speed, step 0.1 of the 36-pixel canvas
+    assert (np.abs(np.diff(np.sign(np.diff(sx, axis=0)), axis=0)) > 0).any()   # somebody bounced
+    digit = np.zeros((1, 28, 28), np.float32); digit[0, 3:7, 10:12] = 0.8
+    v = MM.render(digit, np.array([[5], [30]]), np.array([[2], [36]]))
+    assert v.shape == (1, 2, 64, 64) and v[0, 0, 8:12, 12:14].min() == np.float32(0.8) and v[0, 0].sum() == np.float32(0.8) * 8
+    assert v[0, 1, 33:37, 46:48].min() == np.float32(0.8)
+    rs = np.random.RandomState(1)
+    sets = tuple((rs.uniform(0, 1, size=(n, 784)).astype(np.float32), rs.randint(0, 10, size=n)) for n in (12, 4, 6))
+    path = str(tmp_path / "mnist.pkl.gz")
+    with gzip.open(path, 'wb') as f:
+        pickle.dump(sets, f, protocol=2)
+    train, test = MM.load_video(5, 4, filepath=path)
+    vids, labels = next(train())
+    assert vids.shape == (4, 5, 4096) and vids.dtype == np.float32 and labels.shape == (4,) and len(list(train())) == 4
+    assert len(list(test())) == 1
