@@ -161,3 +161,53 @@ def test_data_parallel_plan_cuts_at_the_gradient_exchange_and_chains_statistic_e
         pos = {gi: i for i, gi in enumerate(order)}
         seq = [gi for gi in order if plan.groups[gi].get("ordered")]
         assert seq == sorted(seq, key=lambda gi: pos[gi]) and all(pos[a] < pos[b] for a, b in zip(seq, seq[1:]))
+
+
+ALL_SCRIPTS = {
+    "gmgan_inference_mnist": dict(BATCH_SIZE=4),
+    "gmgan_inference_cifar10": dict(BATCH_SIZE=4),
+    "gmgan_inference_cifar10:reinforce": dict(BATCH_SIZE=4, MODE_K='REINFORCE'),
+    "gmgan_inference_cifar10:local_epce": dict(BATCH_SIZE=4, MODE='local_epce'),
+    "gmgan_inference_svhn": dict(BATCH_SIZE=4),
+    "gmgan_inference_face": dict(BATCH_SIZE=2, N_COMS=10),
+    "gmgan_inference_face:ali": dict(BATCH_SIZE=2, N_COMS=10, MODE='ali'),
+    "gan_inference_mnist": dict(BATCH_SIZE=4),
+    "gan_inference_mnist:vegan-wgan-gp": dict(BATCH_SIZE=4, MODE='vegan-wgan-gp'),
+    "gan_inference_cifar10:wali-gp": dict(BATCH_SIZE=4, MODE='wali-gp'),
+    "gan_inference_cifar10:alice": dict(BATCH_SIZE=4, MODE='alice'),
+    "gan_inference_svhn:wali": dict(BATCH_SIZE=4, MODE='wali'),
+    "gan_inference_face": dict(BATCH_SIZE=2),
+    "ssgan_inference_moving_mnist": dict(BATCH_SIZE=2, LEN=4),
+    "ssgan_inference_chairs": dict(BATCH_SIZE=2, LEN=4),
+    "ssgan_inference_chairs:local_epce-z": dict(BATCH_SIZE=2, LEN=3, MODE='local_epce-z'),
+}
+
+
+@pytest.mark.parametrize("script", sorted(ALL_SCRIPTS))
+def test_every_script_compiles_to_a_launch_list(cpu_device, script):
+    """all ten reference scripts (and their non-default modes) go through the plan compiler: every node has a launcher,
+    every layout pattern fits the kernels' index limits, both train steps schedule on 6 streams"""
+    import importlib
+    import tensorflow as tf
+    import tflib as lib
+    from gg.executor import RT, Plan
+    from gg.ops import toposort
+    mod = importlib.import_module(script.split(":")[0])
+    tf.reset_default_graph()
+    lib.delete_all_params()
+    np.random.seed(2)
+    g = mod.build_graph(**ALL_SCRIPTS[script])
+    for cost, op in ((g.gen_cost, g.gen_train_op), (g.disc_cost, g.disc_train_op)):
+        roots = [cost] + [d for d in op.deps if d is not None]
+        fed = [n for n in toposort(roots) if n.op == "placeholder"]
+        plan = Plan(RT, [cost, op], fed)
+        assert len(plan.steps) > 20 and plan.groups
+        order, assign, waits, _ = plan._schedule_range(range(len(plan.groups)), 6)
+        assert sorted(order) == list(range(len(plan.groups)))
+        record = cpu_device
+        del record[:]
+        for f in plan.steps:
+            f(0)
+        names = [n for n, _ in record]
+        assert sum(n.startswith(("gg_adam_multi", "gg_rmsprop_multi")) for n in names) == 1
+        assert any(n in ("gg_conv2d_fwd", "gg_conv2d_dgrad") for n in names)
