@@ -73,7 +73,7 @@ def conv_case(B, H, W, Ci, Co, k=5, s=2):
         hot = graph_time(fn, False)
         cold = graph_time(fn, True) - flush_only
         print("conv %-5s B%d %dx%d %d->%d k%d s%d  hot %6.1f us (%6.1f TF/s)  cold %6.1f us  backend %d" %
-              (name, B, H, W, Ci, Co, k, s, hot, gf / hot * 1e3 / 1e3, cold, cabi.lib.gg_last_backend()), flush=True)
+              (name, B, H, W, Ci, Co, k, s, hot, gf / hot * 1e3, cold, cabi.lib.gg_last_backend()), flush=True)
 
 
 def gemm_case(M, N, K, ta=0, tb=0):
