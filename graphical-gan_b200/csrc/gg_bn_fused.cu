@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(kThreads) bn_fwd_fused_kernel(const float* __r
                                                                 float* __restrict__ y, float* __restrict__ mean_out,
                                                                 float* __restrict__ rstd_out, int R, int C, int cs, int act,
                                                                 float alpha) {
+  GG_PDL_ENTRY();
   constexpr int cw = Q * 4, RL = kThreads / Q;
   __shared__ float wred[kThreads / 32][kMaxCw][2];
   __shared__ double xch[kMaxCw][2];
@@ -166,6 +167,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_fused_kernel(const float* __r
                                                                 float* __restrict__ dx, float* __restrict__ dgamma,
                                                                 float* __restrict__ dbeta, int R, int C, int cs, int act,
                                                                 float alpha) {
+  GG_PDL_ENTRY();
   constexpr int cw = Q * 4, RL = kThreads / Q;
   __shared__ float wred[kThreads / 32][kMaxCw][2];
   __shared__ double xch[kMaxCw][2];
@@ -250,13 +252,22 @@ int launch_clustered(Kern kern, const BnPlan& pl, cudaStream_t st, const char* w
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)pl.cs;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pl.cs > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = (unsigned)pl.cs;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (g_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pl.cs > 1 ? 1 : 0;
+  cfg.numAttrs = na;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, args...);
   if (e != cudaSuccess) {
     cudaGetLastError();

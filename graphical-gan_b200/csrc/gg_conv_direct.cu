@@ -38,6 +38,7 @@ template <int PIX, int CV>
 __global__ void __launch_bounds__(128) conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                        const float* __restrict__ bias, float* __restrict__ y, ConvP p, int act,
                                                        float alpha) {
+  GG_PDL_ENTRY();
   int cog = (p.Co + CV - 1) / CV;           // co groups
   int wog = (p.Wo + PIX - 1) / PIX;         // wo groups
   long long total = (long long)p.B * p.Ho * wog * cog;
@@ -99,6 +100,7 @@ template <int CV>
 __global__ void __launch_bounds__(128) conv_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
                                                          const float* __restrict__ bias, float* __restrict__ dx, ConvP p,
                                                          int act, float alpha) {
+  GG_PDL_ENTRY();
   int cig = (p.Ci + CV - 1) / CV;
   long long total = (long long)p.B * p.H * p.W * cig;
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -162,6 +164,7 @@ __global__ void __launch_bounds__(128) conv_dgrad_kernel(const float* __restrict
 template <int CV>
 __global__ void __launch_bounds__(128) conv_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                          float* __restrict__ part, ConvP p, int slices) {
+  GG_PDL_ENTRY();
   int cog = (p.Co + CV - 1) / CV;
   int total = p.k * p.k * p.Ci * cog;
   int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -202,6 +205,7 @@ __global__ void __launch_bounds__(128) conv_wgrad_kernel(const float* __restrict
 }
 
 __global__ void __launch_bounds__(256) sum_slices_kernel(const float* __restrict__ part, float* __restrict__ out, long long n, int slices) {
+  GG_PDL_ENTRY();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float a = 0.f;
@@ -217,6 +221,7 @@ __global__ void __launch_bounds__(256) sum_slices_kernel(const float* __restrict
 // products run as plain GEMMs on the tcgen05 kernel:  y = P W,  dW = P^T dy,  dP = dy W^T followed by a col2im gather.
 // The filter matrix is read in place: its rows beyond k*k*Cin are TMA out-of-bounds zeros.
 __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x, float* __restrict__ P, ConvP p, int Kp) {
+  GG_PDL_ENTRY();
   const int kv = Kp / 4;
   const long long total = (long long)p.B * p.Ho * p.Wo * kv;
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -245,6 +250,7 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x
 
 __global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ dP, const float* __restrict__ bias,
                                                      float* __restrict__ dx, ConvP p, int Kp, int act, float alpha) {
+  GG_PDL_ENTRY();
   const long long total = (long long)p.B * p.H * p.W * p.Ci;
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
@@ -341,7 +347,7 @@ extern "C" int gg_conv2d_fwd(const float* x, const float* w, const float* bias, 
     if (sc.ok && workspace != nullptr && workspace_bytes >= sc.tc_bytes + sc.p_bytes) {
       float* P = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + sc.tc_bytes);
       const long long total = sc.M * (sc.Kp / 4);
-      im2col_kernel<<<ceil_div(total, 256), 256, 0, st>>>(x, P, p, sc.Kp);
+      GG_LAUNCH(im2col_kernel, ceil_div(total, 256), 256, 0, st, x, P, p, sc.Kp);
       rc = check_launch("gg_conv2d_fwd/im2col");
       if (rc) return rc;
       bool handled = false;
@@ -362,10 +368,10 @@ extern "C" int gg_conv2d_fwd(const float* x, const float* w, const float* bias, 
   g_last_backend = 0;
   if (Co % 4 == 0) {
     long long total = (long long)B * Ho * ((Wo + 3) / 4) * (Co / 4);
-    conv_fwd_kernel<4, 4><<<ceil_div(total, 128), 128, 0, st>>>(x, w, bias, y, p, act, alpha);
+    GG_LAUNCH((conv_fwd_kernel<4, 4>), ceil_div(total, 128), 128, 0, st, x, w, bias, y, p, act, alpha);
   } else {
     long long total = (long long)B * Ho * ((Wo + 3) / 4) * Co;
-    conv_fwd_kernel<4, 1><<<ceil_div(total, 128), 128, 0, st>>>(x, w, bias, y, p, act, alpha);
+    GG_LAUNCH((conv_fwd_kernel<4, 1>), ceil_div(total, 128), 128, 0, st, x, w, bias, y, p, act, alpha);
   }
   return check_launch("gg_conv2d_fwd(direct)");
 }
@@ -393,7 +399,7 @@ extern "C" int gg_conv2d_dgrad(const float* dy, const float* w, const float* bia
       if (rc) return rc;
       if (handled) {
         const long long total = (long long)B * H * W * Ci;
-        col2im_kernel<<<ceil_div(total, 256), 256, 0, st>>>(dP, bias, dx, p, sc.Kp, act, alpha);
+        GG_LAUNCH(col2im_kernel, ceil_div(total, 256), 256, 0, st, dP, bias, dx, p, sc.Kp, act, alpha);
         g_last_backend = 1;
         return check_launch("gg_conv2d_dgrad/col2im");
       }
@@ -410,10 +416,10 @@ extern "C" int gg_conv2d_dgrad(const float* dy, const float* w, const float* bia
   g_last_backend = 0;
   if (Ci % 4 == 0) {
     long long total = (long long)B * H * W * (Ci / 4);
-    conv_dgrad_kernel<4><<<ceil_div(total, 128), 128, 0, st>>>(dy, w, bias, dx, p, act, alpha);
+    GG_LAUNCH((conv_dgrad_kernel<4>), ceil_div(total, 128), 128, 0, st, dy, w, bias, dx, p, act, alpha);
   } else {
     long long total = (long long)B * H * W * Ci;
-    conv_dgrad_kernel<1><<<ceil_div(total, 128), 128, 0, st>>>(dy, w, bias, dx, p, act, alpha);
+    GG_LAUNCH((conv_dgrad_kernel<1>), ceil_div(total, 128), 128, 0, st, dy, w, bias, dx, p, act, alpha);
   }
   return check_launch("gg_conv2d_dgrad(direct)");
 }
@@ -464,7 +470,7 @@ extern "C" int gg_conv2d_wgrad(const float* x, const float* dy, float* dw, int B
     if (sc.ok && workspace != nullptr && workspace_bytes >= sc.tc_bytes + sc.p_bytes) {
       float* P = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + sc.tc_bytes);
       const long long total = sc.M * (sc.Kp / 4);
-      im2col_kernel<<<ceil_div(total, 256), 256, 0, st>>>(x, P, p, sc.Kp);
+      GG_LAUNCH(im2col_kernel, ceil_div(total, 256), 256, 0, st, x, P, p, sc.Kp);
       rc = check_launch("gg_conv2d_wgrad/im2col");
       if (rc) return rc;
       bool handled = false;
@@ -490,14 +496,14 @@ extern "C" int gg_conv2d_wgrad(const float* x, const float* dy, float* dw, int B
   if (Co % 4 == 0) {
     int threads = k * k * Ci * (Co / 4);
     dim3 grid(ceil_div(threads, 128), S);
-    conv_wgrad_kernel<4><<<grid, 128, 0, st>>>(x, dy, part, p, S);
+    GG_LAUNCH((conv_wgrad_kernel<4>), grid, 128, 0, st, x, dy, part, p, S);
   } else {
     int threads = k * k * Ci * Co;
     dim3 grid(ceil_div(threads, 128), S);
-    conv_wgrad_kernel<1><<<grid, 128, 0, st>>>(x, dy, part, p, S);
+    GG_LAUNCH((conv_wgrad_kernel<1>), grid, 128, 0, st, x, dy, part, p, S);
   }
   rc = check_launch("gg_conv2d_wgrad(direct)");
   if (rc) return rc;
-  sum_slices_kernel<<<ceil_div(wsz, 256), 256, 0, st>>>(part, dw, wsz, S);
+  GG_LAUNCH(sum_slices_kernel, ceil_div(wsz, 256), 256, 0, st, part, dw, wsz, S);
   return check_launch("gg_conv2d_wgrad(direct)/sum");
 }

@@ -32,6 +32,7 @@ template <int CI>
 __global__ void __launch_bounds__(256) conv_small_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                              const float* __restrict__ bias, float* __restrict__ y, SmallP p,
                                                              int act, float alpha) {
+  GG_PDL_ENTRY();
   extern __shared__ __align__(16) float smem_f[];
   const int K = p.k * p.k * CI;
   const int IW = (kTile - 1) * p.stride + p.k;          // input patch extent (square)
@@ -141,6 +142,7 @@ template <int CI, int KS>
 __global__ void __launch_bounds__(128) conv_small_fwd_v2_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                 const float* __restrict__ bias, float* __restrict__ y, SmallP p,
                                                                 int act, float alpha) {
+  GG_PDL_ENTRY();
   extern __shared__ __align__(16) float smem_f[];
   const int k = KS > 0 ? KS : p.k;
   const int K = k * k * CI;
@@ -253,6 +255,7 @@ template <int CI>
 __global__ void __launch_bounds__(128) conv_small_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
                                                                const float* __restrict__ bias, float* __restrict__ dx, SmallP p,
                                                                int PH, int PW, int act, float alpha) {
+  GG_PDL_ENTRY();
   extern __shared__ __align__(16) float smem_f[];
   const int pitch = p.Co + 4;                           // floats per dy pixel / per filter row: +4 keeps float4 reads of
                                                         // neighbouring pixels on different banks
@@ -386,8 +389,8 @@ int conv_small_fwd(const float* x, const float* w, const float* bias, float* y, 
   if (v2 < 0) { const char* e = getenv("GG_CONV_SMALL_V2"); v2 = (e && e[0] == '1') ? 1 : 0; }
   if (v2) {
 #define GG_V2(CI_)                                                                                                        \
-    if (k == 5) conv_small_fwd_v2_kernel<CI_, 5><<<grid, 128, smem, st>>>(x, w, bias, y, p, act, alpha);                    \
-    else conv_small_fwd_v2_kernel<CI_, 0><<<grid, 128, smem, st>>>(x, w, bias, y, p, act, alpha)
+    if (k == 5) GG_LAUNCH((conv_small_fwd_v2_kernel<CI_, 5>), grid, 128, smem, st, x, w, bias, y, p, act, alpha);                    \
+    else GG_LAUNCH((conv_small_fwd_v2_kernel<CI_, 0>), grid, 128, smem, st, x, w, bias, y, p, act, alpha)
     switch (Ci) {
       case 1: GG_V2(1); break;
       case 2: GG_V2(2); break;
@@ -399,10 +402,10 @@ int conv_small_fwd(const float* x, const float* w, const float* bias, float* y, 
     return check_launch("gg_conv2d_fwd(small-channel v2)");
   }
   switch (Ci) {
-    case 1: conv_small_fwd_kernel<1><<<grid, 256, smem, st>>>(x, w, bias, y, p, act, alpha); break;
-    case 2: conv_small_fwd_kernel<2><<<grid, 256, smem, st>>>(x, w, bias, y, p, act, alpha); break;
-    case 3: conv_small_fwd_kernel<3><<<grid, 256, smem, st>>>(x, w, bias, y, p, act, alpha); break;
-    default: conv_small_fwd_kernel<4><<<grid, 256, smem, st>>>(x, w, bias, y, p, act, alpha); break;
+    case 1: GG_LAUNCH((conv_small_fwd_kernel<1>), grid, 256, smem, st, x, w, bias, y, p, act, alpha); break;
+    case 2: GG_LAUNCH((conv_small_fwd_kernel<2>), grid, 256, smem, st, x, w, bias, y, p, act, alpha); break;
+    case 3: GG_LAUNCH((conv_small_fwd_kernel<3>), grid, 256, smem, st, x, w, bias, y, p, act, alpha); break;
+    default: GG_LAUNCH((conv_small_fwd_kernel<4>), grid, 256, smem, st, x, w, bias, y, p, act, alpha); break;
   }
   *handled = true;
   return check_launch("gg_conv2d_fwd(small-channel)");
@@ -421,10 +424,10 @@ int conv_small_dgrad(const float* dy, const float* w, const float* bias, float* 
   if (smem > 48 * 1024 || B > 65535) return GG_OK;
   dim3 grid(ceil_div(H, kDH) * ceil_div(W, kDW), B);
   switch (Ci) {
-    case 1: conv_small_dgrad_kernel<1><<<grid, 128, smem, st>>>(dy, w, bias, dx, p, PH, PW, act, alpha); break;
-    case 2: conv_small_dgrad_kernel<2><<<grid, 128, smem, st>>>(dy, w, bias, dx, p, PH, PW, act, alpha); break;
-    case 3: conv_small_dgrad_kernel<3><<<grid, 128, smem, st>>>(dy, w, bias, dx, p, PH, PW, act, alpha); break;
-    default: conv_small_dgrad_kernel<4><<<grid, 128, smem, st>>>(dy, w, bias, dx, p, PH, PW, act, alpha); break;
+    case 1: GG_LAUNCH((conv_small_dgrad_kernel<1>), grid, 128, smem, st, dy, w, bias, dx, p, PH, PW, act, alpha); break;
+    case 2: GG_LAUNCH((conv_small_dgrad_kernel<2>), grid, 128, smem, st, dy, w, bias, dx, p, PH, PW, act, alpha); break;
+    case 3: GG_LAUNCH((conv_small_dgrad_kernel<3>), grid, 128, smem, st, dy, w, bias, dx, p, PH, PW, act, alpha); break;
+    default: GG_LAUNCH((conv_small_dgrad_kernel<4>), grid, 128, smem, st, dy, w, bias, dx, p, PH, PW, act, alpha); break;
   }
   *handled = true;
   return check_launch("gg_conv2d_dgrad(small-channel)");

@@ -113,6 +113,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   const int kStages = p.stages;
   __shared__ uint32_t tmem_base_sh;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: the next kernel may start its own prologue now
   __shared__ long long s_row_off[128];                  // element offset of each accumulator row's output row (-1: masked)
   __shared__ __align__(16) float s_bias[kMaxNTile];   // bias slice of this n-tile (read from HBM/L2 once, before the accumulator is ready)
 
@@ -171,6 +172,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (cl) cluster_sync_all();                  // peers must not signal cl_bar before it is initialised
   else __syncthreads();
   tc_fence_after();
+  // PDL: everything above (barrier init, tensor-map prefetch, TMEM allocation) is independent of the producer kernel; its
+  // activations / gradients are first touched below (TMA loads, bias read), so the dependency is resolved here.  A no-op
+  // for launches without a programmatic dependency.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t tmem_d = tmem_base_sh;
   if (threadIdx.x == 0) GG_DBG(0);
   if (p.dbg && threadIdx.x == 0) atomicMin(reinterpret_cast<unsigned long long*>(p.dbg + 201), (unsigned long long)gtime());
@@ -731,15 +736,17 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, TcPlan& pl, void* ws,
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeCooperative;
     attr[0].val.cooperative = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = (g_pdl && env_int("GG_PDL_COOP", 0) != 0) ? 2 : 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<MODE>, tmA, tmB, p);
     if (e != cudaSuccess) { cudaGetLastError(); return fail(GG_ERR_CUDA_BASE + (int)e, "conv_tc: cooperative launch failed: %s", cudaGetErrorString(e)); }
   } else {
-    conv_tc_kernel<MODE><<<grid, kThreads, smem, st>>>(tmA, tmB, p);
+    GG_LAUNCH((conv_tc_kernel<MODE>), grid, kThreads, smem, st, tmA, tmB, p);
   }
   return check_launch(MODE == 0 ? "gg_conv2d_fwd(tcgen05)" : (MODE == 1 ? "gg_conv2d_dgrad(tcgen05)" : "gg_conv2d_wgrad(tcgen05)"));
 }

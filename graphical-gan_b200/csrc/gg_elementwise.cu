@@ -9,6 +9,7 @@ thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 thread_local int g_last_backend = 0;
 int g_conv_backend = 0;
+int g_pdl = 0;   // programmatic dependent launch for the stream-ordered kernels (gg_set_pdl / GG_PDL=1)
 }  // namespace gg
 
 using namespace gg;
@@ -23,6 +24,10 @@ extern "C" int gg_set_conv_backend(int mode) {
   return GG_OK;
 }
 extern "C" int gg_get_conv_backend(void) { return g_conv_backend; }
+extern "C" int gg_set_pdl(int on) {
+  g_pdl = on ? 1 : 0;
+  return GG_OK;
+}
 extern "C" int gg_last_backend(void) { return g_last_backend; }
 
 // ------------------------------------------------------------------------------------------
@@ -58,6 +63,7 @@ __device__ __forceinline__ float unary_apply(int op, float x, float a, float b) 
 template <int OP>
 __global__ void __launch_bounds__(256) unary_kernel(const float* __restrict__ x, float* __restrict__ y, long long n,
                                                     float a, float b) {
+  GG_PDL_ENTRY();
   long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   long long stride = (long long)gridDim.x * blockDim.x * 4;
   bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
@@ -84,7 +90,7 @@ static int ew_grid(long long n, int per_thread = 4, int threads = 256) {
 }
 
 #define GG_UNARY_CASE(OPC) \
-  case OPC: unary_kernel<OPC><<<grid, 256, 0, st>>>(x, y, n, a, b); break;
+  case OPC: GG_LAUNCH((unary_kernel<OPC>), grid, 256, 0, st, x, y, n, a, b); break;
 
 extern "C" int gg_unary(int op, const float* x, float* y, long long n, float a, float b, void* stream) {
   if (n <= 0) return GG_OK;
@@ -129,6 +135,7 @@ __device__ __forceinline__ float binary_apply(int op, float a, float b, float al
 // same-shape contiguous fast path
 __global__ void __launch_bounds__(256) binary_flat_kernel(int op, const float* __restrict__ a, const float* __restrict__ b,
                                                           float* __restrict__ out, long long n, float alpha) {
+  GG_PDL_ENTRY();
   long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   long long stride = (long long)gridDim.x * blockDim.x * 4;
   bool vec = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
@@ -152,6 +159,7 @@ struct Dims4 { int d[4]; int sa[4]; int sb[4]; };
 
 __global__ void __launch_bounds__(256) binary_bcast_kernel(int op, const float* __restrict__ a, const float* __restrict__ b,
                                                            float* __restrict__ out, Dims4 p, long long n, float alpha) {
+  GG_PDL_ENTRY();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
@@ -183,11 +191,11 @@ extern "C" int gg_binary(int op, const float* a, const float* b, float* out, con
   }
   cudaStream_t st = as_stream(stream);
   if (flat) {
-    binary_flat_kernel<<<ew_grid(n), 256, 0, st>>>(op, a, b, out, n, alpha);
+    GG_LAUNCH(binary_flat_kernel, ew_grid(n), 256, 0, st, op, a, b, out, n, alpha);
   } else {
     Dims4 p;
     for (int i = 0; i < 4; ++i) { p.d[i] = dims4[i]; p.sa[i] = sa4[i]; p.sb[i] = sb4[i]; }
-    binary_bcast_kernel<<<ew_grid(n, 1), 256, 0, st>>>(op, a, b, out, p, n, alpha);
+    GG_LAUNCH(binary_bcast_kernel, ew_grid(n, 1), 256, 0, st, op, a, b, out, p, n, alpha);
   }
   return check_launch("gg_binary");
 }
@@ -198,6 +206,7 @@ extern "C" int gg_binary(int op, const float* a, const float* b, float* out, con
 // inner == 1: one warp (or block) per output row, lanes stride over `red`.
 __global__ void __launch_bounds__(256) reduce_rows_kernel(int op, const float* __restrict__ x, float* __restrict__ y,
                                                           int outer, int red) {
+  GG_PDL_ENTRY();
   __shared__ float sh[32];
   int o = blockIdx.x;
   if (o >= outer) return;
@@ -222,6 +231,7 @@ __global__ void __launch_bounds__(256) reduce_rows_kernel(int op, const float* _
 // inner > 1: thread per (outer, inner) column, coalesced over inner; rows split over threadIdx.y then smem-combined
 __global__ void __launch_bounds__(256) reduce_cols_kernel(int op, const float* __restrict__ x, float* __restrict__ y,
                                                           int outer, int red, int inner) {
+  GG_PDL_ENTRY();
   __shared__ float sh[8][33];
   int i = blockIdx.x * 32 + threadIdx.x;
   int o = blockIdx.y;
@@ -247,6 +257,7 @@ __global__ void __launch_bounds__(256) reduce_cols_kernel(int op, const float* _
 // then the same kernel folds the S partial rows.  Deterministic (fixed summation order), fills the SMs.
 __global__ void __launch_bounds__(256) reduce_cols_sliced_kernel(int op, const float* __restrict__ x, float* __restrict__ part,
                                                                  int red, int inner, int rows_per) {
+  GG_PDL_ENTRY();
   __shared__ float sh[8][33];
   int i = blockIdx.x * 32 + threadIdx.x;
   int s = blockIdx.y;
@@ -283,11 +294,11 @@ extern "C" int gg_reduce_ws(int op, const float* x, float* y, int outer, int red
   S = ceil_div(red, rows_per);
   float* part = reinterpret_cast<float*>(workspace);
   dim3 block(32, 8);
-  reduce_cols_sliced_kernel<<<dim3(ctiles, S), block, 0, st>>>(op == 1 ? 0 : op, x, part, red, inner, rows_per);
+  GG_LAUNCH(reduce_cols_sliced_kernel, dim3(ctiles, S), block, 0, st, op == 1 ? 0 : op, x, part, red, inner, rows_per);
   int rc = check_launch("gg_reduce_ws/slices");
   if (rc) return rc;
   // fold the S partial rows; the mean divides by the true row count
-  reduce_cols_kernel<<<dim3(ctiles, 1), block, 0, st>>>(op == 1 ? 0 : op, part, y, 1, S, inner);
+  GG_LAUNCH(reduce_cols_kernel, dim3(ctiles, 1), block, 0, st, op == 1 ? 0 : op, part, y, 1, S, inner);
   rc = check_launch("gg_reduce_ws/fold");
   if (rc || op != 1) return rc;
   return gg_unary(GG_U_DIVC, y, y, inner, (float)red, 0.f, stream);
@@ -305,10 +316,10 @@ extern "C" int gg_reduce(int op, const float* x, float* y, int outer, int red, i
   cudaStream_t st = as_stream(stream);
   if (inner == 1) {
     int threads = red >= 1024 ? 256 : (red >= 128 ? 128 : 32);
-    reduce_rows_kernel<<<outer, threads, 0, st>>>(op, x, y, outer, red);
+    GG_LAUNCH(reduce_rows_kernel, outer, threads, 0, st, op, x, y, outer, red);
   } else {
     dim3 grid(ceil_div(inner, 32), outer), block(32, 8);
-    reduce_cols_kernel<<<grid, block, 0, st>>>(op, x, y, outer, red, inner);
+    GG_LAUNCH(reduce_cols_kernel, grid, block, 0, st, op, x, y, outer, red, inner);
   }
   return check_launch("gg_reduce");
 }
@@ -317,6 +328,7 @@ extern "C" int gg_reduce(int op, const float* x, float* y, int outer, int red, i
 // softmax over the last axis (HyperExtractor, gmgan_inference_cifar10.py:162-163): one warp per row
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) softmax_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int R, int C) {
+  GG_PDL_ENTRY();
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (row >= R) return;
@@ -333,6 +345,7 @@ __global__ void __launch_bounds__(128) softmax_fwd_kernel(const float* __restric
 
 __global__ void __launch_bounds__(128) softmax_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy,
                                                           float* __restrict__ dx, int R, int C) {
+  GG_PDL_ENTRY();
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (row >= R) return;
@@ -346,12 +359,12 @@ __global__ void __launch_bounds__(128) softmax_bwd_kernel(const float* __restric
 
 extern "C" int gg_softmax_fwd(const float* x, float* y, int R, int C, void* stream) {
   if (R <= 0 || C <= 0) return GG_OK;
-  softmax_fwd_kernel<<<ceil_div(R, 4), 128, 0, as_stream(stream)>>>(x, y, R, C);
+  GG_LAUNCH(softmax_fwd_kernel, ceil_div(R, 4), 128, 0, as_stream(stream), x, y, R, C);
   return check_launch("gg_softmax_fwd");
 }
 extern "C" int gg_softmax_bwd(const float* y, const float* dy, float* dx, int R, int C, void* stream) {
   if (R <= 0 || C <= 0) return GG_OK;
-  softmax_bwd_kernel<<<ceil_div(R, 4), 128, 0, as_stream(stream)>>>(y, dy, dx, R, C);
+  GG_LAUNCH(softmax_bwd_kernel, ceil_div(R, 4), 128, 0, as_stream(stream), y, dy, dx, R, C);
   return check_launch("gg_softmax_bwd");
 }
 
@@ -359,6 +372,7 @@ extern "C" int gg_softmax_bwd(const float* y, const float* dy, float* dx, int R,
 // transposes
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) transpose_b2d_kernel(const float* __restrict__ x, float* __restrict__ y, int R, int C) {
+  GG_PDL_ENTRY();
   __shared__ float tile[32][33];
   int b = blockIdx.z;
   const float* xb = x + (long long)b * R * C;
@@ -379,12 +393,13 @@ extern "C" int gg_transpose_b2d(const float* x, float* y, int Bt, int R, int C, 
   if (Bt <= 0 || R <= 0 || C <= 0) return GG_OK;
   GG_REQUIRE(Bt <= 65535, "gg_transpose_b2d");
   dim3 grid(ceil_div(C, 32), ceil_div(R, 32), Bt), block(32, 8);
-  transpose_b2d_kernel<<<grid, block, 0, as_stream(stream)>>>(x, y, R, C);
+  GG_LAUNCH(transpose_b2d_kernel, grid, block, 0, as_stream(stream), x, y, R, C);
   return check_launch("gg_transpose_b2d");
 }
 
 struct Perm4 { int od[4]; long long is[4]; };
 __global__ void __launch_bounds__(256) transpose4_kernel(const float* __restrict__ x, float* __restrict__ y, Perm4 p, long long n) {
+  GG_PDL_ENTRY();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
@@ -411,7 +426,7 @@ extern "C" int gg_transpose4(const float* x, float* y, const int* dims4, const i
     p.od[i] = dims4[s];
     p.is[i] = istr[s];
   }
-  transpose4_kernel<<<ew_grid(n, 1), 256, 0, as_stream(stream)>>>(x, y, p, n);
+  GG_LAUNCH(transpose4_kernel, ew_grid(n, 1), 256, 0, as_stream(stream), x, y, p, n);
   return check_launch("gg_transpose4");
 }
 
@@ -420,6 +435,7 @@ extern "C" int gg_transpose4(const float* x, float* y, const int* dims4, const i
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) copy2d_kernel(const float* __restrict__ src, long long src_ld, float* __restrict__ dst,
                                                      long long dst_ld, long long rows, long long cols, int accumulate) {
+  GG_PDL_ENTRY();
   long long n = rows * cols;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
@@ -433,22 +449,24 @@ __global__ void __launch_bounds__(256) copy2d_kernel(const float* __restrict__ s
 extern "C" int gg_copy2d(const float* src, long long src_ld, float* dst, long long dst_ld, long long rows,
                          long long cols, int accumulate, void* stream) {
   if (rows <= 0 || cols <= 0) return GG_OK;
-  copy2d_kernel<<<ew_grid(rows * cols, 1), 256, 0, as_stream(stream)>>>(src, src_ld, dst, dst_ld, rows, cols, accumulate);
+  GG_LAUNCH(copy2d_kernel, ew_grid(rows * cols, 1), 256, 0, as_stream(stream), src, src_ld, dst, dst_ld, rows, cols, accumulate);
   return check_launch("gg_copy2d");
 }
 
 __global__ void __launch_bounds__(256) fill_kernel(float* x, long long n, float v) {
+  GG_PDL_ENTRY();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) x[i] = v;
 }
 extern "C" int gg_fill(float* x, long long n, float v, void* stream) {
   if (n <= 0) return GG_OK;
-  fill_kernel<<<ew_grid(n, 1), 256, 0, as_stream(stream)>>>(x, n, v);
+  GG_LAUNCH(fill_kernel, ew_grid(n, 1), 256, 0, as_stream(stream), x, n, v);
   return check_launch("gg_fill");
 }
 
 __global__ void __launch_bounds__(256) one_hot_kernel(const int32_t* __restrict__ idx, float* __restrict__ out, int n, int depth) {
+  GG_PDL_ENTRY();
   long long total = (long long)n * depth;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
@@ -459,12 +477,13 @@ __global__ void __launch_bounds__(256) one_hot_kernel(const int32_t* __restrict_
 }
 extern "C" int gg_one_hot(const int32_t* idx, float* out, int n, int depth, void* stream) {
   if (n <= 0 || depth <= 0) return GG_OK;
-  one_hot_kernel<<<ew_grid((long long)n * depth, 1), 256, 0, as_stream(stream)>>>(idx, out, n, depth);
+  GG_LAUNCH(one_hot_kernel, ew_grid((long long)n * depth, 1), 256, 0, as_stream(stream), idx, out, n, depth);
   return check_launch("gg_one_hot");
 }
 
 // first maximal index, like tf.argmax
 __global__ void __launch_bounds__(128) argmax_kernel(const float* __restrict__ x, int32_t* __restrict__ idx, int R, int C) {
+  GG_PDL_ENTRY();
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (row >= R) return;
@@ -485,12 +504,13 @@ __global__ void __launch_bounds__(128) argmax_kernel(const float* __restrict__ x
 }
 extern "C" int gg_argmax(const float* x, int32_t* idx, int R, int C, void* stream) {
   if (R <= 0 || C <= 0) return GG_OK;
-  argmax_kernel<<<ceil_div(R, 4), 128, 0, as_stream(stream)>>>(x, idx, R, C);
+  GG_LAUNCH(argmax_kernel, ceil_div(R, 4), 128, 0, as_stream(stream), x, idx, R, C);
   return check_launch("gg_argmax");
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256) cast_to_f32_kernel(const T* __restrict__ x, float* __restrict__ y, long long n, float a, float b) {
+  GG_PDL_ENTRY();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
   // TF evaluates 2*((float(x)/255.)-.5): the host passes (a, b) and we keep the same operation order
@@ -500,27 +520,29 @@ __global__ void __launch_bounds__(256) cast_to_f32_kernel(const T* __restrict__ 
 }
 extern "C" int gg_cast_i32_f32(const int32_t* x, float* y, long long n, float a, float b, void* stream) {
   if (n <= 0) return GG_OK;
-  cast_to_f32_kernel<int32_t><<<ew_grid(n, 1), 256, 0, as_stream(stream)>>>(x, y, n, a, b);
+  GG_LAUNCH((cast_to_f32_kernel<int32_t>), ew_grid(n, 1), 256, 0, as_stream(stream), x, y, n, a, b);
   return check_launch("gg_cast_i32_f32");
 }
 extern "C" int gg_cast_u8_f32(const uint8_t* x, float* y, long long n, float a, float b, void* stream) {
   if (n <= 0) return GG_OK;
-  cast_to_f32_kernel<uint8_t><<<ew_grid(n, 1), 256, 0, as_stream(stream)>>>(x, y, n, a, b);
+  GG_LAUNCH((cast_to_f32_kernel<uint8_t>), ew_grid(n, 1), 256, 0, as_stream(stream), x, y, n, a, b);
   return check_launch("gg_cast_u8_f32");
 }
 __global__ void __launch_bounds__(256) cast_f32_i32_kernel(const float* __restrict__ x, int32_t* __restrict__ y, long long n) {
+  GG_PDL_ENTRY();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) y[i] = (int32_t)x[i];  // truncation toward zero, like tf.cast / numpy astype
 }
 extern "C" int gg_cast_f32_i32(const float* x, int32_t* y, long long n, void* stream) {
   if (n <= 0) return GG_OK;
-  cast_f32_i32_kernel<<<ew_grid(n, 1), 256, 0, as_stream(stream)>>>(x, y, n);
+  GG_LAUNCH(cast_f32_i32_kernel, ew_grid(n, 1), 256, 0, as_stream(stream), x, y, n);
   return check_launch("gg_cast_f32_i32");
 }
 
 struct PtrList { const float* p[16]; };
 __global__ void __launch_bounds__(256) add_n_kernel(PtrList pl, int count, float* __restrict__ out, long long n) {
+  GG_PDL_ENTRY();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
@@ -534,6 +556,6 @@ extern "C" int gg_add_n(const float* const* ptrs, int count, float* out, long lo
   if (count < 1 || count > 16) return fail(GG_ERR_BAD_ARG, "gg_add_n: count must be in [1,16]%s");
   PtrList pl;
   for (int i = 0; i < count; ++i) pl.p[i] = ptrs[i];
-  add_n_kernel<<<ew_grid(n, 1), 256, 0, as_stream(stream)>>>(pl, count, out, n);
+  GG_LAUNCH(add_n_kernel, ew_grid(n, 1), 256, 0, as_stream(stream), pl, count, out, n);
   return check_launch("gg_add_n");
 }

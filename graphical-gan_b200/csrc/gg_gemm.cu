@@ -26,6 +26,7 @@ template <int TA, int TB>
 __global__ void __launch_bounds__(256) gemm_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                    const float* __restrict__ bias, float* __restrict__ C, int M, int N, int K,
                                                    int k_per_split, int splits, int act, float alpha) {
+  GG_PDL_ENTRY();
   __shared__ float As[TK][TM + 4];
   __shared__ float Bs[TK][TN + 4];
   int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(const float* __restrict__ A, 
 __global__ void __launch_bounds__(256) gemm_splitk_finish(const float* __restrict__ ws, const float* __restrict__ bias,
                                                           float* __restrict__ C, long long MN, int N, int splits, int act,
                                                           float alpha) {
+  GG_PDL_ENTRY();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= MN) return;
   float v = 0.f;
@@ -161,7 +163,7 @@ extern "C" int gg_gemm(const float* A, const float* Bm, const float* bias, float
   float* out = splits > 1 ? reinterpret_cast<float*>(workspace) : C;
   g_last_backend = 0;
 #define GG_LAUNCH_GEMM(TA, TB) \
-  gemm_kernel<TA, TB><<<grid, 256, 0, st>>>(A, Bm, bias, out, M, N, K, k_per, splits, act, alpha)
+  GG_LAUNCH((gemm_kernel<TA, TB>), grid, 256, 0, st, A, Bm, bias, out, M, N, K, k_per, splits, act, alpha)
   if (!ta && !tb) GG_LAUNCH_GEMM(0, 0);
   else if (ta && !tb) GG_LAUNCH_GEMM(1, 0);
   else if (!ta && tb) GG_LAUNCH_GEMM(0, 1);
@@ -171,7 +173,7 @@ extern "C" int gg_gemm(const float* A, const float* Bm, const float* bias, float
   if (rc) return rc;
   if (splits > 1) {
     long long MN = (long long)M * N;
-    gemm_splitk_finish<<<ceil_div(MN, 256), 256, 0, st>>>(out, bias, C, MN, N, splits, act, alpha);
+    GG_LAUNCH(gemm_splitk_finish, ceil_div(MN, 256), 256, 0, st, out, bias, C, MN, N, splits, act, alpha);
     rc = check_launch("gg_gemm/finish");
   }
   return rc;

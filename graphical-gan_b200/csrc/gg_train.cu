@@ -21,6 +21,7 @@ static int bn_slices(int R, int C) {
 extern "C" int gg_bn_slices(int R, int C) { return bn_slices(R, C); }
 
 __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ x, float* __restrict__ partial, int R, int C, int S) {
+  GG_PDL_ENTRY();
   __shared__ float s1[8][33], s2[8][33];
   int c = blockIdx.x * 32 + threadIdx.x;
   int s = blockIdx.y;
@@ -49,7 +50,7 @@ extern "C" int gg_bn_stats(const float* x, float* partial, int R, int C, void* s
   if (R <= 0 || C <= 0) return GG_OK;
   int S = bn_slices(R, C);
   dim3 grid(ceil_div(C, 32), S), block(32, 8);
-  bn_stats_kernel<<<grid, block, 0, as_stream(stream)>>>(x, partial, R, C, S);
+  GG_LAUNCH(bn_stats_kernel, grid, block, 0, as_stream(stream), x, partial, R, C, S);
   return check_launch("gg_bn_stats");
 }
 
@@ -58,6 +59,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
                                                        const float* __restrict__ beta, float eps, float* __restrict__ y,
                                                        float* __restrict__ mean_out, float* __restrict__ rstd_out, int R, int C,
                                                        int rows_per, int act, float alpha) {
+  GG_PDL_ENTRY();
   __shared__ float sc[32], sh[32];
   __shared__ double pa[8][33], pb[8][33];
   int c = blockIdx.x * 32 + threadIdx.x;
@@ -112,7 +114,7 @@ extern "C" int gg_bn_apply(const float* x, const float* partial, int S, float co
   int rows_per = ceil_div(R, gy);
   gy = ceil_div(R, rows_per);
   dim3 grid(ctiles, gy), block(32, 8);
-  bn_apply_kernel<<<grid, block, 0, as_stream(stream)>>>(x, partial, S, count, gamma, beta, eps, y, mean_out, rstd_out, R, C,
+  GG_LAUNCH(bn_apply_kernel, grid, block, 0, as_stream(stream), x, partial, S, count, gamma, beta, eps, y, mean_out, rstd_out, R, C,
                                                          rows_per, act, alpha);
   return check_launch("gg_bn_apply");
 }
@@ -121,6 +123,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
                                                             const float* __restrict__ y, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, float* __restrict__ partial, int R,
                                                             int C, int S, int act, float alpha) {
+  GG_PDL_ENTRY();
   __shared__ float s1[8][33], s2[8][33];
   int c = blockIdx.x * 32 + threadIdx.x;
   int s = blockIdx.y;
@@ -157,7 +160,7 @@ extern "C" int gg_bn_bwd_reduce(const float* dy, const float* x, const float* y,
   if (act != GG_ACT_NONE && y == nullptr) return fail(GG_ERR_BAD_ARG, "gg_bn_bwd_reduce: y required when act is fused%s");
   int S = bn_slices(R, C);
   dim3 grid(ceil_div(C, 32), S), block(32, 8);
-  bn_bwd_reduce_kernel<<<grid, block, 0, as_stream(stream)>>>(dy, x, y, mean, rstd, partial, R, C, S, act, alpha);
+  GG_LAUNCH(bn_bwd_reduce_kernel, grid, block, 0, as_stream(stream), dy, x, y, mean, rstd, partial, R, C, S, act, alpha);
   return check_launch("gg_bn_bwd_reduce");
 }
 
@@ -168,6 +171,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
                                                            float* __restrict__ dx, float* __restrict__ dgamma,
                                                            float* __restrict__ dbeta, int R, int C, int rows_per, int act,
                                                            float alpha) {
+  GG_PDL_ENTRY();
   __shared__ float sg[32], sgx[32];
   __shared__ double pa[8][33], pb[8][33];
   int c = blockIdx.x * 32 + threadIdx.x;
@@ -222,12 +226,13 @@ extern "C" int gg_bn_bwd_apply(const float* dy, const float* x, const float* y, 
   int rows_per = ceil_div(R, gy);
   gy = ceil_div(R, rows_per);
   dim3 grid(ctiles, gy), block(32, 8);
-  bn_bwd_apply_kernel<<<grid, block, 0, as_stream(stream)>>>(dy, x, y, mean, rstd, gamma, partial, S, count, dx, dgamma, dbeta,
+  GG_LAUNCH(bn_bwd_apply_kernel, grid, block, 0, as_stream(stream), dy, x, y, mean, rstd, gamma, partial, S, count, dx, dgamma, dbeta,
                                                              R, C, rows_per, act, alpha);
   return check_launch("gg_bn_bwd_apply");
 }
 
 __global__ void __launch_bounds__(256) bn_fold_kernel(const float* __restrict__ partial, int S, float* __restrict__ out, int C2) {
+  GG_PDL_ENTRY();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= C2) return;
   double a = 0.0;
@@ -236,7 +241,7 @@ __global__ void __launch_bounds__(256) bn_fold_kernel(const float* __restrict__ 
 }
 extern "C" int gg_bn_fold_partials(const float* partial, int S, float* out, int C, void* stream) {
   if (C <= 0) return GG_OK;
-  bn_fold_kernel<<<ceil_div(2 * C, 256), 256, 0, as_stream(stream)>>>(partial, S, out, 2 * C);
+  GG_LAUNCH(bn_fold_kernel, ceil_div(2 * C, 256), 256, 0, as_stream(stream), partial, S, out, 2 * C);
   return check_launch("gg_bn_fold_partials");
 }
 
@@ -245,6 +250,7 @@ extern "C" int gg_bn_fold_partials(const float* partial, int S, float* out, int 
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bce_mean_kernel(const float* __restrict__ x, int n, float label, float weight,
                                                        float* __restrict__ out, int accumulate) {
+  GG_PDL_ENTRY();
   __shared__ float sh[32];
   float acc = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -259,13 +265,14 @@ __global__ void __launch_bounds__(256) bce_mean_kernel(const float* __restrict__
 }
 extern "C" int gg_bce_mean(const float* x, int n, float label, float weight, float* out, int accumulate, void* stream) {
   GG_REQUIRE(n > 0, "gg_bce_mean");
-  bce_mean_kernel<<<1, 256, 0, as_stream(stream)>>>(x, n, label, weight, out, accumulate);
+  GG_LAUNCH(bce_mean_kernel, 1, 256, 0, as_stream(stream), x, n, label, weight, out, accumulate);
   return check_launch("gg_bce_mean");
 }
 
 __global__ void __launch_bounds__(256) bce_mean_grad_kernel(const float* __restrict__ x, int n, float label, float weight,
                                                             const float* __restrict__ gscale, float* __restrict__ dx,
                                                             int accumulate) {
+  GG_PDL_ENTRY();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float s = weight / (float)n * (gscale ? gscale[0] : 1.f);
@@ -275,13 +282,14 @@ __global__ void __launch_bounds__(256) bce_mean_grad_kernel(const float* __restr
 extern "C" int gg_bce_mean_grad(const float* x, int n, float label, float weight, const float* gscale, float* dx,
                                 int accumulate, void* stream) {
   GG_REQUIRE(n > 0, "gg_bce_mean_grad");
-  bce_mean_grad_kernel<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(x, n, label, weight, gscale, dx, accumulate);
+  GG_LAUNCH(bce_mean_grad_kernel, ceil_div(n, 256), 256, 0, as_stream(stream), x, n, label, weight, gscale, dx, accumulate);
   return check_launch("gg_bce_mean_grad");
 }
 
 // two-stage deterministic mean of (x-y)^2 or |x-y|; stage 2 is folded into the last-arriving block
 __global__ void __launch_bounds__(256) dist_partial_kernel(const float* __restrict__ x, const float* __restrict__ y, long long n,
                                                            int p, float* __restrict__ part) {
+  GG_PDL_ENTRY();
   __shared__ float sh[32];
   float acc = 0.f;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -295,6 +303,7 @@ __global__ void __launch_bounds__(256) dist_partial_kernel(const float* __restri
 }
 __global__ void __launch_bounds__(256) dist_final_kernel(const float* __restrict__ part, int nb, long long n, float weight,
                                                          float* __restrict__ out, int accumulate) {
+  GG_PDL_ENTRY();
   __shared__ float sh[32];
   float acc = 0.f;
   for (int i = threadIdx.x; i < nb; i += blockDim.x) acc += part[i];
@@ -314,15 +323,16 @@ extern "C" int gg_dist_mean(const float* x, const float* y, long long n, int p, 
   }
   int nb = ceil_div(n, 256 * 8);
   if (nb > 592) nb = 592;
-  dist_partial_kernel<<<nb, 256, 0, as_stream(stream)>>>(x, y, n, p, g_dist_scratch);
+  GG_LAUNCH(dist_partial_kernel, nb, 256, 0, as_stream(stream), x, y, n, p, g_dist_scratch);
   int rc = check_launch("gg_dist_mean/partial");
   if (rc) return rc;
-  dist_final_kernel<<<1, 256, 0, as_stream(stream)>>>(g_dist_scratch, nb, n, weight, out, accumulate);
+  GG_LAUNCH(dist_final_kernel, 1, 256, 0, as_stream(stream), g_dist_scratch, nb, n, weight, out, accumulate);
   return check_launch("gg_dist_mean/final");
 }
 
 // slopes[r] = ||g[r,:]||_2 ; out = weight * mean (slope-1)^2.  One warp per row, single block does the final mean.
 __global__ void __launch_bounds__(256) gp_slopes_kernel(const float* __restrict__ g, int R, int C, float* __restrict__ slopes) {
+  GG_PDL_ENTRY();
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (row >= R) return;
@@ -333,6 +343,7 @@ __global__ void __launch_bounds__(256) gp_slopes_kernel(const float* __restrict_
   if (lane == 0) slopes[row] = sqrtf(acc);
 }
 __global__ void __launch_bounds__(256) gp_penalty_kernel(const float* __restrict__ slopes, int R, float weight, float* __restrict__ out) {
+  GG_PDL_ENTRY();
   __shared__ float sh[32];
   float acc = 0.f;
   for (int i = threadIdx.x; i < R; i += blockDim.x) { float d = slopes[i] - 1.f; acc += d * d; }
@@ -341,10 +352,10 @@ __global__ void __launch_bounds__(256) gp_penalty_kernel(const float* __restrict
 }
 extern "C" int gg_gp_slope_penalty(const float* g, int R, int C, float weight, float* slopes, float* out, void* stream) {
   GG_REQUIRE(R > 0 && C > 0, "gg_gp_slope_penalty");
-  gp_slopes_kernel<<<ceil_div(R, 8), 256, 0, as_stream(stream)>>>(g, R, C, slopes);
+  GG_LAUNCH(gp_slopes_kernel, ceil_div(R, 8), 256, 0, as_stream(stream), g, R, C, slopes);
   int rc = check_launch("gg_gp_slope_penalty/slopes");
   if (rc) return rc;
-  gp_penalty_kernel<<<1, 256, 0, as_stream(stream)>>>(slopes, R, weight, out);
+  GG_LAUNCH(gp_penalty_kernel, 1, 256, 0, as_stream(stream), slopes, R, weight, out);
   return check_launch("gg_gp_slope_penalty/mean");
 }
 
@@ -354,6 +365,7 @@ extern "C" int gg_gp_slope_penalty(const float* g, int R, int C, float weight, f
 struct AdamState { double b1t; double b2t; long long t; };
 
 __global__ void adam_tick_kernel(AdamState* st, double b1, double b2) {
+  GG_PDL_ENTRY();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     if (st->t == 0) { st->b1t = 1.0; st->b2t = 1.0; }
     st->t += 1;
@@ -366,6 +378,7 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const gg_adam_entry* __
                                                          const gg_adam_chunk* __restrict__ chunks, int n_chunks,
                                                          const AdamState* __restrict__ st, float lr, float b1, float b2,
                                                          float eps, float gscale) {
+  GG_PDL_ENTRY();
   int ci = blockIdx.x;
   if (ci >= n_chunks) return;
   gg_adam_chunk ch = chunks[ci];
@@ -407,10 +420,10 @@ extern "C" int gg_adam_multi(const gg_adam_entry* table, const gg_adam_chunk* ch
                              float beta1, float beta2, float eps, float grad_scale, void* stream) {
   if (n_chunks <= 0) return GG_OK;
   cudaStream_t st = as_stream(stream);
-  adam_tick_kernel<<<1, 32, 0, st>>>(reinterpret_cast<AdamState*>(state), (double)beta1, (double)beta2);
+  GG_LAUNCH(adam_tick_kernel, 1, 32, 0, st, reinterpret_cast<AdamState*>(state), (double)beta1, (double)beta2);
   int rc = check_launch("gg_adam_multi/tick");
   if (rc) return rc;
-  adam_multi_kernel<<<n_chunks, 256, 0, st>>>(table, chunks, n_chunks, reinterpret_cast<const AdamState*>(state), lr, beta1,
+  GG_LAUNCH(adam_multi_kernel, n_chunks, 256, 0, st, table, chunks, n_chunks, reinterpret_cast<const AdamState*>(state), lr, beta1,
                                               beta2, eps, grad_scale);
   return check_launch("gg_adam_multi");
 }
@@ -418,6 +431,7 @@ extern "C" int gg_adam_multi(const gg_adam_entry* table, const gg_adam_chunk* ch
 __global__ void __launch_bounds__(256) rmsprop_multi_kernel(const gg_adam_entry* __restrict__ table,
                                                             const gg_adam_chunk* __restrict__ chunks, int n_chunks, float lr,
                                                             float decay, float eps, float gscale) {
+  GG_PDL_ENTRY();
   int ci = blockIdx.x;
   if (ci >= n_chunks) return;
   gg_adam_chunk ch = chunks[ci];
@@ -434,13 +448,14 @@ __global__ void __launch_bounds__(256) rmsprop_multi_kernel(const gg_adam_entry*
 extern "C" int gg_rmsprop_multi(const gg_adam_entry* table, const gg_adam_chunk* chunks, int n_chunks, float lr, float decay,
                                 float eps, float grad_scale, void* stream) {
   if (n_chunks <= 0) return GG_OK;
-  rmsprop_multi_kernel<<<n_chunks, 256, 0, as_stream(stream)>>>(table, chunks, n_chunks, lr, decay, eps, grad_scale);
+  GG_LAUNCH(rmsprop_multi_kernel, n_chunks, 256, 0, as_stream(stream), table, chunks, n_chunks, lr, decay, eps, grad_scale);
   return check_launch("gg_rmsprop_multi");
 }
 
 __global__ void __launch_bounds__(256) pack_kernel(const gg_adam_entry* __restrict__ table, const gg_adam_chunk* __restrict__ chunks,
                                                    int n_chunks, const long long* __restrict__ flat_offsets,
                                                    float* __restrict__ flat, int to_flat) {
+  GG_PDL_ENTRY();
   int ci = blockIdx.x;
   if (ci >= n_chunks) return;
   gg_adam_chunk ch = chunks[ci];
@@ -456,7 +471,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const gg_adam_entry* __restri
 extern "C" int gg_pack_grads(const gg_adam_entry* table, const gg_adam_chunk* chunks, int n_chunks,
                              const long long* flat_offsets, float* flat, int to_flat, void* stream) {
   if (n_chunks <= 0) return GG_OK;
-  pack_kernel<<<n_chunks, 256, 0, as_stream(stream)>>>(table, chunks, n_chunks, flat_offsets, flat, to_flat);
+  GG_LAUNCH(pack_kernel, n_chunks, 256, 0, as_stream(stream), table, chunks, n_chunks, flat_offsets, flat, to_flat);
   return check_launch("gg_pack_grads");
 }
 
@@ -480,10 +495,11 @@ __device__ __forceinline__ float u32_to_unit(uint32_t v) {  // [0,1)
 }
 
 __global__ void rng_tick_kernel(unsigned long long* tick) {
+  GG_PDL_ENTRY();
   if (threadIdx.x == 0 && blockIdx.x == 0) tick[0] += 1ull;
 }
 extern "C" int gg_rng_tick(void* tick_counter, void* stream) {
-  rng_tick_kernel<<<1, 32, 0, as_stream(stream)>>>(reinterpret_cast<unsigned long long*>(tick_counter));
+  GG_LAUNCH(rng_tick_kernel, 1, 32, 0, as_stream(stream), reinterpret_cast<unsigned long long*>(tick_counter));
   return check_launch("gg_rng_tick");
 }
 
@@ -491,6 +507,7 @@ extern "C" int gg_rng_tick(void* tick_counter, void* stream) {
 __global__ void __launch_bounds__(256) rng_fill_kernel(float* __restrict__ out, long long n, int mode, float a, float b,
                                                        unsigned long long seed, uint32_t stream_id,
                                                        const unsigned long long* __restrict__ tick) {
+  GG_PDL_ENTRY();
   unsigned long long t = tick ? tick[0] : 0ull;
   uint2 key = make_uint2((uint32_t)seed ^ (stream_id * 0x9E3779B9u), (uint32_t)(seed >> 32) + stream_id);
   long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -532,14 +549,14 @@ static int rng_grid(long long n) {
 extern "C" int gg_rng_normal(float* out, long long n, float mean, float stddev, uint64_t seed, uint32_t stream_id,
                              const void* tick_counter, void* stream) {
   if (n <= 0) return GG_OK;
-  rng_fill_kernel<<<rng_grid(n), 256, 0, as_stream(stream)>>>(out, n, 0, mean, stddev, seed, stream_id,
+  GG_LAUNCH(rng_fill_kernel, rng_grid(n), 256, 0, as_stream(stream), out, n, 0, mean, stddev, seed, stream_id,
                                                              reinterpret_cast<const unsigned long long*>(tick_counter));
   return check_launch("gg_rng_normal");
 }
 extern "C" int gg_rng_uniform(float* out, long long n, float lo, float hi, uint64_t seed, uint32_t stream_id,
                               const void* tick_counter, void* stream) {
   if (n <= 0) return GG_OK;
-  rng_fill_kernel<<<rng_grid(n), 256, 0, as_stream(stream)>>>(out, n, 1, lo, hi, seed, stream_id,
+  GG_LAUNCH(rng_fill_kernel, rng_grid(n), 256, 0, as_stream(stream), out, n, 1, lo, hi, seed, stream_id,
                                                              reinterpret_cast<const unsigned long long*>(tick_counter));
   return check_launch("gg_rng_uniform");
 }
@@ -547,6 +564,7 @@ extern "C" int gg_rng_uniform(float* out, long long n, float lo, float hi, uint6
 __global__ void __launch_bounds__(256) rng_categorical_kernel(int32_t* __restrict__ idx, int n, const float* __restrict__ probs,
                                                               int K, unsigned long long seed, uint32_t stream_id,
                                                               const unsigned long long* __restrict__ tick) {
+  GG_PDL_ENTRY();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   unsigned long long t = tick ? tick[0] : 0ull;
@@ -567,7 +585,7 @@ extern "C" int gg_rng_categorical(int32_t* idx, int n, const float* probs, int K
                                   const void* tick_counter, void* stream) {
   if (n <= 0) return GG_OK;
   GG_REQUIRE(K > 0, "gg_rng_categorical");
-  rng_categorical_kernel<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(idx, n, probs, K, seed, stream_id,
+  GG_LAUNCH(rng_categorical_kernel, ceil_div(n, 256), 256, 0, as_stream(stream), idx, n, probs, K, seed, stream_id,
                                                                          reinterpret_cast<const unsigned long long*>(tick_counter));
   return check_launch("gg_rng_categorical");
 }

@@ -39,6 +39,7 @@ SIGNATURES = {
     "gg_set_conv_backend": (c_i, [c_i]),
     "gg_get_conv_backend": (c_i, []),
     "gg_last_backend": (c_i, []),
+    "gg_set_pdl": (c_i, [c_i]),
     "gg_set_tc_max_ctas": (c_i, [c_i]),
     "gg_set_tc_stages": (c_i, [c_i]),
     "gg_conv2d_fwd": (c_i, [c_p, c_p, c_p, c_p] + [c_i] * 11 + [c_i, c_f, c_p, c_sz, c_p]),

@@ -55,6 +55,9 @@ int gg_get_conv_backend(void);
 int gg_last_backend(void);
 /* upper bound on the CTAs one tensor-core conv / dense launch may occupy (split-K is sized to it).  148 = the whole
  * GPU (default, best for a kernel running alone); the multi-stream executor sets 74 so two launches can overlap. */
+/* programmatic dependent launch for the stream-ordered (non-cooperative) kernels: 1 = launch every kernel with
+ * cudaLaunchAttributeProgrammaticStreamSerialization; kernels wait with griddepcontrol.wait after their prologue */
+int gg_set_pdl(int on);
 int gg_set_tc_max_ctas(int n);
 /* cap the operand-ring depth of the tensor-core kernels (0 = as deep as fits; 3 lets two CTAs share an SM) */
 int gg_set_tc_stages(int n);

@@ -21,7 +21,7 @@ def cpu_device(monkeypatch):
     real = cabi.call
 
     def fake(name, *args):
-        if name in ("gg_set_tc_max_ctas", "gg_set_tc_stages"):
+        if name in ("gg_set_tc_max_ctas", "gg_set_tc_stages", "gg_set_pdl"):
             return real(name, *args)
         record.append((name, args))
     monkeypatch.setattr(cabi, "call", fake)

@@ -28,7 +28,7 @@ executor.Runtime.dev = lambda self: torch.device("cpu")
 _orig_pin = torch.Tensor.pin_memory
 torch.Tensor.pin_memory = lambda self, *a, **k: self
 _real_call = cabi.call
-HOST_ONLY = ("gg_set_tc_max_ctas", "gg_set_tc_stages")
+HOST_ONLY = ("gg_set_tc_max_ctas", "gg_set_tc_stages", "gg_set_pdl")
 _record = []
 
 
