@@ -433,7 +433,12 @@ extern "C" size_t gg_conv2d_wgrad_workspace(int B, int H, int W, int Ci, int Co,
   return direct > tc ? direct : tc;
 }
 
-namespace gg { void conv_tc_set_stage_cap(int n); }
+namespace gg { void conv_tc_set_stage_cap(int n); void conv_tc_last_info(int* out8); }
+extern "C" int gg_last_tc_info(int* out8) {
+  if (!out8) return fail(GG_ERR_BAD_ARG, "gg_last_tc_info: null output%s");
+  gg::conv_tc_last_info(out8);
+  return GG_OK;
+}
 extern "C" int gg_set_tc_stages(int n) {
   gg::conv_tc_set_stage_cap(n);
   return GG_OK;

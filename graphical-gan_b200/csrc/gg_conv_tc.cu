@@ -567,7 +567,14 @@ bool pixel_box(int PW, int PH, int PB, int target, int* wt, int* ht, int* bt) {
   return true;
 }
 
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && e[0]) ? atoi(e) : dflt;
+}
+
 int pick_n_tile(int n) {
+  const int forced = env_int("GG_TC_NTILE", 0);   // experiment knob
+  if (forced > 0 && n % forced == 0) return forced;
   if (n % 128 == 0) return 128;
   if (n % 64 == 0) return 64;
   if (n % 32 == 0) return 32;
@@ -576,11 +583,6 @@ int pick_n_tile(int n) {
 
 int g_tc_max_ctas = kNumSMs;
 int g_tc_stage_cap = 0;
-
-int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return (e && e[0]) ? atoi(e) : dflt;
-}
 
 int pick_splits(int tiles, int kb_min) {
   int forced = env_int("GG_TC_SPLITS", 0);   // experiment knob
@@ -597,6 +599,7 @@ int pick_splits(int tiles, int kb_min) {
 }
 
 long long* g_dbg = nullptr;
+thread_local int g_last_info[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // gg_last_tc_info
 
 struct TcPlan {
   bool ok;
@@ -714,6 +717,8 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, TcPlan& pl, void* ws,
     attr_set[MODE] = true;
   }
   dim3 grid(pl.grid_x, p.splits);
+  g_last_info[0] = MODE; g_last_info[1] = pl.grid_x; g_last_info[2] = p.splits; g_last_info[3] = p.n_tile;
+  g_last_info[4] = p.stages; g_last_info[5] = p.cluster; g_last_info[6] = (int)smem; g_last_info[7] = p.m_tiles;
   if (p.cluster) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
@@ -840,6 +845,8 @@ int conv_tc_wgrad(const float* x, const float* dy, float* dw, int B, int H, int 
   *handled = true;
   return GG_OK;
 }
+
+void conv_tc_last_info(int* out8) { for (int i = 0; i < 8; ++i) out8[i] = g_last_info[i]; }
 
 void conv_tc_set_stage_cap(int n) { g_tc_stage_cap = n; }
 

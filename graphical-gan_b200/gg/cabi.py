@@ -42,6 +42,7 @@ SIGNATURES = {
     "gg_set_pdl": (c_i, [c_i]),
     "gg_set_tc_max_ctas": (c_i, [c_i]),
     "gg_set_tc_stages": (c_i, [c_i]),
+    "gg_last_tc_info": (c_i, [C.POINTER(c_i)]),
     "gg_conv2d_fwd": (c_i, [c_p, c_p, c_p, c_p] + [c_i] * 11 + [c_i, c_f, c_p, c_sz, c_p]),
     "gg_conv2d_dgrad": (c_i, [c_p, c_p, c_p, c_p] + [c_i] * 11 + [c_i, c_f, c_p, c_sz, c_p]),
     "gg_conv2d_wgrad": (c_i, [c_p, c_p, c_p] + [c_i] * 11 + [c_p, c_sz, c_p]),
@@ -126,6 +127,13 @@ def check(rc, what=""):
 def call(name, *args):
     """Call an int-returning entry point and raise on a non-zero status."""
     check(getattr(lib, name)(*args), name)
+
+
+def last_tc_info():
+    """dict view of gg_last_tc_info"""
+    out = (c_i * 8)()
+    call("gg_last_tc_info", out)
+    return dict(zip(("mode", "tiles", "splits", "n_tile", "stages", "cluster", "smem", "m_tiles"), list(out)))
 
 
 def stream_ptr():

@@ -61,6 +61,10 @@ int gg_set_pdl(int on);
 int gg_set_tc_max_ctas(int n);
 /* cap the operand-ring depth of the tensor-core kernels (0 = as deep as fits; 3 lets two CTAs share an SM) */
 int gg_set_tc_stages(int n);
+/* launch configuration of the calling thread's most recent tensor-core conv / dense launch (parity tests assert that the
+ * production shapes run under the plan's settings): out8 = {mode 0/1/2, tiles (grid.x), K splits (grid.y), n_tile,
+ * ring stages, cluster flag, dynamic shared memory bytes, m_tiles} */
+int gg_last_tc_info(int* out8);
 
 /* ---- activation codes ------------------------------------------------------------ */
 #define GG_ACT_NONE 0

@@ -47,6 +47,8 @@ def spin_up(seconds=0.6):
 
 
 spin_up()
+cabi.call("gg_set_pdl", int(os.environ.get("GG_PDL", "0")))
+cabi.call("gg_set_tc_stages", int(os.environ.get("GG_TC_STAGES", "3")))
 flush_only = graph_time(lambda: None, True)
 
 
@@ -72,8 +74,10 @@ def conv_case(B, H, W, Ci, Co, k=5, s=2):
     for name, fn in fns.items():
         hot = graph_time(fn, False)
         cold = graph_time(fn, True) - flush_only
-        print("conv %-5s B%d %dx%d %d->%d k%d s%d  hot %6.1f us (%6.1f TF/s)  cold %6.1f us  backend %d" %
-              (name, B, H, W, Ci, Co, k, s, hot, gf / hot * 1e3, cold, cabi.lib.gg_last_backend()), flush=True)
+        info = cabi.last_tc_info()
+        print("conv %-5s B%d %dx%d %d->%d k%d s%d  hot %6.1f us (%6.1f TF/s)  cold %6.1f us  backend %d tiles %d splits %d n_tile %d stages %d" %
+              (name, B, H, W, Ci, Co, k, s, hot, gf / hot * 1e3, cold, cabi.lib.gg_last_backend(), info["tiles"], info["splits"],
+               info["n_tile"], info["stages"]), flush=True)
 
 
 def gemm_case(M, N, K, ta=0, tb=0):
@@ -90,6 +94,9 @@ def gemm_case(M, N, K, ta=0, tb=0):
 if __name__ == "__main__":
     print("flush-only %.1f us" % flush_only)
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which == "dom":
+        conv_case(128, 16, 16, 64, 128)
+        sys.exit(0)
     conv_case(64, 16, 16, 64, 128)
     conv_case(64, 8, 8, 128, 256)
     if which in ("all", "batched"):

@@ -59,6 +59,7 @@ def run(name, fn):
 
 
 spin_up()
+cabi.call("gg_set_tc_stages", int(os.environ.get("GG_TC_STAGES", "3")))
 B, H, W, Ci, Co, k, s = 64, 16, 16, 64, 128, 5, 2
 x = torch.randn(B, H, W, Ci, device="cuda"); w = torch.randn(k, k, Ci, Co, device="cuda") * .05
 b = torch.zeros(Co, device="cuda"); dy = torch.randn(B, H // 2, W // 2, Co, device="cuda")
@@ -66,7 +67,9 @@ A_ = torch.randn(64, 512, device="cuda"); B_ = torch.randn(512, 512, device="cud
 A2 = torch.randn(64, 4608, device="cuda"); B2 = torch.randn(4608, 512, device="cuda")
 x1 = torch.randn(64, 32, 32, 3, device="cuda"); w1 = torch.randn(5, 5, 3, 64, device="cuda") * .05; b1 = torch.zeros(64, device="cuda")
 x3 = torch.randn(B, 8, 8, 128, device="cuda"); w3 = torch.randn(k, k, 128, 256, device="cuda") * .05; b3 = torch.zeros(256, device="cuda")
+xb = torch.randn(2 * B, H, W, Ci, device="cuda")
 cases = (
+    ("D.2 fwd batched B=128", lambda: U.conv_fwd(xb, w, b, s, 'SAME', act="leaky")),
     ("gemm 64x512x512", lambda: U.gemm(A_, B_, bias_, 64, 512, 512, 0, 0, act="leaky")),
     ("gemm 64x512x4608", lambda: U.gemm(A2, B2, bias_, 64, 512, 4608, 0, 0, act="leaky")),
     ("conv1 fwd 3->64 (im2col+tc)", lambda: U.conv_fwd(x1, w1, b1, s, 'SAME', act="leaky")),
@@ -75,5 +78,9 @@ cases = (
     ("E.2 dgrad", lambda: U.conv_dgrad(dy, w, None, H, W, s, 'SAME')),
     ("E.2 wgrad", lambda: U.conv_wgrad(x, dy, k, s, 'SAME')),
 )
+only = sys.argv[1:] 
 for name, fn in cases:
+    if only and not any(o in name for o in only):
+        continue
     run(name, fn)
+    print("%-28s   tc info %s" % ("", cabi.last_tc_info()))
