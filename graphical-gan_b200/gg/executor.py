@@ -36,6 +36,7 @@ class Runtime(object):
         self.slots = {}        # (optimizer id, param id) -> (m, v)
         self.opt_state = {}    # optimizer id -> device state tensor {b1^t, b2^t, t}
         self.plans = {}
+        self.pending_restore = {}   # optimiser state read by Saver.restore before the plan that owns it exists
         self.seed = 1234
         self._tick = None
         self._zero = None
@@ -97,6 +98,12 @@ class Runtime(object):
             h = torch.zeros(max(node.size, 1), dtype=dt).pin_memory()
             self.feeds[node.id] = (d, h)
         return self.feeds[node.id]
+
+    def rng_seed(self):
+        """Philox key of the in-graph random ops: the graph seed with the data-parallel rank in the high word, so that every
+        rank draws its OWN slice of the global noise batch (p_z, Gumbel uniforms, dequantisation noise) — with identical
+        keys the global fake batch would be `world` copies of one local batch."""
+        return (int(self.seed) + (ggdist.rank() << 32)) & 0xFFFFFFFFFFFFFFFF
 
     # ---- public -------------------------------------------------------------------------------
     def get_param(self, node):
@@ -472,12 +479,12 @@ class Plan(object):
         kind, a, b = node.attrs["kind"], node.attrs.get("a", 0.0), node.attrs.get("b", 1.0)
         rt = self.rt
         if kind == "normal":
-            self.steps.append(lambda st: cabi.call("gg_rng_normal", op_, n, a, b, rt.seed, sid, tick, st))
+            self.steps.append(lambda st: cabi.call("gg_rng_normal", op_, n, a, b, rt.rng_seed(), sid, tick, st))
         elif kind == "uniform":
-            self.steps.append(lambda st: cabi.call("gg_rng_uniform", op_, n, a, b, rt.seed, sid, tick, st))
+            self.steps.append(lambda st: cabi.call("gg_rng_uniform", op_, n, a, b, rt.rng_seed(), sid, tick, st))
         else:
             pp, K = self._in(node, 0).data_ptr(), node.inputs[0].size
-            self.steps.append(lambda st: cabi.call("gg_rng_categorical", op_, n, pp, K, rt.seed, sid, tick, st))
+            self.steps.append(lambda st: cabi.call("gg_rng_categorical", op_, n, pp, K, rt.rng_seed(), sid, tick, st))
 
     # layout
     def _emit_transpose(self, node):
@@ -703,11 +710,21 @@ class Plan(object):
         for (v, _), p in zip(pairs, params):
             key = (op.attrs["opt_id"], v.id)
             if key not in rt.slots:
-                rt.slots[key] = (torch.zeros_like(p), torch.zeros_like(p))
+                # Adam: m = v = 0.  RMSProp: tf.train.RMSPropOptimizer creates its `rms` slot as ONES (and `momentum` as
+                # zeros); with a zero slot the first updates would be lr*g/sqrt(0.1 g^2) ~ 3.16 lr sign(g) instead of ~lr*g
+                first = torch.ones_like(p) if op.kind == "rmsprop" else torch.zeros_like(p)
+                rt.slots[key] = (first, torch.zeros_like(p))
+                pend = rt.pending_restore.get("slots", {}).pop("%d/%s" % (key[0], v.name), None)   # Saver.restore before run
+                if pend is not None:
+                    rt.slots[key][0].copy_(pend[0])
+                    rt.slots[key][1].copy_(pend[1])
             ms.append(rt.slots[key][0])
             vs.append(rt.slots[key][1])
         if op.attrs["opt_id"] not in rt.opt_state:
             rt.opt_state[op.attrs["opt_id"]] = torch.zeros(3, dtype=torch.float64, device=rt.dev())
+            pend = rt.pending_restore.get("opt_state", {}).pop(op.attrs["opt_id"], None)
+            if pend is not None:
+                rt.opt_state[op.attrs["opt_id"]].copy_(pend)
         state = rt.opt_state[op.attrs["opt_id"]]
         sizes = [v.size for v, _ in pairs]
         world = ggdist.world_size()

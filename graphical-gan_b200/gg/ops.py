@@ -111,6 +111,9 @@ def concat(values, axis):
     if axis < 0:
         axis += nd
     shape = list(values[0].shape)
+    for v in values[1:]:
+        if len(v.shape) != nd or any(a != b for i, (a, b) in enumerate(zip(v.shape, shape)) if i != axis) or v.dtype != values[0].dtype:
+            raise ValueError("concat along axis %d: shapes %s do not agree off the axis" % (axis, [tuple(t.shape) for t in values]))
     shape[axis] = sum(v.shape[axis] for v in values)
     return Tensor("concat", values, {"axis": axis}, shape, values[0].dtype)
 

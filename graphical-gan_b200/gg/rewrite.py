@@ -118,7 +118,7 @@ class _Matcher(object):
                 return None
             return O.concat(self._batched_inputs(a, b, range(len(a.inputs))), a.attrs["axis"])
         if op == "slice":
-            if a.attrs["axis"] == 0 or not self.same_attrs(a, b):
+            if a.attrs["axis"] == 0 or not self.same_attrs(a, b) or tuple(a.inputs[0].shape[1:]) != tuple(b.inputs[0].shape[1:]):
                 return None
             return O.slice_axis(self.match(a.inputs[0], b.inputs[0]), a.attrs["axis"], a.attrs["start"], a.attrs["size"])
         if op == "softmax":
@@ -126,7 +126,7 @@ class _Matcher(object):
                 return None
             return O.softmax(self.match(a.inputs[0], b.inputs[0]))
         if op == "reduce":
-            if 0 in a.attrs["axes"] or not self.same_attrs(a, b):
+            if 0 in a.attrs["axes"] or not self.same_attrs(a, b) or tuple(a.inputs[0].shape[1:]) != tuple(b.inputs[0].shape[1:]):
                 return None
             x = self.match(a.inputs[0], b.inputs[0])
             return Tensor("reduce", (x,), a.attrs, (Ba + Bb,) + tuple(a.shape[1:]), float32)

@@ -434,12 +434,32 @@ class RMSPropOptimizer(_Optimizer):
 
 class Saver(object):
     """Registry + optimiser-state checkpoint (the reference only ever saves, at the last iteration:
-    gmgan_inference_cifar10.py:465,548-549); restore is provided for completeness."""
+    gmgan_inference_cifar10.py:465,548-549); restore is provided for completeness.
+
+    Parameters are enumerated from the tflib registry and tf.Variable list, NOT from the runtime's lazily filled buffer
+    table: build graph -> restore -> train works before any Session.run, and save() includes variables no plan has touched
+    yet (e.g. batch-norm moving_mean / moving_variance).  Optimiser slots restored before their plan exists are parked in
+    RT.pending_restore and applied when the optimiser step is emitted.  Missing / unexpected names raise."""
+
+    @staticmethod
+    def _variables():
+        import tflib as lib
+        nodes = {}
+        for name, node in lib._params.items():
+            nodes[name] = node
+        for node in _trainable:
+            if node.name is not None:
+                nodes.setdefault(node.name, node)
+        return nodes
 
     def save(self, sess, path):
         import torch
         from .executor import RT
-        state = {"params": {RT.param_nodes[i].name: t.cpu() for i, t in RT.params.items()},
+        nodes = self._variables()
+        for i, n in RT.param_nodes.items():
+            if n.name is not None:
+                nodes.setdefault(n.name, n)
+        state = {"params": {name: RT.param_buffer(n).cpu() for name, n in nodes.items()},
                  "slots": {"%d/%s" % (k[0], RT.param_nodes[k[1]].name): (m.cpu(), v.cpu()) for k, (m, v) in RT.slots.items()},
                  "opt_state": {k: v.cpu() for k, v in RT.opt_state.items()}}
         torch.save(state, path)
@@ -449,19 +469,36 @@ class Saver(object):
         import torch
         from .executor import RT
         state = torch.load(path)
-        by_name = {n.name: i for i, n in RT.param_nodes.items()}
+        nodes = self._variables()
+        for i, n in RT.param_nodes.items():
+            if n.name is not None:
+                nodes.setdefault(n.name, n)
+        missing = sorted(set(nodes) - set(state["params"]))
+        unexpected = sorted(set(state["params"]) - set(nodes))
+        if missing or unexpected:
+            raise KeyError("checkpoint %s does not match the graph: missing %s, unexpected %s" % (path, missing[:8], unexpected[:8]))
         for name, t in state["params"].items():
-            if name in by_name:
-                RT.params[by_name[name]].copy_(t)
+            buf = RT.param_buffer(nodes[name])
+            if buf.numel() != t.numel():
+                raise ValueError("checkpoint variable %s has %d elements, the graph's has %d" % (name, t.numel(), buf.numel()))
+            buf.copy_(t)
+        by_name = {n.name: i for i, n in RT.param_nodes.items()}
+        pend = RT.pending_restore
+        pend.setdefault("slots", {})
+        pend.setdefault("opt_state", {})
         for key, (m, v) in state["slots"].items():
             oid, name = key.split("/", 1)
             k = (int(oid), by_name.get(name))
             if k in RT.slots:
                 RT.slots[k][0].copy_(m)
                 RT.slots[k][1].copy_(v)
+            else:
+                pend["slots"][key] = (m, v)
         for k, v in state["opt_state"].items():
             if k in RT.opt_state:
                 RT.opt_state[k].copy_(v)
+            else:
+                pend["opt_state"][k] = v
 
 
 class _Train(object):
@@ -493,5 +530,7 @@ class Session(object):
 
 def reset_default_graph():
     from .executor import reset_runtime
+    global _opt_ids
     del _trainable[:]
+    _opt_ids = itertools.count()      # optimiser ids key the checkpointed slots: a rebuilt graph numbers them like a fresh process
     reset_runtime()

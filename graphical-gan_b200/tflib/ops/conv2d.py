@@ -35,7 +35,7 @@ def Conv2D(name, input_dim, output_dim, filter_size, inputs, he_init=True, mask_
     """inputs / returns: (batch size, num channels, height, width); mask_type: None or ('a'|'b', n_channels)."""
     kshape = (filter_size, filter_size, input_dim, output_dim)
     fan_in = input_dim * filter_size ** 2
-    fan_out = output_dim * filter_size ** 2 / (stride ** 2)
+    fan_out = output_dim * filter_size ** 2 // (stride ** 2)     # Python-2 integer division in the reference (conv2d.py:63)
     if mask_type is not None:            # "only approximately correct" (conv2d.py:65-67)
         fan_in, fan_out = fan_in / 2., fan_out / 2.
     stdev = _weights_stdev if _weights_stdev is not None else _init.fan_stdev(fan_in, fan_out, he_init)

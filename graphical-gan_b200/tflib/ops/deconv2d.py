@@ -37,7 +37,7 @@ def Deconv2D(name, input_dim, output_dim, filter_size, inputs, he_init=True, wei
     if mask_type is not None:
         raise Exception('Unsupported configuration')
     kshape = (filter_size, filter_size, output_dim, input_dim)
-    fan_in = input_dim * filter_size ** 2 / (stride ** 2)
+    fan_in = input_dim * filter_size ** 2 // (stride ** 2)      # Python-2 integer division in the reference (deconv2d.py:52)
     fan_out = output_dim * filter_size ** 2
     stdev = _weights_stdev if _weights_stdev is not None else _init.fan_stdev(fan_in, fan_out, he_init)
     filter_values = _init.uniform(stdev, kshape) * gain
