@@ -528,6 +528,31 @@ extern "C" int gg_cast_u8_f32(const uint8_t* x, float* y, long long n, float a, 
   GG_LAUNCH((cast_to_f32_kernel<uint8_t>), ew_grid(n, 1), 256, 0, as_stream(stream), x, y, n, a, b);
   return check_launch("gg_cast_u8_f32");
 }
+// uint8 -> int32 widening of a fed image batch: the host stages and copies ONE byte per pixel (the datasets' on-disk
+// dtype, tflib/cifar10.py:8-48) and the int32 placeholder of the graph (gmgan_inference_cifar10.py:341) is filled on
+// the device; 16 pixels per thread (one 16-byte load, four 16-byte stores).  Bit exact.
+__global__ void __launch_bounds__(256) widen_u8_i32_kernel(const uint8_t* __restrict__ x, int32_t* __restrict__ y, long long n) {
+  GG_PDL_ENTRY();
+  const long long n16 = n >> 4;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long v = i; v < n16; v += stride) {
+    const uint4 q = reinterpret_cast<const uint4*>(x)[v];
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    int4* o = reinterpret_cast<int4*>(y) + v * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      o[j] = make_int4((int)(w[j] & 0xffu), (int)((w[j] >> 8) & 0xffu), (int)((w[j] >> 16) & 0xffu), (int)(w[j] >> 24));
+  }
+  for (long long t = (n16 << 4) + i; t < n; t += stride) y[t] = (int32_t)x[t];
+}
+extern "C" int gg_widen_u8_i32(const uint8_t* x, int32_t* y, long long n, void* stream) {
+  if (n <= 0) return GG_OK;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15))
+    return fail(GG_ERR_BAD_ARG, "gg_widen_u8_i32: buffers must be 16-byte aligned%s");
+  GG_LAUNCH(widen_u8_i32_kernel, ew_grid((n + 15) / 16, 1), 256, 0, as_stream(stream), x, y, n);
+  return check_launch("gg_widen_u8_i32");
+}
 __global__ void __launch_bounds__(256) cast_f32_i32_kernel(const float* __restrict__ x, int32_t* __restrict__ y, long long n) {
   GG_PDL_ENTRY();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -75,6 +75,7 @@ SIGNATURES = {
     "gg_cast_i32_f32": (c_i, [c_p, c_p, c_ll, c_f, c_f, c_p]),
     "gg_cast_u8_f32": (c_i, [c_p, c_p, c_ll, c_f, c_f, c_p]),
     "gg_cast_f32_i32": (c_i, [c_p, c_p, c_ll, c_p]),
+    "gg_widen_u8_i32": (c_i, [c_p, c_p, c_ll, c_p]),
     "gg_add_n": (c_i, [C.POINTER(c_p), c_i, c_p, c_ll, c_p]),
     "gg_bce_mean": (c_i, [c_p, c_i, c_f, c_f, c_p, c_i, c_p]),
     "gg_bce_mean_grad": (c_i, [c_p, c_i, c_f, c_f, c_p, c_p, c_i, c_p]),

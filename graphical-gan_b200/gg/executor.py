@@ -90,6 +90,16 @@ class Runtime(object):
             self.consts[node.id] = torch.from_numpy(arr.copy()).to(self.dev())
         return self.consts[node.id]
 
+    def feed_buffer_u8(self, node):
+        """uint8 staging pair (device, pinned host) of an int32 placeholder fed with a uint8 array: one byte per element
+        crosses PCIe and gg_widen_u8_i32 fills the int32 feed buffer on the device (bit exact)"""
+        torch = _torch()
+        key = ("u8", node.id)
+        if key not in self.feeds:
+            n = max(node.size, 1)
+            self.feeds[key] = (torch.zeros(n, dtype=torch.uint8, device=self.dev()), torch.zeros(n, dtype=torch.uint8).pin_memory())
+        return self.feeds[key]
+
     def feed_buffer(self, node):
         torch = _torch()
         if node.id not in self.feeds:
@@ -1000,6 +1010,14 @@ class Plan(object):
                 arr = np.asarray(value)
                 if arr.size != node.size:
                     raise ValueError("feed for %s has %d elements, expected %s" % (node.name, arr.size, tuple(node.shape)))
+                if arr.dtype == np.uint8 and node.dtype == int32:
+                    d8, h8 = self.rt.feed_buffer_u8(node)
+                    h8.copy_(torch.from_numpy(np.ascontiguousarray(arr.reshape(-1))))
+                    d8.copy_(h8, non_blocking=True)
+                    cabi.call("gg_widen_u8_i32", d8.data_ptr(), d.data_ptr(), node.size, cabi.stream_ptr())
+                    self.h2d_bytes = getattr(self, "h2d_bytes", 0) + arr.size
+                    continue
+                self.h2d_bytes = getattr(self, "h2d_bytes", 0) + arr.size * 4
                 h.copy_(torch.from_numpy(np.ascontiguousarray(arr.reshape(-1).astype(node.dtype.as_numpy_dtype, copy=False))))
                 d.copy_(h, non_blocking=True)
         self.runs += 1

@@ -661,9 +661,59 @@ def _grad_bn(n, g, need):
     return [bg, reshape(aux(bg, 1, (C,)), gamma.shape), reshape(aux(bg, 2, (C,)), beta.shape)]
 
 
+def substitute(roots, mapping):
+    """clone the expression graph above the keys of `mapping` ({node: replacement}); untouched sub-graphs are shared"""
+    memo = {k.id: v for k, v in mapping.items()}
+
+    def rec(t):
+        if t.id in memo:
+            return memo[t.id]
+        new_in = [rec(i) for i in t.inputs]
+        r = t if all(a is b for a, b in zip(new_in, t.inputs)) else Tensor(t.op, new_in, t.attrs, t.shape, t.dtype)
+        memo[t.id] = r
+        return r
+    return [rec(t) if t is not None else None for t in roots]
+
+
 def _grad_bn_grad(n, g, need):
-    raise NotImplementedError("second-order gradient through batch norm (no reference configuration needs it: the "
-                              "WGAN-GP critics of gan_inference_svhn.py run with BN_FLAG=False or without BN in D)")
+    """Second-order gradient through batch norm: gan_inference_mnist.py MODE='wali-gp' puts BN inside the critic (:225,230)
+    and differentiates tf.gradients(D(x_hat), x_hat) again (:346-357).  The first-order node dx = bn_grad(gy, x, ...) is
+    re-expressed over proxy leaves with primitive ops whose gradient rules exist — statistics recomputed from x, so the
+    dependence of mean / rstd on x is differentiated too:
+        xh = (x - mean(x)) rsqrt(var(x) + eps);  ga = act'(y) gy;  dx = gamma rstd (ga - mean(ga) - xh mean(ga xh))
+    — that expression is differentiated symbolically w.r.t. (gy, x, gamma) and the proxies are replaced by the real nodes.
+    The fused activation's mask act'(y) is piecewise constant in x (zero derivative almost everywhere, like TF's ReluGrad).
+    Gradients flowing into the dgamma / dbeta outputs of a bn_grad node are not propagated (no reference graph does that)."""
+    gy, x, y, mean, rstd, gamma = n.inputs
+    bn_node = y if y.op == "bn" else None
+    eps = bn_node.attrs["eps"] if bn_node is not None else 1e-5
+    act, alpha = n.attrs["act"], n.attrs["alpha"]
+    C = x.shape[-1]
+    axes = list(range(len(x.shape) - 1))
+    px = placeholder(float32, x.shape, name="bn2_x")
+    pgy = placeholder(float32, gy.shape, name="bn2_gy")
+    pgamma = placeholder(float32, (C,), name="bn2_gamma")
+    py = placeholder(float32, y.shape, name="bn2_y")
+    mu = reduce("mean", px, axes, keepdims=True)
+    xc = sub(px, mu)
+    var = reduce("mean", unary("square", xc), axes, keepdims=True)
+    rs = unary("rsqrt", unary("affine", var, 1.0, float(eps)))
+    xh = mul(xc, rs)
+    ga = _act_grad(py, pgy, act, alpha)
+    m1 = reduce("mean", ga, axes, keepdims=True)
+    m2 = reduce("mean", mul(ga, xh), axes, keepdims=True)
+    gam = reshape(pgamma, (1,) * len(axes) + (C,))
+    dx = mul(mul(gam, rs), sub(sub(ga, m1), mul(xh, m2)))
+    d_gy, d_x, d_gamma = gradients(dx, [pgy, px, pgamma], grad_ys=[g])
+    d_gy, d_x, d_gamma = substitute([d_gy, d_x, d_gamma], {px: x, pgy: gy, pgamma: reshape(gamma, (C,)), py: y})
+    out = [None] * 6
+    if need[0]:
+        out[0] = d_gy
+    if need[1]:
+        out[1] = d_x
+    if need[5] and d_gamma is not None:
+        out[5] = reshape(d_gamma, gamma.shape)
+    return out
 
 
 def _grad_concat(n, g, need):

@@ -5,9 +5,9 @@
 (:134), 28 -> 14 -> 7 -> 4 strided convolutions, BN_FLAG = True for the non-vegan modes (:66-71) — here also INSIDE the
 (x, z) critic (Discriminator.BN2 / BN3, :229-236), which also has two extra dense layers (Discriminator.2 on the z branch,
 zx2; :241-254).  Consequences: sibling batching of D(fake) / D(real) stops at the critic's batch norms (rows are coupled
-there: each tower keeps its own statistics, as in the reference), and MODE='wali-gp' would need the second-order gradient
-of batch norm, which no kernel provides — it raises NotImplementedError at graph construction (the reference's default MODE
-is 'ali').  Line numbers refer to /root/reference/gan_inference_mnist.py.
+there: each tower keeps its own statistics, as in the reference), and MODE='wali-gp' needs the second-order gradient
+of batch norm: gg/ops.py::_grad_bn_grad re-expresses the batch-norm gradient with primitive ops and differentiates those
+(pinned against torch's double backward in tests/test_cpu_oracle_models.py; the reference's default MODE is 'ali').  Line numbers refer to /root/reference/gan_inference_mnist.py.
 """
 import os
 import sys

@@ -209,6 +209,10 @@ int gg_argmax(const float* x, int32_t* idx, int R, int C, void* stream);
 int gg_cast_i32_f32(const int32_t* x, float* y, long long n, float a, float b, void* stream);
 int gg_cast_u8_f32(const uint8_t* x, float* y, long long n, float a, float b, void* stream);
 int gg_cast_f32_i32(const float* x, int32_t* y, long long n, void* stream);
+/* y[i] = (int32) x[i]: a uint8 image batch (the dtype tflib/cifar10.py:8-48 and svhn / celebA loaders hand to
+ * session.run) widened on the device into the graph's int32 placeholder (gmgan_inference_cifar10.py:341) — one byte per
+ * pixel crosses PCIe instead of four.  Both pointers 16-byte aligned.  Bit exact. */
+int gg_widen_u8_i32(const uint8_t* x, int32_t* y, long long n, void* stream);
 /* out = sum_i in[i] over `count` same-sized tensors whose device pointers are listed in ptrs (host array) */
 int gg_add_n(const float* const* ptrs, int count, float* out, long long n, void* stream);
 

@@ -18,10 +18,14 @@ TEMP = 0.1
 
 
 class GMGANCifar10(object):
-    def __init__(self, params, dtype=torch.float32, dim=DIM, n_coms=N_COMS, threads=None):
-        """params: {name: ndarray} with the tflib names ('Generator.2.Filters', 'Discriminator.zx1.W', ...)."""
+    def __init__(self, params, dtype=torch.float32, dim=DIM, n_coms=N_COMS, threads=None, mode='local_ep', bn=None, lamb=1.):
+        """params: {name: ndarray} with the tflib names ('Generator.2.Filters', 'Discriminator.zx1.W', ...).
+        mode: 'local_ep' (north star) | 'local_epce' | 'ali' | 'alice' | 'vegan'  (:355-410); batch norm is on except in
+        'vegan' (:59-63 of the script: BN_FLAG False, DIM_LATENT 8)."""
         if threads:
             torch.set_num_threads(threads)
+        self.mode, self.lamb = mode, lamb
+        self.bn = (mode != 'vegan') if bn is None else bn
         self.dtype = dtype
         self.dim = dim
         self.n_coms = n_coms
@@ -35,13 +39,14 @@ class GMGANCifar10(object):
     # ---- networks -----------------------------------------------------------------------------
     def generator(self, noise):                                                     # :175-195
         p, D = self.p, self.dim
+        bn = lambda t, name, axes: O.batchnorm(t, p[name + '.scale'], p[name + '.offset'], axes) if self.bn else t
         out = O.linear(noise, p['Generator.Input.W'], p['Generator.Input.b'])
-        out = O.batchnorm(out, p['Generator.BN1.scale'], p['Generator.BN1.offset'], [0])
+        out = bn(out, 'Generator.BN1', [0])
         out = torch.relu(out).reshape(-1, 4 * D, 4, 4)
         out = O.conv2d_transpose(out, p['Generator.2.Filters'], 2, 'SAME', p['Generator.2.Biases'])
-        out = torch.relu(O.batchnorm(out, p['Generator.BN2.scale'], p['Generator.BN2.offset'], [0, 2, 3]))
+        out = torch.relu(bn(out, 'Generator.BN2', [0, 2, 3]))
         out = O.conv2d_transpose(out, p['Generator.3.Filters'], 2, 'SAME', p['Generator.3.Biases'])
-        out = torch.relu(O.batchnorm(out, p['Generator.BN3.scale'], p['Generator.BN3.offset'], [0, 2, 3]))
+        out = torch.relu(bn(out, 'Generator.BN3', [0, 2, 3]))
         out = O.conv2d_transpose(out, p['Generator.5.Filters'], 2, 'SAME', p['Generator.5.Biases'])
         return torch.tanh(out).reshape(-1, 3072)
 
@@ -49,10 +54,11 @@ class GMGANCifar10(object):
         p = self.p
         out = x.reshape(-1, 3, 32, 32)
         out = O.leaky_relu(O.conv2d(out, p['Extractor.1.Filters'], 2, 'SAME', p['Extractor.1.Biases']))
+        bn = lambda t, name, axes: O.batchnorm(t, p[name + '.scale'], p[name + '.offset'], axes) if self.bn else t
         out = O.conv2d(out, p['Extractor.2.Filters'], 2, 'SAME', p['Extractor.2.Biases'])
-        out = O.leaky_relu(O.batchnorm(out, p['Extractor.BN2.scale'], p['Extractor.BN2.offset'], [0, 2, 3]))
+        out = O.leaky_relu(bn(out, 'Extractor.BN2', [0, 2, 3]))
         out = O.conv2d(out, p['Extractor.3.Filters'], 2, 'SAME', p['Extractor.3.Biases'])
-        out = O.leaky_relu(O.batchnorm(out, p['Extractor.BN3.scale'], p['Extractor.BN3.offset'], [0, 2, 3]))
+        out = O.leaky_relu(bn(out, 'Extractor.BN3', [0, 2, 3]))
         out = out.reshape(-1, 4 * 4 * 4 * self.dim)
         return O.linear(out, p['Extractor.Output.W'], p['Extractor.Output.b'])
 
@@ -86,6 +92,16 @@ class GMGANCifar10(object):
         out = O.leaky_relu(O.linear(out, p['Discriminator.zx1.W'], p['Discriminator.zx1.b']))
         return O.linear(out, p['Discriminator.Output.W'], p['Discriminator.Output.b']).reshape(-1)
 
+    def discriminator_xzk(self, x, z, k):                                           # :309-336 (ali / alice: one joint critic)
+        p = self.p
+        out = x.reshape(-1, 3, 32, 32)
+        for i in (1, 2, 3):
+            out = O.leaky_relu(O.conv2d(out, p['Discriminator.x%d.Filters' % i], 2, 'SAME', p['Discriminator.x%d.Biases' % i]))
+        out = out.reshape(-1, 4 * 4 * 4 * self.dim)
+        zk = O.leaky_relu(O.linear(torch.cat([z, k], 1), p['Discriminator.zk1.W'], p['Discriminator.zk1.b']))
+        out = O.leaky_relu(O.linear(torch.cat([out, zk], 1), p['Discriminator.zkx1.W'], p['Discriminator.zkx1.b']))
+        return O.linear(out, p['Discriminator.Output.W'], p['Discriminator.Output.b']).reshape(-1)
+
     # ---- graph (:341-397) -----------------------------------------------------------------------
     def costs(self, real_x_int, hyper_p_z, k_idx, U):
         t = lambda a: torch.as_tensor(np.asarray(a)).to(self.dtype)
@@ -95,9 +111,23 @@ class GMGANCifar10(object):
         k1h = torch.nn.functional.one_hot(torch.as_tensor(np.asarray(k_idx)).long(), self.n_coms).to(self.dtype)
         p_z = self.hyper_generator(k1h, t(hyper_p_z))
         fake_x = self.generator(p_z)
-        disc_fake = [self.hyper_discriminator(p_z, k1h), self.discriminator(fake_x, p_z)]
-        disc_real = [self.hyper_discriminator(q_z, q_k), self.discriminator(real_x, q_z)]
-        gen_cost, disc_cost = O.local_ep_costs(disc_fake, disc_real)
+        rec = lambda: 1. * O.distance(real_x, self.generator(q_z), 'l2')           # DISTANCE_X = 'l2' (:52-55)
+        if self.mode in ('local_ep', 'local_epce'):
+            disc_fake = [self.hyper_discriminator(p_z, k1h), self.discriminator(fake_x, p_z)]
+            disc_real = [self.hyper_discriminator(q_z, q_k), self.discriminator(real_x, q_z)]
+            if self.mode == 'local_ep':
+                gen_cost, disc_cost = O.local_ep_costs(disc_fake, disc_real)
+            else:
+                gen_cost, disc_cost = O.local_epce_costs(disc_fake, disc_real, rec())
+        elif self.mode == 'vegan':                                                 # :355-359, critic on (z, k) only
+            disc_fake, disc_real = self.hyper_discriminator(p_z, k1h), self.hyper_discriminator(q_z, q_k)
+            gen_cost, disc_cost = O.vegan_costs(disc_fake, disc_real, rec(), self.lamb)
+        else:                                                                      # ali / alice :371-376
+            disc_real, disc_fake = self.discriminator_xzk(real_x, q_z, q_k), self.discriminator_xzk(fake_x, p_z, k1h)
+            if self.mode == 'ali':
+                gen_cost, disc_cost = O.ali_costs(disc_fake, disc_real)
+            else:
+                gen_cost, disc_cost = O.alice_costs(disc_fake, disc_real, rec())
         return gen_cost, disc_cost, dict(q_z=q_z, p_z=p_z, fake_x=fake_x, q_k=q_k, disc_fake=disc_fake, disc_real=disc_real)
 
     def disc_step(self, real_x_int, hyper_p_z, k_idx, U, apply=True):

@@ -169,6 +169,44 @@ def ali_costs(disc_fake, disc_real, s_f=None):
     return gen, disc
 
 
+def local_epce_costs(disc_fake_list, disc_real_list, rec_penalty, s_f=None):
+    """gan_inference.py:121-147: local_ep, then the reconstruction penalty is added AFTER the division by the list length."""
+    gen, disc = local_ep_costs(disc_fake_list, disc_real_list, s_f)
+    return gen + rec_penalty, disc
+
+
+def alice_costs(disc_fake, disc_real, rec_penalty, s_f=None):
+    """gan_inference.py:161-181."""
+    gen, disc = ali_costs(disc_fake, disc_real, s_f)
+    return gen + rec_penalty, disc
+
+
+def vegan_costs(disc_fake, disc_real, rec_penalty, lamb, s_f=None):
+    """gan_inference.py:194-212: the generator term sees only the fake logits; disc_cost is scaled by lamb/2."""
+    gen = bce_mean(disc_fake, 1.0)
+    if s_f is not None:
+        gen = gen + s_f
+    gen = gen * lamb + rec_penalty
+    disc = (bce_mean(disc_fake, 0.0) + bce_mean(disc_real, 1.0)) * (lamb / 2)
+    return gen, disc
+
+
+def local_ep_dynamic_costs(disc_fake_zz, disc_real_zz, disc_fake_xz, disc_real_xz, rec_penalty=None):
+    """gan_inference.py:246-293: the zz pairs are averaged over len+1, the xz pair is added un-normalised."""
+    gen, disc = 0.0, 0.0
+    for df, dr in zip(disc_fake_zz, disc_real_zz):
+        gen = gen + bce_mean(df, 1.0) + bce_mean(dr, 0.0)
+        disc = disc + bce_mean(df, 0.0) + bce_mean(dr, 1.0)
+    if len(disc_fake_zz) > 0:
+        gen = gen / (len(disc_fake_zz) + 1)
+        disc = disc / (len(disc_fake_zz) + 1)
+    gen = gen + bce_mean(disc_fake_xz, 1.0) + bce_mean(disc_real_xz, 0.0)
+    disc = disc + bce_mean(disc_fake_xz, 0.0) + bce_mean(disc_real_xz, 1.0)
+    if rec_penalty is not None:
+        gen = gen + rec_penalty
+    return gen, disc
+
+
 def wali_gp_costs(disc_fake, disc_real, gp):
     """gan_inference.py:28-32."""
     gen = -disc_fake.mean() + disc_real.mean()
