@@ -17,20 +17,36 @@
 //
 // Operands are fp32 in HBM; the tensor maps use CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 so the TMA unit rounds to tf32
 // (round-to-nearest, measured unbiased) on the way into shared memory; accumulation is fp32 in TMEM.
-// Pipeline: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warps 2-5 = epilogue (TMEM -> registers ->
-// bias + activation -> global).  4-stage full/empty mbarrier ring.  The GEMMs of this workload are small
-// (E.2: 4096x128x1600), so K is split across CTAs to fill the 148 SMs; partial tiles go to an L2-resident workspace
-// and the last CTA to arrive on a tile (atomic ticket) sums them in split order (deterministic) and runs the epilogue.
+//
+// Roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-9 = epilogue.  Round 2 (profiles/
+// timeline_conv_r2_baseline.txt) showed every phase of this kernel bound by instruction LATENCY of too few threads rather
+// than by bytes or flops: the producer / issuer loops cost ~0.3 us per 32-wide K block regardless of tile bytes (single
+// divergent lane, shared-memory addresses re-derived per instruction), the 4-warp epilogue took 1.7 us to move a 64 KB
+// accumulator, and the split-K exchange through an L2 workspace (write, fence, ticket, re-read) 6-8 us.  Now:
+//   * the producer / issuer loops run warp-convergent with one elected lane issuing, on precomputed 32-bit shared
+//     addresses and descriptor halves;
+//   * eight epilogue warps (two per TMEM lane quadrant, each taking half of the tile's columns);
+//   * split-K runs inside a thread-block cluster: the `splits` CTAs of a tile park their partial tile in their own shared
+//     memory and PUSH every peer's column slice with one bulk copy each (cp.async.bulk shared::cta -> shared::cluster,
+//     completion counted on the owner's mbarrier); every CTA then reduces its own slice in split order (deterministic)
+//     out of local shared memory.  No global workspace, no atomics, no cooperative launch.
 #include "gg_tc_common.cuh"
+
+#include <map>
+#include <tuple>
 
 namespace gg {
 
 namespace {
 
-constexpr int kMaxStages = 6;                  // 6 x 32 KB operand stages + 1 KB alignment slack fit the 227 KB of an SM
+constexpr int kMaxStages = 6;                  // 6 x 32 KB operand stages + slack fit the 227 KB of an SM
 constexpr int kABytes = 128 * 32 * 4;          // 16 KB: 128 rows (or 4 x 32 MN-blocks) of 32 fp32
 constexpr int kMaxNTile = 128;
-constexpr int kThreads = 192;
+constexpr int kEpiThreads = 256;               // warps 2..9
+constexpr int kThreads = 64 + kEpiThreads;
+constexpr int kMaxSplits = 8;                  // portable thread-block-cluster size
+constexpr int kMaxDynSmem = 227 * 1024 - 4096; // dynamic shared memory opt-in (the 227 KB limit includes ~3 KB of static)
+constexpr int kClusterStages = 4;              // split-K: ring depth that leaves room for the landing slots (<= 56 KB)
 
 struct TcParams {
   int B, H, W, Ci, Co, k, stride, pad_t, pad_l, Ho, Wo;
@@ -39,24 +55,59 @@ struct TcParams {
   int PH, PW;                 // pixel grid the tiles walk (fwd: Ho,Wo; dgrad: class grid; wgrad: Ho,Wo)
   int n_tile, n_tiles;        // GEMM N tiling
   int m_tiles;                // fwd/dgrad: tw*th*tb (per class); wgrad: ceil(taps*Ci/128)
-  int splits;
-  int stages;                 // depth of the operand ring (as many as fit)
-  int cluster;                // 1: the `splits` CTAs of a tile form a thread-block cluster and reduce through DSMEM
-  int bulk;                   // 1: split-K slices come back through cp.async.bulk (copy engine) instead of per-thread L2 loads
+  int splits;                 // K splits = cluster size along grid.y
+  int stages;                 // depth of the operand ring
+  int stage_off;              // split-K: byte offset of the compact staging tile inside the (idle) ring
+  int land_off;               // split-K: byte offset of the landing slots (dedicated shared memory behind the ring)
+  int ncols_max;              // split-K: float4 columns of the widest owner slice
   int act;
   float alpha;
   float* out;
   const float* bias;
-  float* partial;             // [splits][tiles][128][n_tile]
-  unsigned* counters;         // [tiles], zero on entry, left zero
   long long* dbg;             // optional timeline of CTA (0,0): see gg_debug_set_buffer
   int out_rows;               // wgrad: rows of the [taps*Ci, Co] result that exist in memory (im2col-padded K)
 };
 
+// ---- PTX wrappers on 32-bit shared-window addresses (computed once per kernel, not per instruction) -----------------
 __device__ __forceinline__ long long gtime() {
   long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t done, spins = 0;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (!done && ++spins > (1u << 24)) __trap();      // a mis-programmed pipeline traps instead of hanging the GPU box
+  } while (!done);
+}
+__device__ __forceinline__ void mbar_wait_cluster_a(uint32_t bar, uint32_t parity) {
+  uint32_t done, spins = 0;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (!done && ++spins > (1u << 24)) __trap();
+  } while (!done);
+}
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_a(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_a(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma_commit_a(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {   // every thread of every CTA of the cluster
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -67,32 +118,36 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
   return r;
 }
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t remote_bar_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar_addr) : "memory");
+// shared::cta -> shared::cluster bulk copy (the copy engine moves the slice; completion = bytes counted on the destination
+// CTA's mbarrier)
+__device__ __forceinline__ void bulk_s2c(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(bar_cluster) : "memory");
 }
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t done, spins = 0;
-  do {
-    asm volatile(
-        "{\n.reg .pred p;\n"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n}\n"
-        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    if (!done && ++spins > (1u << 24)) __trap();
-  } while (!done);
-}
-__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
-  return v;
-}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-// 1-D bulk copy global -> shared through the async proxy (copy engine), completion counted on an mbarrier
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+// 32 lanes x 16 consecutive fp32 columns (n_tile = 32: each of the two warps of a quadrant takes 16 columns)
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// shared-memory operand descriptor halves: lo = start address | leading byte offset, hi = stride byte offset | version | layout
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);
+}
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 
 #ifdef GG_TIMELINE
 #define GG_DBG(slot) do { if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0) p.dbg[slot] = gtime(); } while (0)
@@ -106,25 +161,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], accum_bar, cl_bar;
+  __shared__ uint32_t tmem_base_sh;
+  __shared__ long long s_row_off[128];                  // element offset of each accumulator row's output row (-1: masked)
+  __shared__ __align__(16) float s_bias[kMaxNTile];     // bias slice of this n-tile (fetched while the main loop runs)
+#ifdef GG_TIMELINE
   if (p.dbg && threadIdx.x == 0) {             // timeline (tools/timeline_conv.py): earliest CTA entry of the launch
     const long long t_in = gtime();
     atomicMin(reinterpret_cast<unsigned long long*>(p.dbg + 210), (unsigned long long)t_in);
     if (blockIdx.x == 0 && blockIdx.y == 0) p.dbg[211] = t_in;
   }
-  const int kStages = p.stages;
-  __shared__ uint32_t tmem_base_sh;
+#endif
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: the next kernel may start its own prologue now
-  __shared__ long long s_row_off[128];                  // element offset of each accumulator row's output row (-1: masked)
-  __shared__ __align__(16) float s_bias[kMaxNTile];   // bias slice of this n-tile (read from HBM/L2 once, before the accumulator is ready)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kStages = p.stages;
   const int stage_bytes = kABytes + p.n_tile * 128;
   const int cblocks = (MODE == 1 ? p.Co : p.Ci) / 32;       // 32-channel K blocks (fwd: ci, dgrad: co)
   const int taps = p.k * p.k;
+  const uint32_t ring = smem_u32(smem);
+  const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+  const uint32_t accum_a = smem_u32(&accum_bar), cl_a = smem_u32(&cl_bar);
 
   // ---- tile decode -------------------------------------------------------------------------------------
-  int tile = blockIdx.x;                 // over (class,) m-tile, n-tile
-  const int split = blockIdx.y;
+  const int tile = blockIdx.x;           // over (class,) m-tile, n-tile
+  const int split = blockIdx.y;          // = rank inside the cluster (cluster dims (1, splits, 1))
   const int nt = tile % p.n_tiles;
   int mt = tile / p.n_tiles;
   const int n0 = nt * p.n_tile;
@@ -160,7 +220,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kMaxStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&accum_bar, 1);
-    mbar_init(&cl_bar, (uint32_t)p.splits);      // cluster mode: one arrival per CTA of the tile
+    mbar_init(&cl_bar, 1);                       // split-K: this CTA's own arrive.expect_tx; peers only complete bytes
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -168,148 +228,149 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_cols = p.n_tile <= 32 ? 32 : (p.n_tile <= 64 ? 64 : 128);
   if (warp == 2) tmem_alloc(&tmem_base_sh, tmem_cols);
   tc_fence_before();
-  const bool cl = p.cluster != 0;
-  if (cl) cluster_sync_all();                  // peers must not signal cl_bar before it is initialised
+  const bool cl = p.splits > 1;
+  if (cl) cluster_sync_all();                    // peers must not signal cl_bar before it is initialised
   else __syncthreads();
   tc_fence_after();
-  // PDL: everything above (barrier init, tensor-map prefetch, TMEM allocation) is independent of the producer kernel; its
-  // activations / gradients are first touched below (TMA loads, bias read), so the dependency is resolved here.  A no-op
-  // for launches without a programmatic dependency.
+  // PDL: everything above is independent of the producer kernel; its activations / gradients are first touched below
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t tmem_d = tmem_base_sh;
   if (threadIdx.x == 0) GG_DBG(0);
+#ifdef GG_TIMELINE
   if (p.dbg && threadIdx.x == 0) atomicMin(reinterpret_cast<unsigned long long*>(p.dbg + 201), (unsigned long long)gtime());
+#endif
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
-    // Coordinates advance incrementally (no integer divisions in the issue loop: one elected lane issues every TMA of
-    // the CTA, so its instruction stream IS the load-issue rate); each operand stage is one TMA where the layout allows.
-    if (lane == 0) {
-      int c_cb = 0, c_s = 0, c_r = 0;          // fwd / dgrad: channel block, tap column, tap row (dgrad: class-local)
-      int px_w = 0, px_h = 0, px_b = 0;        // wgrad: pixel-block origin
-      int qa_c[4], qa_w[4], qa_h[4];           // wgrad: loop-invariant (ci block, tap offsets) of the 4 A boxes
-      if (MODE == 2) {
-        px_w = (kb0 % p.tw) * p.wt;
-        px_h = ((kb0 / p.tw) % p.th) * p.ht;
-        px_b = (kb0 / (p.tw * p.th)) * p.bt;
-        const int qblocks = p.Ci / 32;
+    // The whole warp walks the loop (warp-uniform control flow and coordinates); one elected lane issues.  Coordinates
+    // advance incrementally: no integer divisions in the issue loop.
+    int c_cb = 0, c_s = 0, c_r = 0;          // fwd / dgrad: channel block, tap column, tap row (dgrad: class-local)
+    int px_w = 0, px_h = 0, px_b = 0;        // wgrad: pixel-block origin
+    int qa_c[4], qa_w[4], qa_h[4];           // wgrad: loop-invariant (ci block, tap offsets) of the 4 A boxes
+    if (MODE == 2) {
+      px_w = (kb0 % p.tw) * p.wt;
+      px_h = ((kb0 / p.tw) % p.th) * p.ht;
+      px_b = (kb0 / (p.tw * p.th)) * p.bt;
+      const int qblocks = p.Ci / 32;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          int q = mt * 4 + j;
-          if (q >= taps * qblocks) q = taps * qblocks - 1;        // padded rows: valid data, masked at the store
-          const int tap = q / qblocks;
-          qa_c[j] = (q % qblocks) * 32;
-          qa_w[j] = tap % p.k - p.pad_l;
-          qa_h[j] = tap / p.k - p.pad_t;
-        }
-      } else {
-        const int t0 = kb0 / cblocks;
-        c_cb = kb0 % cblocks;
-        const int row_len = (MODE == 0) ? p.k : ns;
-        c_r = t0 / row_len;
-        c_s = t0 % row_len;
+      for (int j = 0; j < 4; ++j) {
+        int q = mt * 4 + j;
+        if (q >= taps * qblocks) q = taps * qblocks - 1;        // padded rows: valid data, masked at the store
+        const int tap = q / qblocks;
+        qa_c[j] = (q % qblocks) * 32;
+        qa_w[j] = tap % p.k - p.pad_l;
+        qa_h[j] = tap / p.k - p.pad_t;
       }
-      int s = 0;
-      uint32_t ph = 0;
-      for (int i = 0; i < nkb; ++i) {
-        mbar_wait(&empty_bar[s], ph ^ 1);            // a fresh barrier passes a parity-1 wait: first lap never blocks
-        uint8_t* sA = smem + s * stage_bytes;
-        uint8_t* sB = sA + kABytes;
+    } else {
+      const int t0 = kb0 / cblocks;
+      c_cb = kb0 % cblocks;
+      const int row_len = (MODE == 0) ? p.k : ns;
+      c_r = t0 / row_len;
+      c_s = t0 % row_len;
+    }
+    const int row_len = (MODE == 0) ? p.k : ns;
+    const int xw0 = (MODE == 0) ? w0 * p.stride - p.pad_l : w0 + d_w;
+    const int xh0 = (MODE == 0) ? h0 * p.stride - p.pad_t : h0 + d_h;
+    const bool leader = elect_one();
+    int s = 0;
+    uint32_t ph = 0;
+    for (int i = 0; i < nkb; ++i) {
+      mbar_wait_a(empty0 + 8u * s, ph ^ 1);           // a fresh barrier passes a parity-1 wait: first lap never blocks
+      if (leader) {
+        const uint32_t sA = ring + (uint32_t)(s * stage_bytes), sB = sA + kABytes, fb = full0 + 8u * s;
         if (i < 60) GG_DBG(1 + i);
-        mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+        mbar_expect_tx_a(fb, (uint32_t)stage_bytes);
         if (MODE == 0) {
-          tma_load_4d(sA, &tmA, &full_bar[s], c_cb * 32, w0 * p.stride + c_s - p.pad_l, h0 * p.stride + c_r - p.pad_t, b0);
-          tma_load_4d(sB, &tmB, &full_bar[s], 0, c_cb * 32, n0 / 32, c_r * p.k + c_s);
+          tma_load_4d_a(sA, &tmA, fb, c_cb * 32, xw0 + c_s, xh0 + c_r, b0);
+          tma_load_4d_a(sB, &tmB, fb, 0, c_cb * 32, n0 / 32, c_r * p.k + c_s);
         } else if (MODE == 1) {
-          tma_load_4d(sA, &tmA, &full_bar[s], c_cb * 32, w0 + d_w - c_s, h0 + d_h - c_r, b0);
-          tma_load_3d(sB, &tmB, &full_bar[s], c_cb * 32, n0, (a_h + p.stride * c_r) * p.k + a_w + p.stride * c_s);
+          tma_load_4d_a(sA, &tmA, fb, c_cb * 32, xw0 - c_s, xh0 - c_r, b0);
+          tma_load_3d_a(sB, &tmB, fb, c_cb * 32, n0, (a_h + p.stride * c_r) * p.k + a_w + p.stride * c_s);
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            tma_load_4d(sA + j * 4096, &tmA, &full_bar[s], qa_c[j], px_w * p.stride + qa_w[j], px_h * p.stride + qa_h[j], px_b);
-          tma_load_3d(sB, &tmB, &full_bar[s], 0, (kb0 + i) * 32, n0 / 32);
+            tma_load_4d_a(sA + j * 4096, &tmA, fb, qa_c[j], px_w * p.stride + qa_w[j], px_h * p.stride + qa_h[j], px_b);
+          tma_load_3d_a(sB, &tmB, fb, 0, (kb0 + i) * 32, n0 / 32);
         }
-        if (MODE == 2) {
-          px_w += p.wt;
-          if (px_w == p.PW) { px_w = 0; px_h += p.ht; if (px_h == p.PH) { px_h = 0; px_b += p.bt; } }
-        } else {
-          if (++c_cb == cblocks) {
-            c_cb = 0;
-            const int row_len = (MODE == 0) ? p.k : ns;
-            if (++c_s == row_len) { c_s = 0; ++c_r; }
-          }
-        }
-        if (++s == kStages) { s = 0; ph ^= 1; }
       }
+      if (MODE == 2) {
+        px_w += p.wt;
+        if (px_w == p.PW) { px_w = 0; px_h += p.ht; if (px_h == p.PH) { px_h = 0; px_b += p.bt; } }
+      } else {
+        if (++c_cb == cblocks) {
+          c_cb = 0;
+          if (++c_s == row_len) { c_s = 0; ++c_r; }
+        }
+      }
+      if (++s == kStages) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      constexpr int a_mn = (MODE == 2) ? 1 : 0;
-      constexpr int b_mn = (MODE == 1) ? 0 : 1;
-      const uint32_t idesc = make_idesc_tf32(128, p.n_tile, a_mn, b_mn);
-      int s = 0;
-      uint32_t ph = 0;
-      for (int i = 0; i < nkb; ++i) {
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
+    constexpr int a_mn = (MODE == 2) ? 1 : 0;
+    constexpr int b_mn = (MODE == 1) ? 0 : 1;
+    const uint32_t idesc = make_idesc_tf32(128, p.n_tile, a_mn, b_mn);
+    // K-major operand: 128B swizzle, LBO 16 B (unused), SBO 1024 B, k-step = +32 B inside the swizzle atom
+    // MN-major operand: 128B swizzle with 32-byte atoms, LBO 4096 B (next 32-wide MN block), SBO 512 B, k-step = +1024 B
+    const uint32_t a_hi = a_mn ? desc_hi(512, kLayoutSW128_32B) : desc_hi(1024, kLayoutSW128);
+    const uint32_t b_hi = b_mn ? desc_hi(512, kLayoutSW128_32B) : desc_hi(1024, kLayoutSW128);
+    const uint32_t a_lbo = a_mn ? 4096u : 16u, b_lbo = b_mn ? 4096u : 16u;
+    const uint32_t a_step = a_mn ? (1024u >> 4) : (32u >> 4), b_step = b_mn ? (1024u >> 4) : (32u >> 4);
+    const bool leader = elect_one();
+    int s = 0;
+    uint32_t ph = 0;
+    for (int i = 0; i < nkb; ++i) {
+      mbar_wait_a(full0 + 8u * s, ph);
+      tc_fence_after();
+      if (leader) {
         if (i < 60) GG_DBG(64 + i);
-        const uint32_t aBase = smem_u32(smem + s * stage_bytes);
-        const uint32_t bBase = aBase + kABytes;
+        const uint32_t aBase = ring + (uint32_t)(s * stage_bytes);
+        uint32_t a_lo = desc_lo(aBase, a_lbo), b_lo = desc_lo(aBase + kABytes, b_lbo);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const uint64_t ad = a_mn ? make_smem_desc(aBase + j * 1024, 4096, 512, kLayoutSW128_32B)
-                                   : make_smem_desc(aBase + j * 32, 16, 1024, kLayoutSW128);
-          const uint64_t bd = b_mn ? make_smem_desc(bBase + j * 1024, 4096, 512, kLayoutSW128_32B)
-                                   : make_smem_desc(bBase + j * 32, 16, 1024, kLayoutSW128);
-          umma_tf32(tmem_d, ad, bd, idesc, (i | j) != 0);
+          umma_tf32(tmem_d, desc64(a_lo, a_hi), desc64(b_lo, b_hi), idesc, (i | j) != 0);
+          a_lo += a_step;
+          b_lo += b_step;
         }
-        umma_commit(&empty_bar[s]);          // frees the smem stage once these MMAs have read it
-        if (++s == kStages) { s = 0; ph ^= 1; }
+        umma_commit_a(empty0 + 8u * s);       // frees the smem stage once these MMAs have read it
       }
-      umma_commit(&accum_bar);               // accumulator complete
+      if (++s == kStages) { s = 0; ph ^= 1; }
     }
+    if (leader) umma_commit_a(accum_a);       // accumulator complete
   } else {
-    // =========================== epilogue (warps 2..5) ===========================
+    // =========================== epilogue (warps 2..9) ===========================
+    const int et = threadIdx.x - 64;              // 0..255
     const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;             // which half of the tile's columns this warp reads out of TMEM
     const int m = quad * 32 + lane;               // accumulator row
-    const int et = threadIdx.x - 64;              // 0..127
-    // While the main loop runs these warps are idle: fetch the bias slice now.  (Loading it from global memory inside the
-    // read-out loop cost one exposed L2 round trip per 32-column chunk — the tcgen05.ld asm is a compiler barrier —
-    // ~2 us of a ~3.4 us epilogue on the timeline.)
+    const int hcols = p.n_tile >> 1;              // 64 / 32 / 16 columns per warp
+    const int cw0 = half * hcols;
+    // While the main loop runs these warps are idle: fetch the bias slice and the output-row table now.
     const bool has_bias = (MODE != 2) && p.bias != nullptr;
-    if (has_bias && et < p.n_tile) s_bias[et] = p.bias[nt * p.n_tile + et];
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    mbar_wait(&accum_bar, 0);
+    if (has_bias && et < p.n_tile) s_bias[et] = p.bias[n0 + et];
+    if (half == 0) {
+      bool valid;
+      long long off;
+      if (MODE == 0) {
+        const int wi = m % p.wt, hi = (m / p.wt) % p.ht, bi = m / (p.wt * p.ht);
+        valid = (b0 + bi) < p.B;
+        off = ((long long)(((long long)(b0 + bi) * p.Ho + h0 + hi) * p.Wo + w0 + wi)) * p.Co + n0;
+      } else if (MODE == 1) {
+        const int wi = m % p.wt, hi = (m / p.wt) % p.ht, bi = m / (p.wt * p.ht);
+        const int hh = (h0 + hi) * p.stride + e_h, ww = (w0 + wi) * p.stride + e_w;
+        valid = (b0 + bi) < p.B && hh < p.H && ww < p.W;
+        off = ((long long)(((long long)(b0 + bi) * p.H + hh) * p.W + ww)) * p.Ci + n0;
+      } else {
+        const int row = mt * 128 + m;
+        valid = row < p.out_rows;
+        off = (long long)row * p.Co + n0;
+      }
+      s_row_off[m] = valid ? off : -1;
+    }
+    epi_bar();
+    mbar_wait_a(accum_a, 0);
     tc_fence_after();
     if (et == 0) GG_DBG(128);
-    bool valid;
-    float* orow;
-    if (MODE == 0) {
-      const int wi = m % p.wt, hi = (m / p.wt) % p.ht, bi = m / (p.wt * p.ht);
-      valid = (b0 + bi) < p.B;
-      orow = p.out + ((size_t)(((size_t)(b0 + bi) * p.Ho + h0 + hi) * p.Wo + w0 + wi)) * p.Co + n0;
-    } else if (MODE == 1) {
-      const int wi = m % p.wt, hi = (m / p.wt) % p.ht, bi = m / (p.wt * p.ht);
-      const int hh = (h0 + hi) * p.stride + e_h, ww = (w0 + wi) * p.stride + e_w;
-      valid = (b0 + bi) < p.B && hh < p.H && ww < p.W;
-      orow = p.out + ((size_t)(((size_t)(b0 + bi) * p.H + hh) * p.W + ww)) * p.Ci + n0;
-    } else {
-      const int row = mt * 128 + m;
-      valid = row < p.out_rows;
-      orow = p.out + (size_t)row * p.Co + n0;
-    }
     const uint32_t taddr = tmem_d + ((uint32_t)(quad * 32) << 16);
-    // The operand ring is idle once accum_bar has fired: reuse it as a [128][n_tile+4] staging tile so that the final
-    // global stores are row-coalesced (a warp writes one whole output row per instruction).
-    // (cluster mode keeps this CTA's partial tile in the first 64 KB for its peers to read; staging goes behind it)
-    const int stage_off = cl ? 128 * p.n_tile * 4 : 0;
-    float* stage_tile = reinterpret_cast<float*>(smem + stage_off);
-    long long* row_off = s_row_off;
-    int ld = p.n_tile + 4;                        // staging row pitch (floats)
-    int col0 = 0;                                 // float4 column of the tile held in staging column 0
-    row_off[m] = valid ? (long long)(orow - p.out) : -1;
-    bool do_store = true;
     // activation / bias parameters hoisted into registers: none / relu / leaky are max(a*v, v) with a = 1 / 0 / alpha
     const float a_eff = act_slope(p.act, p.alpha);
     const bool slow_act = (MODE != 2) && p.act >= GG_ACT_TANH;
@@ -330,195 +391,111 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }                                                                                         \
       }                                                                                           \
     } while (0)
-    int cbeg = 0, cend = p.n_tile / 4;          // float4 column range of the tile this CTA writes out
-    if (p.splits == 1) {
-      for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
-        float v[32];
-        tmem_ld_32x32(taddr + (uint32_t)c0, v);
+    // The operand ring is idle once accum_bar has fired: it becomes the staging area of the epilogue.
+    float* stage_tile;
+    int ld;                                       // staging row pitch (floats)
+    int cbeg = 0, cend = p.n_tile / 4;            // float4 column range of the tile this CTA writes out
+    if (!cl) {
+      // un-split: TMEM -> registers -> bias + activation -> [128][n_tile+4] staging tile
+      stage_tile = reinterpret_cast<float*>(smem);
+      ld = p.n_tile + 4;
+      if (hcols >= 32) {
+        for (int c0 = cw0; c0 < cw0 + hcols; c0 += 32) {
+          float v[32];
+          tmem_ld_32x32(taddr + (uint32_t)c0, v);
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
+          for (int i = 0; i < 32; i += 4) {
+            float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            GG_FINISH4(o, c0 + i);
+            *reinterpret_cast<float4*>(stage_tile + m * ld + c0 + i) = o;
+          }
+        }
+      } else {
+        float v[16];
+        tmem_ld_32x16(taddr + (uint32_t)cw0, v);
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
           float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-          GG_FINISH4(o, c0 + i);
-          *reinterpret_cast<float4*>(stage_tile + m * ld + c0 + i) = o;
-        }
-      }
-    } else if (cl) {
-      // split-K inside a thread-block cluster: each CTA parks its partial tile in its OWN shared memory ([n_tile/4][128]
-      // float4), signals every peer's mbarrier, and then sums its column slice straight out of the peers' shared memory
-      // (DSMEM) in split order — no global round trip, no atomics, no cooperative launch.
-      float4* ptile = reinterpret_cast<float4*>(smem);
-      for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
-        float v[32];
-        if (nkb > 0) tmem_ld_32x32(taddr + (uint32_t)c0, v);
-        else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = 0.f;
-        }
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) ptile[((c0 + i) >> 2) * 128 + m] = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-      }
-      asm volatile("fence.acq_rel.cluster;" ::: "memory");
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (et < p.splits) mbar_arrive_remote(map_to_cta(smem_u32(&cl_bar), (uint32_t)et));
-      mbar_wait_cluster(&cl_bar, 0);
-      const int nc = p.n_tile / 4;
-      cbeg = (split * nc) / p.splits;
-      cend = ((split + 1) * nc) / p.splits;
-      const uint32_t my_ptile = smem_u32(ptile);
-      for (int c4 = cbeg; c4 < cend; c4 += 4) {
-        float4 acc[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int sp = 0; sp < p.splits; sp += 2) {
-          float4 t[2][4];
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const uint32_t peer = map_to_cta(my_ptile, (uint32_t)min(sp + q, p.splits - 1));
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              t[q][u] = (sp + q < p.splits && c4 + u < cend) ? ld_dsmem_f4(peer + (uint32_t)(((c4 + u) * 128 + m) * 16))
-                                                             : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-#pragma unroll
-          for (int q = 0; q < 2; ++q)
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              acc[u].x += t[q][u].x; acc[u].y += t[q][u].y; acc[u].z += t[q][u].z; acc[u].w += t[q][u].w;
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (c4 + u < cend) {
-            float4 o = acc[u];
-            GG_FINISH4(o, (c4 + u) * 4);
-            *reinterpret_cast<float4*>(stage_tile + m * ld + (c4 + u) * 4) = o;
-          }
+          GG_FINISH4(o, cw0 + i);
+          *reinterpret_cast<float4*>(stage_tile + m * ld + cw0 + i) = o;
         }
       }
     } else {
-      // split-K: park the partial tile in the (L2-resident) workspace in a [n_tile/4][128 rows] float4 layout (coalesced
-      // for the thread-per-row TMEM readout); the last CTA to take a ticket on this tile sums the splits in split order.
-      const size_t tile_elems = (size_t)128 * p.n_tile;
-      const size_t ntiles_all = gridDim.x;
-      float4* pme = reinterpret_cast<float4*>(p.partial + ((size_t)split * ntiles_all + blockIdx.x) * tile_elems) + m;
-      for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
-        float v[32];
-        if (nkb > 0) tmem_ld_32x32(taddr + (uint32_t)c0, v);
+      // ---- split-K inside the cluster -------------------------------------------------------------------
+      // 1. park this CTA's partial tile in its own shared memory as [n_tile/4][128 rows] float4 (conflict-free for the
+      //    thread-per-row TMEM read-out; an owner's column slice is one contiguous block)
+      float4* ptile = reinterpret_cast<float4*>(smem);
+      if (hcols >= 32) {
+        for (int c0 = cw0; c0 < cw0 + hcols; c0 += 32) {
+          float v[32];
+          if (nkb > 0) tmem_ld_32x32(taddr + (uint32_t)c0, v);
+          else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) ptile[((c0 + i) >> 2) * 128 + m] = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+      } else {
+        float v[16];
+        if (nkb > 0) tmem_ld_32x16(taddr + (uint32_t)cw0, v);
         else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          for (int i = 0; i < 16; ++i) v[i] = 0.f;
         }
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) pme[(size_t)((c0 + i) >> 2) * 128] = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        for (int i = 0; i < 16; i += 4) ptile[((cw0 + i) >> 2) * 128 + m] = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
       }
-      if (et == 0) GG_DBG(129);
-      // All `splits` CTAs of this tile are co-resident (cooperative launch, grid <= #SMs): rendezvous on a ticket, then
-      // EVERY CTA reduces its own 1/splits column slice of the tile (summing the splits in split order: deterministic)
-      // instead of one CTA serially re-reading all partials — the reduction's L2 round trips run on `splits` SMs at once.
-      __threadfence();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (et == 0) {
-        // arrival needs no return value: a reduction (fire and forget) instead of an atomic round trip before the poll
-        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.counters + blockIdx.x) : "memory");
-        unsigned seen;
-        unsigned spins = 0;
-        do {
-          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.counters + blockIdx.x) : "memory");
-          if (seen < (unsigned)p.splits) { __nanosleep(32); if (++spins > (1u << 22)) __trap(); }
-        } while (seen < (unsigned)p.splits);
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (et == 0) GG_DBG(212);
+      fence_proxy_async();                        // generic-proxy writes -> visible to the copy engine
+      epi_bar();
       const int nc = p.n_tile / 4;
       cbeg = (split * nc) / p.splits;
       cend = ((split + 1) * nc) / p.splits;
-      if (p.bulk) {
-        // The slice [cbeg, cend) x 128 rows of one split's partial tile is CONTIGUOUS in the [n_tile/4][128] float4 layout:
-        // one elected thread asks the copy engine for the `splits` slices (cp.async.bulk -> the idle operand ring) and
-        // the 128 epilogue threads then sum them out of shared memory in split order.  Replaces two dependent rounds of
-        // 16 L2 loads per thread (2.8 us on the timeline) by one bulk transfer of <= 64 KB.
-        const int ncols = cend - cbeg;
-        const int ncols_max = (nc + p.splits - 1) / p.splits;
-        const uint32_t chunk = (uint32_t)ncols * 2048u;
-        if (ncols > 0) {
-          if (et == 0) {
-            fence_proxy_async_all();               // partials were written through the generic proxy (by other CTAs)
-            mbar_expect_tx(&accum_bar, chunk * (uint32_t)p.splits);
-            const uint8_t* src0 = reinterpret_cast<const uint8_t*>(p.partial + (size_t)blockIdx.x * tile_elems) + (size_t)cbeg * 2048;
-            const size_t split_stride_bytes = ntiles_all * tile_elems * sizeof(float);
-            for (int sp = 0; sp < p.splits; ++sp) bulk_g2s(smem + (size_t)sp * chunk, src0 + (size_t)sp * split_stride_bytes, chunk, &accum_bar);
-          }
-          mbar_wait(&accum_bar, 1);
-        }
-        stage_tile = reinterpret_cast<float*>(smem + (size_t)p.splits * ncols_max * 2048);
-        ld = ncols * 4 + 4;
-        col0 = cbeg;
-        const float4* land = reinterpret_cast<const float4*>(smem) + m;
-        for (int c = 0; c < ncols; ++c) {
-          float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-          for (int sp = 0; sp < p.splits; ++sp) {
-            const float4 t = land[((size_t)sp * ncols + c) * 128];
-            o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
-          }
-          GG_FINISH4(o, (cbeg + c) * 4);
-          *reinterpret_cast<float4*>(stage_tile + m * ld + c * 4) = o;
-        }
-      } else {
-        const float4* pbase = reinterpret_cast<const float4*>(p.partial + (size_t)blockIdx.x * tile_elems) + m;
-        const size_t split_stride4 = ntiles_all * tile_elems / 4;
-        // up to 16 independent L2 loads in flight per thread (4 column groups x 4 splits)
-        for (int c4 = cbeg; c4 < cend; c4 += 4) {
-          float4 acc[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int sp = 0; sp < p.splits; sp += 4) {
-            float4 t[4][4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-#pragma unroll
-              for (int u = 0; u < 4; ++u)
-                t[q][u] = (sp + q < p.splits && c4 + u < cend)
-                              ? __ldcg(pbase + (size_t)(sp + q) * split_stride4 + (size_t)(c4 + u) * 128)
-                              : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                acc[u].x += t[q][u].x; acc[u].y += t[q][u].y; acc[u].z += t[q][u].z; acc[u].w += t[q][u].w;
-              }
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (c4 + u < cend) {
-              float4 o = acc[u];
-              GG_FINISH4(o, (c4 + u) * 4);
-              *reinterpret_cast<float4*>(stage_tile + m * ld + (c4 + u) * 4) = o;
-            }
-          }
-        }
-      }
-      // second ticket: the last CTA to finish reading the partials re-arms both counters for the next launch
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int ncols = cend - cbeg;
+      const uint32_t slot_bytes = (uint32_t)p.ncols_max * 2048u;
+      // 2. one elected thread: expect the peers' slices, push every peer ITS slice of this partial
       if (et == 0) {
-        const unsigned old = atomicAdd(&p.counters[gridDim.x + blockIdx.x], 1u);
-        if (old == (unsigned)(p.splits - 1)) { p.counters[blockIdx.x] = 0u; p.counters[gridDim.x + blockIdx.x] = 0u; }
+        mbar_expect_tx_a(cl_a, (uint32_t)(p.splits - 1) * (uint32_t)ncols * 2048u);
+        for (int j = 0; j < p.splits; ++j) {
+          if (j == split) continue;
+          const int cb = (j * nc) / p.splits, ce = ((j + 1) * nc) / p.splits;
+          const int slot = split < j ? split : split - 1;             // slot of source `split` at owner j
+          const uint32_t dst = map_to_cta(ring + (uint32_t)p.land_off + (uint32_t)slot * slot_bytes, (uint32_t)j);
+          bulk_s2c(dst, ring + (uint32_t)cb * 2048u, (uint32_t)(ce - cb) * 2048u, map_to_cta(cl_a, (uint32_t)j));
+        }
+        GG_DBG(129);
+      }
+      // 3. wait for the (splits-1) incoming slices, then reduce the own slice in split order (deterministic)
+      mbar_wait_cluster_a(cl_a, 0);
+      if (et == 0) GG_DBG(212);
+      stage_tile = reinterpret_cast<float*>(smem + p.stage_off);
+      ld = ncols * 4 + 4;
+      const float4* land = reinterpret_cast<const float4*>(smem + p.land_off);
+      const int slot4 = p.ncols_max * 128;        // float4 per landing slot
+      for (int idx = et; idx < ncols * 128; idx += kEpiThreads) {
+        const int c = idx >> 7, row = idx & 127;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int sp = 0; sp < p.splits; ++sp) {
+          const float4 t = (sp == split) ? ptile[(cbeg + c) * 128 + row]
+                                         : land[(sp < split ? sp : sp - 1) * slot4 + c * 128 + row];
+          o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+        }
+        GG_FINISH4(o, (cbeg + c) * 4);
+        *reinterpret_cast<float4*>(stage_tile + row * ld + c * 4) = o;
       }
     }
 #undef GG_FINISH4
-    (void)do_store;
+    if (p.dbg && et == 0) p.dbg[140] = gtime();
+    epi_bar();
+    // coalesced write-out of columns [cbeg, cend): `ncol` consecutive threads take the consecutive float4 of one row
+    // (a warp stores whole 128..512-byte row segments)
     {
-      if (p.dbg && et == 0) p.dbg[140] = gtime();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (p.dbg && et == 0) p.dbg[141] = gtime();
-      // coalesced write-out of columns [cbeg, cend): `ncol` consecutive threads take the consecutive float4 of one row
-      // (a warp stores whole 128..512-byte row segments); the row/column split is computed once, not per element
       const int ncol = cend - cbeg;
       if (ncol > 0) {
-        const int rpp = 128 / ncol;                 // rows per pass of the 128 threads
+        const int rpp = kEpiThreads / ncol;         // rows per pass of the 256 threads
         const int my_c = et % ncol, my_r = et / ncol;
         if (my_r < rpp) {
-          const float* sp_ = stage_tile + (cbeg - col0 + my_c) * 4;
+          const float* sp_ = stage_tile + my_c * 4;
           float* gp_ = p.out + (size_t)(cbeg + my_c) * 4;
           for (int r = my_r; r < 128; r += 4 * rpp) {
             float4 val[4];
@@ -526,7 +503,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const int rr = r + u * rpp;
-              off[u] = rr < 128 ? row_off[rr] : -1;
+              off[u] = rr < 128 ? s_row_off[rr] : -1;
               val[u] = *reinterpret_cast<const float4*>(sp_ + (rr < 128 ? rr : 0) * ld);
             }
 #pragma unroll
@@ -539,11 +516,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   }
   if (threadIdx.x == 64) GG_DBG(131);
+#ifdef GG_TIMELINE
   if (p.dbg && threadIdx.x == 64) atomicMax(reinterpret_cast<unsigned long long*>(p.dbg + 200), (unsigned long long)gtime());
+#endif
   // ---- teardown -----------------------------------------------------------------------------------------
   tc_fence_before();
   __syncwarp();
-  if (cl) cluster_sync_all();                  // no CTA may exit (and free its shared memory) while a peer still reads it
+  if (cl) cluster_sync_all();                  // no CTA may exit (and free its shared memory) while a peer's copy still reads it
   else __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_d, tmem_cols);
 }
@@ -592,8 +571,7 @@ int pick_splits(int tiles, int kb_min) {
   int cap = kb_min / 3;                      // keep >= 3 k-blocks per CTA so the pipeline fills
   if (cap < 1) cap = 1;
   if (s > cap) s = cap;
-  static int use_cluster = env_int("GG_TC_CLUSTER", 0);
-  if (s > (use_cluster ? 8 : 16)) s = use_cluster ? 8 : 16;   // 8 = portable thread-block-cluster size
+  if (s > kMaxSplits) s = kMaxSplits;        // the K splits of a tile form one thread-block cluster (portable size 8)
   if (s < 1) s = 1;
   return s;
 }
@@ -605,7 +583,6 @@ struct TcPlan {
   bool ok;
   TcParams p;
   int grid_x;
-  size_t partial_bytes, counter_bytes;
 };
 
 bool env_disable_tc() {
@@ -662,97 +639,119 @@ TcPlan make_plan(int mode, int B, int H, int W, int Ci, int Co, int k, int strid
   }
   if (p.wt * stride > 256 || p.ht * stride > 256) return pl;
   p.splits = pick_splits(pl.grid_x, kb_min);
-  pl.partial_bytes = p.splits > 1 ? (size_t)p.splits * pl.grid_x * 128 * p.n_tile * sizeof(float) : 0;
-  pl.counter_bytes = ((size_t)2 * pl.grid_x * sizeof(unsigned) + 255) & ~size_t(255);   // arrival + completion tickets
+  if (p.splits > p.n_tile / 4) p.splits = p.n_tile / 4;      // every split owns at least one float4 column of the tile
   pl.ok = true;
   return pl;
 }
 
-size_t plan_workspace(const TcPlan& pl) { return pl.ok ? pl.counter_bytes + pl.partial_bytes : 0; }
+// split-K needs no global workspace any more (partials travel through distributed shared memory); the C-ABI keeps its
+// workspace arguments for the direct / im2col paths
+size_t plan_workspace(const TcPlan& pl) { return pl.ok ? 256 : 0; }
+
+// shared-memory layout of a launch: operand ring (doubling as partial tile + staging tile in the epilogue) and, for
+// split-K, the landing slots behind it
+size_t smem_layout(TcParams& p) {
+  const size_t stage_bytes = kABytes + (size_t)p.n_tile * 128;
+  size_t ring = (size_t)p.stages * stage_bytes;
+  const size_t tile = (size_t)128 * p.n_tile * 4;
+  if (p.splits == 1) {
+    const size_t staging = (size_t)128 * (p.n_tile + 4) * 4;
+    if (ring < staging) ring = staging;
+    p.stage_off = 0; p.land_off = 0; p.ncols_max = 0;
+    return ring + 1024;
+  }
+  const int nc = p.n_tile / 4;
+  p.ncols_max = (nc + p.splits - 1) / p.splits;
+  const size_t staging = (size_t)128 * (p.ncols_max * 4 + 4) * 4;
+  if (ring < tile + staging) ring = tile + staging;
+  ring = (ring + 1023) & ~size_t(1023);
+  p.stage_off = (int)tile;
+  p.land_off = (int)ring;
+  return ring + (size_t)(p.splits - 1) * p.ncols_max * 2048 + 1024;
+}
+
+// how many clusters of `splits` CTAs with `smem` bytes each can be resident at once (cached: one driver query per shape)
+template <int MODE>
+int max_active_clusters(int splits, size_t smem) {
+  static std::map<std::pair<int, size_t>, int> cache;
+  auto key = std::make_pair(splits, smem);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(kNumSMs, splits);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = (unsigned)splits;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  cudaError_t e = cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<MODE>, &cfg);
+  if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
+  cache[key] = n;
+  return n;
+}
 
 template <int MODE>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, TcPlan& pl, void* ws, size_t ws_bytes, cudaStream_t st) {
   TcParams& p = pl.p;
-  if (p.splits > 1 && (ws == nullptr || ws_bytes < plan_workspace(pl))) {
-    // not enough workspace for split-K: run unsplit (slower, still correct)
-    p.splits = 1;
-  }
-  p.counters = reinterpret_cast<unsigned*>(ws);
+  (void)ws; (void)ws_bytes;
   p.dbg = g_dbg;
-  p.partial = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + pl.counter_bytes);
+  static bool attr_set[3] = {false, false, false};
+  if (!attr_set[MODE]) {
+    // opt-in limit is 227 KB per block INCLUDING the kernel's static shared memory (barriers, row table, bias: ~3 KB)
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+    if (e != cudaSuccess) return fail(GG_ERR_CUDA_BASE + (int)e, "conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    attr_set[MODE] = true;
+  }
   p.stages = kMaxStages;
   if ((long long)pl.grid_x * p.splits > kNumSMs) {
     // more CTAs than SMs: keep the footprint under half an SM so two CTAs co-reside and one's epilogue overlaps the
     // other's main loop
-    int fit = (int)((113 * 1024 - 1024) / (kABytes + p.n_tile * 128));
+    int fit = (int)((113 * 1024 - 4096) / (kABytes + p.n_tile * 128));
     p.stages = fit < 3 ? 3 : (fit > kMaxStages ? kMaxStages : fit);
   }
-  // ring-depth cap (gg_set_tc_stages): 3 stages = 97 KB, so two CTAs — of the same or of two concurrent launches on
-  // different streams — share an SM; the main loop is TMA-issue-bound, not latency-bound, and loses nothing
+  // ring-depth cap (gg_set_tc_stages): 3 stages = 97 KB, so two un-split CTAs — of the same or of two concurrent launches
+  // on different streams — share an SM
   if (g_tc_stage_cap >= 2 && g_tc_stage_cap < p.stages) p.stages = g_tc_stage_cap;
-  // Thread-block-cluster / DSMEM reduction (GG_TC_CLUSTER=1): correct (same tests pass) but measured no faster than the
-  // L2 workspace rendezvous on B200 (E.2 fwd 13.7 vs 14.2 us, E.3 fwd 26 vs 13 us: 8-CTA clusters of 197 KB CTAs place
-  // badly on 16-20-SM GPCs), so it is off by default.
-  p.cluster = (p.splits > 1 && p.splits <= 8 && env_int("GG_TC_CLUSTER", 0) != 0) ? 1 : 0;
-  if (p.cluster) p.stages = kMaxStages;        // the cluster epilogue parks a partial tile AND a staging tile in the ring
-  // the epilogue re-uses the ring as a [128][n_tile+4] staging tile; split-K with the bulk-copy reduction lands the
-  // `splits` slices ([splits][ncols][128] float4, <= 64 KB + rounding) in front of a compact [128][4*ncols+4] staging tile
-  // (GG_TC_BULK=1, opt-in: measured SLOWER than the per-thread L2 loads on B200 — rendezvous -> staged 3.7 us vs 2.8 us for
-  // the E.2 forward conv, profiles/timeline_conv_r1.txt — the 1-D bulk copies of 16 KB slices do not beat 16 loads in flight
-  // per thread here; kept as a documented negative result.)
-  p.bulk = (p.splits > 1 && !p.cluster && env_int("GG_TC_BULK", 0) != 0) ? 1 : 0;
-  size_t ring = (size_t)p.stages * (kABytes + p.n_tile * 128);
-  size_t staging = (size_t)128 * (p.n_tile + 4) * 4;
-  if (p.bulk) {
-    const int nc = p.n_tile / 4, ncols_max = (nc + p.splits - 1) / p.splits;
-    staging = (size_t)p.splits * ncols_max * 2048 + (size_t)128 * (ncols_max * 4 + 4) * 4;
-  }
-  if (ring < staging) ring = staging;
-  const size_t smem = ring + 1024;
-  static bool attr_set[3] = {false, false, false};
-  if (!attr_set[MODE]) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kMaxStages * (kABytes + kMaxNTile * 128) + 1024);
-    if (e != cudaSuccess) return fail(GG_ERR_CUDA_BASE + (int)e, "conv_tc: cudaFuncSetAttribute failed%s");
-    attr_set[MODE] = true;
+  if (p.splits > 1 && p.stages > kClusterStages) p.stages = kClusterStages;
+  size_t smem = smem_layout(p);
+  if (smem > (size_t)kMaxDynSmem) return fail(GG_ERR_BAD_ARG, "conv_tc: shared-memory layout%s of %lld bytes exceeds the limit", "", (long long)smem);
+  // the K splits of a tile are one cluster: shrink the split count until every tile's cluster is resident at once (a second
+  // wave of clusters would serialise the launch)
+  while (p.splits > 1 && max_active_clusters<MODE>(p.splits, smem) < pl.grid_x) {
+    --p.splits;
+    smem = smem_layout(p);
   }
   dim3 grid(pl.grid_x, p.splits);
   g_last_info[0] = MODE; g_last_info[1] = pl.grid_x; g_last_info[2] = p.splits; g_last_info[3] = p.n_tile;
-  g_last_info[4] = p.stages; g_last_info[5] = p.cluster; g_last_info[6] = (int)smem; g_last_info[7] = p.m_tiles;
-  if (p.cluster) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid;
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 1;
-    attr[0].val.clusterDim.y = (unsigned)p.splits;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<MODE>, tmA, tmB, p);
-    if (e != cudaSuccess) { cudaGetLastError(); return fail(GG_ERR_CUDA_BASE + (int)e, "conv_tc: cluster launch failed: %s", cudaGetErrorString(e)); }
-  } else if (p.splits > 1) {
-    // the split-K rendezvous spins on a ticket: all CTAs of the grid must be co-resident -> cooperative launch
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid;
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeCooperative;
-    attr[0].val.cooperative = 1;
-    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = (g_pdl && env_int("GG_PDL_COOP", 0) != 0) ? 2 : 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<MODE>, tmA, tmB, p);
-    if (e != cudaSuccess) { cudaGetLastError(); return fail(GG_ERR_CUDA_BASE + (int)e, "conv_tc: cooperative launch failed: %s", cudaGetErrorString(e)); }
-  } else {
-    GG_LAUNCH((conv_tc_kernel<MODE>), grid, kThreads, smem, st, tmA, tmB, p);
+  g_last_info[4] = p.stages; g_last_info[5] = p.splits > 1 ? 1 : 0; g_last_info[6] = (int)smem; g_last_info[7] = p.m_tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (p.splits > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 1;
+    attr[na].val.clusterDim.y = (unsigned)p.splits;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
   }
+  if (g_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<MODE>, tmA, tmB, p);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(GG_ERR_CUDA_BASE + (int)e, "conv_tc: launch failed: %s", cudaGetErrorString(e)); }
   return check_launch(MODE == 0 ? "gg_conv2d_fwd(tcgen05)" : (MODE == 1 ? "gg_conv2d_dgrad(tcgen05)" : "gg_conv2d_wgrad(tcgen05)"));
 }
 
@@ -790,7 +789,6 @@ int conv_tc_fwd(const float* x, const float* w, const float* bias, float* y, int
   *handled = false;
   TcPlan pl = make_plan(0, B, H, W, Ci, Co, k, stride, pad_t, pad_l, Ho, Wo);
   if (!pl.ok) return GG_OK;
-  if (ws == nullptr || ws_bytes < pl.counter_bytes) return GG_OK;     // needs at least the ticket area
   CUtensorMap tmA, tmB;
   int rc = act_map(&tmA, x, B, H, W, Ci, pl.p.wt, pl.p.ht, pl.p.bt, stride, 1);
   if (rc) return rc;
@@ -809,7 +807,6 @@ int conv_tc_dgrad(const float* dy, const float* w, const float* bias, float* dx,
   *handled = false;
   TcPlan pl = make_plan(1, B, H, W, Ci, Co, k, stride, pad_t, pad_l, Ho, Wo);
   if (!pl.ok) return GG_OK;
-  if (ws == nullptr || ws_bytes < pl.counter_bytes) return GG_OK;
   CUtensorMap tmA, tmB;
   int rc = act_map(&tmA, dy, B, Ho, Wo, Co, pl.p.wt, pl.p.ht, pl.p.bt, 1, 1);
   if (rc) return rc;
@@ -828,7 +825,6 @@ int conv_tc_wgrad(const float* x, const float* dy, float* dw, int B, int H, int 
   TcPlan pl = make_plan(2, B, H, W, Ci, Co, k, stride, pad_t, pad_l, Ho, Wo);
   pl.p.out_rows = out_rows ? out_rows : k * k * Ci;
   if (!pl.ok) return GG_OK;
-  if (ws == nullptr || ws_bytes < pl.counter_bytes) return GG_OK;
   CUtensorMap tmA, tmB;
   int rc = act_map(&tmA, x, B, H, W, Ci, pl.p.wt, pl.p.ht, pl.p.bt, stride, 2);
   if (rc) return rc;
