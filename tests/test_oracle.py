@@ -118,7 +118,7 @@ def test_initialisers_follow_reference_formulas():
     assert wl.shape == (128, 4096) and np.abs(wl).max() <= math.sqrt(2. / (128 + 4096)) * math.sqrt(3)
 
 
-GOLDEN = sorted(f for f in os.listdir(GOLD) if f.endswith(".npz")) if os.path.isdir(GOLD) else []
+GOLDEN = sorted(f for f in os.listdir(GOLD) if f.endswith(".npz") and not f.startswith("trajectory")) if os.path.isdir(GOLD) else []
 
 
 @pytest.mark.parametrize("fname", GOLDEN)
@@ -128,3 +128,31 @@ def test_oracle_reproduces_committed_golden_vectors(fname):
     out = MG.compute(str(d["kind"]), {k: d[k] for k in d.files})
     for k, v in out.items():
         np.testing.assert_allclose(v, d["out_" + k], rtol=1e-5, atol=1e-6, err_msg="%s:%s" % (fname, k))
+
+
+def test_oracle_reproduces_first_iterations_of_committed_trajectory():
+    """tests/golden/trajectory100.npz (make_trajectory.py): re-run the first 3 iterations of the fp64 oracle from the
+    tflib-initialised weights and compare cost curve and the iteration-1/2 fixed-noise samples with the committed file"""
+    import torch
+    import tensorflow as tf
+    import tflib as lib
+    import gmgan_inference_cifar10 as S
+    from oracle import gmgan_cifar10 as OM
+    gold = np.load(os.path.join(GOLD, "trajectory100.npz"))
+    B, n_keep = int(gold["batch"]), int(gold["n_keep"])
+    tf.reset_default_graph()
+    lib.delete_all_params()
+    np.random.seed(1234)
+    g = S.build_graph(BATCH_SIZE=B)
+    oracle = OM.GMGANCifar10({n: p.attrs["init"] for n, p in lib._params.items()}, dtype=torch.float64)
+    k1h, noise = g.np_fixed_k.astype(np.float32)[:n_keep], g.np_fixed_noise[:n_keep]
+    step = 0
+    for it in range(2):
+        if it > 0:
+            gc, _ = oracle.gen_step(**OM.synthetic_inputs(B, step)); step += 1
+            assert abs(gc - gold["gen_costs"][it]) < 1e-9
+        dc, _ = oracle.disc_step(**OM.synthetic_inputs(B, step)); step += 1
+        assert abs(dc - gold["disc_costs"][it]) < 1e-9
+        s = oracle.sample(k1h, noise).numpy().astype(np.float32)
+        assert np.abs(s - gold["samples"][it]).max() < 1e-6
+    assert list(gold["checkpoints"]) == [1, 2, 5, 10, 20, 50, 100] and np.isfinite(gold["disc_costs"]).all()
