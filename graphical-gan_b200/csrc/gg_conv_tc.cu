@@ -87,14 +87,6 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
     if (!done && ++spins > (1u << 24)) __trap();      // a mis-programmed pipeline traps instead of hanging the GPU box
   } while (!done);
 }
-__device__ __forceinline__ void mbar_wait_cluster_a(uint32_t bar, uint32_t parity) {
-  uint32_t done, spins = 0;
-  do {
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (!done && ++spins > (1u << 24)) __trap();
-  } while (!done);
-}
 __device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -109,10 +101,6 @@ __device__ __forceinline__ void tma_load_3d_a(uint32_t dst, const CUtensorMap* m
 __device__ __forceinline__ void umma_commit_a(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void cluster_sync_all() {   // every thread of every CTA of the cluster
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_t cta_rank) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
@@ -125,6 +113,18 @@ __device__ __forceinline__ void bulk_s2c(uint32_t dst_cluster, uint32_t src_cta,
                ::"r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(bar_cluster) : "memory");
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// explicit shared-space accesses on 32-bit addresses: the epilogue's pointers are derived from an integer-rounded base, so
+// the compiler would otherwise emit generic LD.E / ST.E for them
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 
 // 32 lanes x 16 consecutive fp32 columns (n_tile = 32: each of the two warps of a quadrant takes 16 columns)
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float* v) {
@@ -229,8 +229,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 2) tmem_alloc(&tmem_base_sh, tmem_cols);
   tc_fence_before();
   const bool cl = p.splits > 1;
-  if (cl) cluster_sync_all();                    // peers must not signal cl_bar before it is initialised
-  else __syncthreads();
+  __syncthreads();
+  // split-K: peers must not signal cl_bar before it is initialised.  Only ARRIVE here; the matching wait sits right in
+  // front of the first remote access (after the main loop), so the cluster rendezvous costs nothing on the way in.
+  if (cl) cluster_arrive();
   tc_fence_after();
   // PDL: everything above is independent of the producer kernel; its activations / gradients are first touched below
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -304,6 +306,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (++s == kStages) { s = 0; ph ^= 1; }
     }
+    __syncwarp();
+    if (cl) { cluster_wait(); cluster_arrive(); }      // phase 1 (start-up rendezvous) consumed; arrive for the exit rendezvous
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     constexpr int a_mn = (MODE == 2) ? 1 : 0;
@@ -336,6 +340,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (++s == kStages) { s = 0; ph ^= 1; }
     }
     if (leader) umma_commit_a(accum_a);       // accumulator complete
+    __syncwarp();
+    if (cl) { cluster_wait(); cluster_arrive(); }
   } else {
     // =========================== epilogue (warps 2..9) ===========================
     const int et = threadIdx.x - 64;              // 0..255
@@ -392,12 +398,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }                                                                                           \
     } while (0)
     // The operand ring is idle once accum_bar has fired: it becomes the staging area of the epilogue.
-    float* stage_tile;
+    uint32_t stage_a;                             // shared address of the staging tile
     int ld;                                       // staging row pitch (floats)
     int cbeg = 0, cend = p.n_tile / 4;            // float4 column range of the tile this CTA writes out
     if (!cl) {
       // un-split: TMEM -> registers -> bias + activation -> [128][n_tile+4] staging tile
-      stage_tile = reinterpret_cast<float*>(smem);
+      stage_a = ring;
       ld = p.n_tile + 4;
       if (hcols >= 32) {
         for (int c0 = cw0; c0 < cw0 + hcols; c0 += 32) {
@@ -407,7 +413,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int i = 0; i < 32; i += 4) {
             float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
             GG_FINISH4(o, c0 + i);
-            *reinterpret_cast<float4*>(stage_tile + m * ld + c0 + i) = o;
+            sts128(stage_a + (uint32_t)(m * ld + c0 + i) * 4u, o);
           }
         }
       } else {
@@ -417,14 +423,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int i = 0; i < 16; i += 4) {
           float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
           GG_FINISH4(o, cw0 + i);
-          *reinterpret_cast<float4*>(stage_tile + m * ld + cw0 + i) = o;
+          sts128(stage_a + (uint32_t)(m * ld + cw0 + i) * 4u, o);
         }
       }
     } else {
       // ---- split-K inside the cluster -------------------------------------------------------------------
       // 1. park this CTA's partial tile in its own shared memory as [n_tile/4][128 rows] float4 (conflict-free for the
       //    thread-per-row TMEM read-out; an owner's column slice is one contiguous block)
-      float4* ptile = reinterpret_cast<float4*>(smem);
       if (hcols >= 32) {
         for (int c0 = cw0; c0 < cw0 + hcols; c0 += 32) {
           float v[32];
@@ -434,7 +439,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int i = 0; i < 32; ++i) v[i] = 0.f;
           }
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) ptile[((c0 + i) >> 2) * 128 + m] = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          for (int i = 0; i < 32; i += 4)
+            sts128(ring + (uint32_t)(((c0 + i) >> 2) * 128 + m) * 16u, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
         }
       } else {
         float v[16];
@@ -444,9 +450,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int i = 0; i < 16; ++i) v[i] = 0.f;
         }
 #pragma unroll
-        for (int i = 0; i < 16; i += 4) ptile[((cw0 + i) >> 2) * 128 + m] = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        for (int i = 0; i < 16; i += 4)
+          sts128(ring + (uint32_t)(((cw0 + i) >> 2) * 128 + m) * 16u, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
       }
       fence_proxy_async();                        // generic-proxy writes -> visible to the copy engine
+      cluster_wait();                             // start-up rendezvous: every peer's cl_bar is initialised
       epi_bar();
       const int nc = p.n_tile / 4;
       cbeg = (split * nc) / p.splits;
@@ -465,23 +473,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         GG_DBG(129);
       }
-      // 3. wait for the (splits-1) incoming slices, then reduce the own slice in split order (deterministic)
-      mbar_wait_cluster_a(cl_a, 0);
+      // 3. wait for the (splits-1) incoming slices (complete_tx on this CTA's own barrier: the same visibility contract as
+      //    a TMA load, so a CTA-scope wait suffices — a cluster-scope acquire would flush the L1), tell the cluster that
+      //    nothing targets this CTA any more (exit rendezvous), then reduce the own slice in split order (deterministic)
+      mbar_wait_a(cl_a, 0);
+      cluster_arrive();
       if (et == 0) GG_DBG(212);
-      stage_tile = reinterpret_cast<float*>(smem + p.stage_off);
+      stage_a = ring + (uint32_t)p.stage_off;
       ld = ncols * 4 + 4;
-      const float4* land = reinterpret_cast<const float4*>(smem + p.land_off);
-      const int slot4 = p.ncols_max * 128;        // float4 per landing slot
+      const uint32_t land_a = ring + (uint32_t)p.land_off;
+      const int nsp = p.splits;
       for (int idx = et; idx < ncols * 128; idx += kEpiThreads) {
         const int c = idx >> 7, row = idx & 127;
+        const uint32_t own = ring + (uint32_t)((cbeg + c) * 128 + row) * 16u;
+        const uint32_t inc = land_a + (uint32_t)(c * 128 + row) * 16u;
+        float4 t[kMaxSplits];
+#pragma unroll
+        for (int sp = 0; sp < kMaxSplits; ++sp)
+          if (sp < nsp) t[sp] = lds128(sp == split ? own : inc + (uint32_t)(sp < split ? sp : sp - 1) * slot_bytes);
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int sp = 0; sp < p.splits; ++sp) {
-          const float4 t = (sp == split) ? ptile[(cbeg + c) * 128 + row]
-                                         : land[(sp < split ? sp : sp - 1) * slot4 + c * 128 + row];
-          o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
-        }
+#pragma unroll
+        for (int sp = 0; sp < kMaxSplits; ++sp)
+          if (sp < nsp) { o.x += t[sp].x; o.y += t[sp].y; o.z += t[sp].z; o.w += t[sp].w; }
         GG_FINISH4(o, (cbeg + c) * 4);
-        *reinterpret_cast<float4*>(stage_tile + row * ld + c * 4) = o;
+        sts128(stage_a + (uint32_t)(row * ld + c * 4) * 4u, o);
       }
     }
 #undef GG_FINISH4
@@ -495,7 +510,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int rpp = kEpiThreads / ncol;         // rows per pass of the 256 threads
         const int my_c = et % ncol, my_r = et / ncol;
         if (my_r < rpp) {
-          const float* sp_ = stage_tile + my_c * 4;
+          const uint32_t sp_ = stage_a + (uint32_t)my_c * 16u;
           float* gp_ = p.out + (size_t)(cbeg + my_c) * 4;
           for (int r = my_r; r < 128; r += 4 * rpp) {
             float4 val[4];
@@ -504,7 +519,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int u = 0; u < 4; ++u) {
               const int rr = r + u * rpp;
               off[u] = rr < 128 ? s_row_off[rr] : -1;
-              val[u] = *reinterpret_cast<const float4*>(sp_ + (rr < 128 ? rr : 0) * ld);
+              val[u] = lds128(sp_ + (uint32_t)((rr < 128 ? rr : 0) * ld) * 4u);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u)
@@ -522,8 +537,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // ---- teardown -----------------------------------------------------------------------------------------
   tc_fence_before();
   __syncwarp();
-  if (cl) cluster_sync_all();                  // no CTA may exit (and free its shared memory) while a peer's copy still reads it
-  else __syncthreads();
+  // exit rendezvous: no CTA may exit (and free its shared memory) while a peer's copy still reads it.  Every thread arrived
+  // above — the epilogue threads only after all slices addressed to their CTA had landed.
+  if (cl) cluster_wait();
+  __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_d, tmem_cols);
 }
 

@@ -35,7 +35,7 @@ def main():
     g = S.build_graph(BATCH_SIZE=BATCH)
     params = {n: p.attrs["init"] for n, p in lib._params.items()}
     oracle = OM.GMGANCifar10(params, dtype=torch.float64)
-    k1h, noise = g.np_fixed_k.astype(np.float32)[:N_KEEP], g.np_fixed_noise[:N_KEEP]
+    k1h, noise = g.np_fixed_k.astype(np.float32), g.np_fixed_noise      # all N_VIS = 300: the generator's batch norm uses THEIR batch statistics
     gen_costs, disc_costs, samples = np.full(ITERS, np.nan), np.zeros(ITERS), {}
     step, t0 = 0, time.time()
     for it in range(ITERS):
@@ -43,7 +43,7 @@ def main():
             gen_costs[it], _ = oracle.gen_step(**OM.synthetic_inputs(BATCH, step)); step += 1
         disc_costs[it], _ = oracle.disc_step(**OM.synthetic_inputs(BATCH, step)); step += 1
         if it + 1 in CHECKPOINTS:
-            samples[it + 1] = oracle.sample(k1h, noise).numpy().astype(np.float32)
+            samples[it + 1] = oracle.sample(k1h, noise).numpy().astype(np.float32)[:N_KEEP]
             print("iteration %d  gen %.6f disc %.6f  (%.0f s)" % (it + 1, gen_costs[it], disc_costs[it], time.time() - t0), flush=True)
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "trajectory100.npz")
     np.savez_compressed(out, gen_costs=gen_costs, disc_costs=disc_costs, checkpoints=np.asarray(CHECKPOINTS),
