@@ -8,8 +8,17 @@
 // (32-byte row segments for cw = 8), its CTAs split the rows, the per-CTA partial sums meet in distributed shared memory
 // (one cluster barrier), and every CTA then normalises its own row slice.  x is read twice (statistics, apply) — the
 // second read is an L1/L2 hit for these sizes — and y written once: 12*R*C bytes algorithmic, HBM/L2-bound.
-// No grid-wide synchronisation, no atomics, deterministic summation order.  The multi-kernel path remains for data
-// parallel runs, where the statistics are all-reduced across ranks between the two halves (SyncBN).
+// No grid-wide synchronisation, no atomics, deterministic summation order.
+//
+// Data parallel (SyncBN, gg_bn_*_fused_dp): batch statistics couple the ranks, so the per-channel sums must be totalled over
+// all GPUs before the normalisation.  Round 1 did that with four launches per layer (stats, fold, a one-CTA all-reduce
+// kernel, apply) — 15 cross-GPU rendezvous per iteration, each with the dependent-launch latencies around it, ~0.35 ms of
+// a 1.0 ms step at N=2.  Here the exchange lives INSIDE the one-launch kernel: the rank-0 CTA of every channel-group
+// cluster writes its group's local sums into every peer's exchange arena over NVLink (plain stores to CUDA-IPC mapped
+// memory), publishes an epoch flag per (group, source rank) with a system-scope release, acquire-spins on the flags the
+// peers wrote into ITS arena, and totals the ranks' sums in rank order (identical result on every GPU); the totals reach
+// the cluster's other CTAs through distributed shared memory.  Per-site flags and parity-double-buffered data slots; the
+// epoch counter of a (site, group) has a single writer.  Spins are bounded (a lost peer traps instead of hanging).
 #include "gg_common.cuh"
 
 using namespace gg;
@@ -18,6 +27,20 @@ namespace {
 
 constexpr int kThreads = 512;
 constexpr int kMaxCw = 32;
+
+constexpr int kMaxPeers = 16;
+// data-parallel context of one batch-norm call site (world == 1: no exchange)
+struct DpCtx {
+  void* peer[kMaxPeers];     // every rank's exchange arena (own included), CUDA-IPC mapped
+  long long site_off;        // byte offset of this call site's region inside every arena
+  int rank, world;
+  int C;                     // channels (layout of the region)
+};
+// region layout: [groups_max] epoch counters | [groups_max][world] flags | [2 parities][world][C] double2 sums
+__host__ __device__ inline size_t dp_groups_max(int C) { return (size_t)(C + 3) / 4; }
+__host__ __device__ inline size_t dp_flags_off(int C) { return ((dp_groups_max(C) * 4 + 127) / 128) * 128; }
+__host__ __device__ inline size_t dp_data_off(int C, int world) { return dp_flags_off(C) + ((dp_groups_max(C) * world * 4 + 127) / 128) * 128; }
+__host__ __device__ inline size_t dp_site_bytes(int C, int world) { return dp_data_off(C, world) + (size_t)2 * world * C * 16; }
 
 struct BnPlan {
   bool ok;
@@ -57,9 +80,60 @@ __device__ __forceinline__ double ld_dsmem_f64(const double* local_ptr, uint32_t
 
 // Reduce per-thread (a[4], b[4]) over all threads of the CTA that share a channel quad, then over the CTAs of the
 // cluster.  Thread t owns quad t % Q; on return threads 0..cw-1 hold the cluster totals of channel c0 + t in (ta, tb).
+__device__ __forceinline__ double2 ld_dsmem_f64x2(const double* local_ptr, uint32_t cta_rank) {
+  return make_double2(ld_dsmem_f64(local_ptr, cta_rank), ld_dsmem_f64(local_ptr + 1, cta_rank));
+}
+
+// Cross-GPU total of the cluster totals held by threads 0..cw-1 of the cluster's rank-0 CTA (see the file header).
+__device__ __forceinline__ void dp_exchange(const DpCtx& dp, int group, int c0, int cw, double& ta, double& tb) {
+  const int tid = threadIdx.x;            // called by warp 0 only (cw <= 32)
+  const int P = dp.world;
+  uint8_t* mine = reinterpret_cast<uint8_t*>(dp.peer[dp.rank]) + dp.site_off;
+  unsigned e = 0;
+  if (tid == 0) {
+    unsigned* ep = reinterpret_cast<unsigned*>(mine) + group;
+    e = ep[0] + 1u;
+    ep[0] = e;
+  }
+  e = __shfl_sync(0xffffffffu, e, 0);
+  const size_t par = (size_t)(e & 1u);
+  const int ch = c0 + tid;
+  const bool ch_ok = tid < cw && ch < dp.C;
+  if (ch_ok) {
+    for (int r = 0; r < P; ++r) {
+      double2* d = reinterpret_cast<double2*>(reinterpret_cast<uint8_t*>(dp.peer[r]) + dp.site_off + dp_data_off(dp.C, P)) +
+                   (par * P + dp.rank) * dp.C + ch;
+      *d = make_double2(ta, tb);
+    }
+  }
+  __threadfence_system();
+  __syncwarp();
+  if (tid < P) {
+    unsigned* f = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(dp.peer[tid]) + dp.site_off + dp_flags_off(dp.C)) +
+                  (size_t)group * P + dp.rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(e) : "memory");
+    const unsigned* w = reinterpret_cast<const unsigned*>(mine + dp_flags_off(dp.C)) + (size_t)group * P + tid;
+    unsigned seen, spins = 0;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(w) : "memory");
+      if ((int)(seen - e) < 0 && ++spins > (1u << 27)) __trap();
+    } while ((int)(seen - e) < 0);
+  }
+  __syncwarp();
+  if (ch_ok) {
+    const double2* d = reinterpret_cast<const double2*>(mine + dp_data_off(dp.C, P)) + par * P * dp.C + ch;
+    ta = 0.0; tb = 0.0;
+    for (int r = 0; r < P; ++r) {          // rank order: identical totals on every GPU
+      const double2 v = __ldcv(d + (size_t)r * dp.C);
+      ta += v.x; tb += v.y;
+    }
+  }
+}
+
 template <int Q>
 __device__ __forceinline__ void reduce_channels(float (&a)[4], float (&b)[4], int cs, double& ta, double& tb,
-                                                float (*wred)[kMaxCw][2], double (*xch)[2]) {
+                                                float (*wred)[kMaxCw][2], double (*xch)[2], const DpCtx& dp, int group, int c0,
+                                                double* la, double* lb) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #pragma unroll
   for (int o = 16; o >= Q; o >>= 1) {
@@ -93,6 +167,22 @@ __device__ __forceinline__ void reduce_channels(float (&a)[4], float (&b)[4], in
     }
     cluster_sync_all();                       // peers have finished reading this CTA's xch: it may exit / reuse
   }
+  *la = ta; *lb = tb;                         // local (this GPU's) totals: the parameter-gradient sums of the backward kernel
+  if (dp.world > 1) {
+    const bool lead = cs == 1 || cluster_ctarank() == 0;
+    if (lead && tid < 32) {
+      dp_exchange(dp, group, c0, cw, ta, tb);
+      if (tid < cw) { xch[tid][0] = ta; xch[tid][1] = tb; }
+    }
+    if (cs > 1) {
+      cluster_sync_all();                     // rank 0's xch now holds the cross-GPU totals
+      if (!lead && tid < cw) {
+        const double2 v = ld_dsmem_f64x2(&xch[tid][0], 0u);
+        ta = v.x; tb = v.y;
+      }
+      cluster_sync_all();
+    }
+  }
 }
 
 template <int Q>
@@ -100,7 +190,7 @@ __global__ void __launch_bounds__(kThreads) bn_fwd_fused_kernel(const float* __r
                                                                 const float* __restrict__ beta, float eps,
                                                                 float* __restrict__ y, float* __restrict__ mean_out,
                                                                 float* __restrict__ rstd_out, int R, int C, int cs, int act,
-                                                                float alpha) {
+                                                                float alpha, const DpCtx dp) {
   GG_PDL_ENTRY();
   constexpr int cw = Q * 4, RL = kThreads / Q;
   __shared__ float wred[kThreads / 32][kMaxCw][2];
@@ -125,13 +215,14 @@ __global__ void __launch_bounds__(kThreads) bn_fwd_fused_kernel(const float* __r
       b[0] += v.x * v.x; b[1] += v.y * v.y; b[2] += v.z * v.z; b[3] += v.w * v.w;
     }
   }
-  double ta, tb;
-  reduce_channels<Q>(a, b, cs, ta, tb, wred, xch);
+  double ta, tb, la, lb;
+  reduce_channels<Q>(a, b, cs, ta, tb, wred, xch, dp, group, c0, &la, &lb);
+  const double Rg = (double)R * (double)dp.world;            // equal shards: the global row count
   if (tid < cw) {
     const int ch = c0 + tid;
     if (ch < C) {
-      const double mean = ta / (double)R;
-      double var = tb / (double)R - mean * mean;             // biased batch variance (fused_batch_norm, is_training)
+      const double mean = ta / Rg;
+      double var = tb / Rg - mean * mean;                    // biased batch variance (fused_batch_norm, is_training)
       if (var < 0.0) var = 0.0;
       const float rstd = (float)(1.0 / sqrt(var + (double)eps));
       const float g = gamma ? gamma[ch] : 1.f, bt = beta ? beta[ch] : 0.f;
@@ -166,7 +257,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_fused_kernel(const float* __r
                                                                 const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                                 float* __restrict__ dx, float* __restrict__ dgamma,
                                                                 float* __restrict__ dbeta, int R, int C, int cs, int act,
-                                                                float alpha) {
+                                                                float alpha, const DpCtx dp) {
   GG_PDL_ENTRY();
   constexpr int cw = Q * 4, RL = kThreads / Q;
   __shared__ float wred[kThreads / 32][kMaxCw][2];
@@ -204,16 +295,17 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_fused_kernel(const float* __r
       b[2] += g.z * ((xv.z - m4.z) * rs4.z); b[3] += g.w * ((xv.w - m4.w) * rs4.w);
     }
   }
-  double ta, tb;
-  reduce_channels<Q>(a, b, cs, ta, tb, wred, xch);
+  double ta, tb, la, lb;
+  reduce_channels<Q>(a, b, cs, ta, tb, wred, xch, dp, group, c0, &la, &lb);
+  const double Rg = (double)R * (double)dp.world;
   if (tid < cw) {
     const int ch = c0 + tid;
     if (ch < C) {
-      s_mg[tid] = (float)(ta / (double)R);
-      s_mgx[tid] = (float)(tb / (double)R);
-      if (rank == 0) {
-        if (dbeta) dbeta[ch] = (float)ta;
-        if (dgamma) dgamma[ch] = (float)tb;
+      s_mg[tid] = (float)(ta / Rg);
+      s_mgx[tid] = (float)(tb / Rg);
+      if (rank == 0) {                                       // LOCAL sums: the gradient all-reduce totals them over the ranks
+        if (dbeta) dbeta[ch] = (float)la;
+        if (dgamma) dgamma[ch] = (float)lb;
       }
     }
   }
@@ -280,36 +372,77 @@ int launch_clustered(Kern kern, const BnPlan& pl, cudaStream_t st, const char* w
 
 extern "C" int gg_bn_fused_supported(int R, int C) { return bn_plan(R, C).ok ? 1 : 0; }
 
-extern "C" int gg_bn_fwd_fused(const float* x, const float* gamma, const float* beta, float eps, float* y, float* mean_out,
-                               float* rstd_out, int R, int C, int act, float alpha, void* stream) {
+static int bn_fwd_launch(const float* x, const float* gamma, const float* beta, float eps, float* y, float* mean_out,
+                         float* rstd_out, int R, int C, int act, float alpha, const DpCtx& dp, void* stream, const char* what) {
   if (R <= 0 || C <= 0) return GG_OK;
   const BnPlan pl = bn_plan(R, C);
-  if (!pl.ok) return fail(GG_ERR_UNSUPPORTED, "gg_bn_fwd_fused: C must be a multiple of 4%s");
+  if (!pl.ok) return fail(GG_ERR_UNSUPPORTED, "%s: C must be a multiple of 4", what);
   cudaStream_t st = as_stream(stream);
   if (pl.cw == 32)
-    return launch_clustered(bn_fwd_fused_kernel<8>, pl, st, "gg_bn_fwd_fused", x, gamma, beta, eps, y, mean_out, rstd_out, R, C,
-                            pl.cs, act, alpha);
+    return launch_clustered(bn_fwd_fused_kernel<8>, pl, st, what, x, gamma, beta, eps, y, mean_out, rstd_out, R, C, pl.cs, act, alpha, dp);
   if (pl.cw == 8)
-    return launch_clustered(bn_fwd_fused_kernel<2>, pl, st, "gg_bn_fwd_fused", x, gamma, beta, eps, y, mean_out, rstd_out, R, C,
-                            pl.cs, act, alpha);
-  return launch_clustered(bn_fwd_fused_kernel<1>, pl, st, "gg_bn_fwd_fused", x, gamma, beta, eps, y, mean_out, rstd_out, R, C,
-                          pl.cs, act, alpha);
+    return launch_clustered(bn_fwd_fused_kernel<2>, pl, st, what, x, gamma, beta, eps, y, mean_out, rstd_out, R, C, pl.cs, act, alpha, dp);
+  return launch_clustered(bn_fwd_fused_kernel<1>, pl, st, what, x, gamma, beta, eps, y, mean_out, rstd_out, R, C, pl.cs, act, alpha, dp);
+}
+
+static int bn_bwd_launch(const float* dy, const float* x, const float* y, const float* mean, const float* rstd, const float* gamma,
+                         float* dx, float* dgamma, float* dbeta, int R, int C, int act, float alpha, const DpCtx& dp, void* stream,
+                         const char* what) {
+  if (R <= 0 || C <= 0) return GG_OK;
+  if (act != GG_ACT_NONE && y == nullptr) return fail(GG_ERR_BAD_ARG, "%s: y required when act is fused", what);
+  const BnPlan pl = bn_plan(R, C);
+  if (!pl.ok) return fail(GG_ERR_UNSUPPORTED, "%s: C must be a multiple of 4", what);
+  cudaStream_t st = as_stream(stream);
+  if (pl.cw == 32)
+    return launch_clustered(bn_bwd_fused_kernel<8>, pl, st, what, dy, x, y, mean, rstd, gamma, dx, dgamma, dbeta, R, C, pl.cs, act, alpha, dp);
+  if (pl.cw == 8)
+    return launch_clustered(bn_bwd_fused_kernel<2>, pl, st, what, dy, x, y, mean, rstd, gamma, dx, dgamma, dbeta, R, C, pl.cs, act, alpha, dp);
+  return launch_clustered(bn_bwd_fused_kernel<1>, pl, st, what, dy, x, y, mean, rstd, gamma, dx, dgamma, dbeta, R, C, pl.cs, act, alpha, dp);
+}
+
+static int make_dp(DpCtx* dp, void* const* peer_arenas_host, int rank, int world, long long site_offset, int C, const char* what) {
+  *dp = DpCtx{};
+  dp->world = 1;
+  dp->C = C;
+  if (world <= 1) return GG_OK;
+  if (world > kMaxPeers || rank < 0 || rank >= world || peer_arenas_host == nullptr || site_offset < 0 || (site_offset & 127))
+    return fail(GG_ERR_BAD_ARG, "%s: bad world / rank / arena / site offset", what);
+  for (int r = 0; r < world; ++r) dp->peer[r] = peer_arenas_host[r];
+  dp->rank = rank; dp->world = world; dp->site_off = site_offset;
+  return GG_OK;
+}
+
+extern "C" int gg_bn_fwd_fused(const float* x, const float* gamma, const float* beta, float eps, float* y, float* mean_out,
+                               float* rstd_out, int R, int C, int act, float alpha, void* stream) {
+  DpCtx dp{};
+  dp.world = 1; dp.C = C;
+  return bn_fwd_launch(x, gamma, beta, eps, y, mean_out, rstd_out, R, C, act, alpha, dp, stream, "gg_bn_fwd_fused");
 }
 
 extern "C" int gg_bn_bwd_fused(const float* dy, const float* x, const float* y, const float* mean, const float* rstd,
                                const float* gamma, float* dx, float* dgamma, float* dbeta, int R, int C, int act, float alpha,
                                void* stream) {
-  if (R <= 0 || C <= 0) return GG_OK;
-  if (act != GG_ACT_NONE && y == nullptr) return fail(GG_ERR_BAD_ARG, "gg_bn_bwd_fused: y required when act is fused%s");
-  const BnPlan pl = bn_plan(R, C);
-  if (!pl.ok) return fail(GG_ERR_UNSUPPORTED, "gg_bn_bwd_fused: C must be a multiple of 4%s");
-  cudaStream_t st = as_stream(stream);
-  if (pl.cw == 32)
-    return launch_clustered(bn_bwd_fused_kernel<8>, pl, st, "gg_bn_bwd_fused", dy, x, y, mean, rstd, gamma, dx, dgamma, dbeta, R,
-                            C, pl.cs, act, alpha);
-  if (pl.cw == 8)
-    return launch_clustered(bn_bwd_fused_kernel<2>, pl, st, "gg_bn_bwd_fused", dy, x, y, mean, rstd, gamma, dx, dgamma, dbeta, R,
-                            C, pl.cs, act, alpha);
-  return launch_clustered(bn_bwd_fused_kernel<1>, pl, st, "gg_bn_bwd_fused", dy, x, y, mean, rstd, gamma, dx, dgamma, dbeta, R,
-                          C, pl.cs, act, alpha);
+  DpCtx dp{};
+  dp.world = 1; dp.C = C;
+  return bn_bwd_launch(dy, x, y, mean, rstd, gamma, dx, dgamma, dbeta, R, C, act, alpha, dp, stream, "gg_bn_bwd_fused");
+}
+
+extern "C" size_t gg_bn_dp_site_bytes(int C, int world) { return (dp_site_bytes(C, world < 1 ? 1 : world) + 127) & ~size_t(127); }
+
+extern "C" int gg_bn_fwd_fused_dp(const float* x, const float* gamma, const float* beta, float eps, float* y, float* mean_out,
+                                  float* rstd_out, int R, int C, int act, float alpha, void* const* peer_arenas_host, int rank,
+                                  int world, long long site_offset, void* stream) {
+  DpCtx dp;
+  int rc = make_dp(&dp, peer_arenas_host, rank, world, site_offset, C, "gg_bn_fwd_fused_dp");
+  if (rc) return rc;
+  return bn_fwd_launch(x, gamma, beta, eps, y, mean_out, rstd_out, R, C, act, alpha, dp, stream, "gg_bn_fwd_fused_dp");
+}
+
+extern "C" int gg_bn_bwd_fused_dp(const float* dy, const float* x, const float* y, const float* mean, const float* rstd,
+                                  const float* gamma, float* dx, float* dgamma, float* dbeta, int R, int C, int act, float alpha,
+                                  void* const* peer_arenas_host, int rank, int world, long long site_offset, void* stream) {
+  DpCtx dp;
+  int rc = make_dp(&dp, peer_arenas_host, rank, world, site_offset, C, "gg_bn_bwd_fused_dp");
+  if (rc) return rc;
+  return bn_bwd_launch(dy, x, y, mean, rstd, gamma, dx, dgamma, dbeta, R, C, act, alpha, dp, stream, "gg_bn_bwd_fused_dp");
 }

@@ -74,6 +74,23 @@ extern "C" int gg_comm_alloc(int max_floats, void** buf_out, void* ipc_handle_ou
   return GG_OK;
 }
 
+// general-purpose exchange arena (SyncBN call sites of the one-launch batch-norm kernels, gg_bn_*_fused_dp): zero-filled,
+// exported with CUDA IPC like the small all-reduce buffer
+extern "C" int gg_comm_alloc_bytes(size_t bytes, void** buf_out, void* ipc_handle_out_64) {
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) return fail(GG_ERR_CUDA_BASE + (int)e, "gg_comm_alloc_bytes: cudaMalloc failed: %s", cudaGetErrorString(e));
+  e = cudaMemset(p, 0, bytes);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return fail(GG_ERR_CUDA_BASE + (int)e, "gg_comm_alloc_bytes: memset failed: %s", cudaGetErrorString(e));
+  cudaIpcMemHandle_t h;
+  e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) return fail(GG_ERR_CUDA_BASE + (int)e, "gg_comm_alloc_bytes: cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+  memcpy(ipc_handle_out_64, &h, 64);
+  *buf_out = p;
+  return GG_OK;
+}
+
 extern "C" int gg_comm_open(const void* ipc_handle_64, void** buf_out) {
   cudaIpcMemHandle_t h;
   memcpy(&h, ipc_handle_64, 64);

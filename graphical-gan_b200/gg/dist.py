@@ -48,6 +48,8 @@ def init_from_env(backend=None):
         t = torch.zeros(1, device="cuda")
         td.all_reduce(t)
         torch.cuda.synchronize()
+    import atexit
+    atexit.register(shutdown)
     return td.get_rank(), td.get_world_size()
 
 
@@ -90,6 +92,72 @@ class SmallAllReduce(object):
     def __call__(self, src, dst, n, stream):
         self.cabi.call("gg_allreduce_small", src.data_ptr(), dst.data_ptr(), int(n), self.peers, self.rank, self.world,
                        self.MAX_FLOATS, self.epoch.data_ptr(), stream)
+
+
+class PeerArena(object):
+    """One CUDA-IPC exchange arena per rank, mapped by every peer over NVLink (csrc/gg_comm.cu::gg_comm_alloc_bytes).  The
+    one-launch SyncBN kernels (gg_bn_*_fused_dp) exchange their per-channel sums through it; every batch-norm call site
+    bump-allocates its own region here — in graph-construction order, i.e. at the same offset on every rank."""
+    BYTES = int(os.environ.get("GG_ARENA_MB", "64")) << 20
+
+    def __init__(self):
+        import ctypes as C
+        from . import cabi
+        self.rank, self.world = rank(), world_size()
+        buf = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        cabi.call("gg_comm_alloc_bytes", self.BYTES, C.byref(buf), handle)
+        handles = [None] * self.world
+        _td().all_gather_object(handles, bytes(handle.raw))
+        ptrs = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                ptrs.append(buf.value)
+            else:
+                q = C.c_void_p()
+                cabi.call("gg_comm_open", C.create_string_buffer(h, 64), C.byref(q))
+                ptrs.append(q.value)
+        self.peers = (C.c_void_p * self.world)(*ptrs)
+        self.off = 0
+        _td().barrier()
+
+    def alloc(self, nbytes):
+        off = self.off
+        self.off += (int(nbytes) + 127) & ~127
+        if self.off > self.BYTES:
+            raise MemoryError("peer exchange arena exhausted (%d bytes): raise GG_ARENA_MB" % self.BYTES)
+        return off
+
+
+_arena = {}
+
+
+def peer_arena():
+    """process-wide PeerArena, or None (single rank, or GG_BN_DP=0 -> the multi-kernel SyncBN form)"""
+    if world_size() <= 1 or os.environ.get("GG_BN_DP", "1") == "0":
+        return None
+    if "obj" not in _arena:
+        _arena["obj"] = PeerArena()
+    return _arena["obj"]
+
+
+def shutdown():
+    """Leave the process group BEFORE the interpreter tears down CUDA graphs that hold captured NCCL kernels (an exit with the
+    communicator alive inside captured graphs hung round 1's dp_check): drop the plans, synchronise, destroy the group."""
+    import gc
+    td = _td()
+    if not (td.is_available() and td.is_initialized()):
+        return
+    try:
+        import torch
+        from . import executor
+        executor.RT.plans.clear()
+        gc.collect()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        td.destroy_process_group()
+    except Exception:
+        pass
 
 
 _small = {}

@@ -197,16 +197,14 @@ class Plan(object):
             self.groups.append(dict(start=0, end=1, reads=set(), writes="tick", barrier=False, collective=False, node=None,
                                     part=(0, 1), ordered=False))
         self._plan_inplace_concats()
+        self._plan_grad_buckets(fetches)
         for node in self.order:
             s0 = len(self.steps)
             self._emit(node)
             self._note_group(node, s0)
         for f in fetches:
             if isinstance(f, Operation):
-                s0 = len(self.steps)
                 self._emit_operation(f)
-                if len(self.steps) > s0:
-                    self._add_groups(s0, len(self.steps), set(), "op%d" % f.id, barrier=True)
         self.graph = None
         self.trace, self.trace_t0 = [], None
         self.kernel_launches = 0   # libgg_b200 kernels per run (counted at capture / eager launch)
@@ -252,7 +250,10 @@ class Plan(object):
             r = set(reads) if prev is None else {prev}
             # peer-memory all-reduce kernels share one exchange buffer and an epoch counter per rank: they must run one at
             # a time and in the same order on every rank, so the scheduler chains the groups that contain one
-            ordered = coll or any(getattr(self.steps[i], "is_small_allreduce", False) for i in range(a, b))
+            # ordering classes: NCCL collectives among themselves (one communicator), peer-memory exchange kernels among
+            # themselves (same order, one at a time on every rank); the two classes are independent of each other so a
+            # gradient bucket's all-reduce can start while later SyncBN layers of the backward pass are still running
+            ordered = "nccl" if coll else ("peer" if any(getattr(self.steps[i], "is_small_allreduce", False) for i in range(a, b)) else None)
             self.groups.append(dict(start=a, end=b, reads=r, writes=w, barrier=barrier and prev is None, collective=coll,
                                     node=node, part=(k, len(ranges)), ordered=ordered))
             prev = w
@@ -286,6 +287,11 @@ class Plan(object):
 
     # ---- emission ---------------------------------------------------------------------------
     def _alloc(self, node):
+        if node.id in self.placed_flat:   # a parameter gradient produced straight into its optimiser's all-reduce bucket
+            oid, off = self.placed_flat[node.id]
+            t = self.flat[oid][off:off + max(node.size, 1)]
+            self.buf[node.id] = t
+            return t
         if node.id in self.placed:       # this node's output lives inside the buffer of an axis-0 concat (zero-copy concat)
             cid, off = self.placed[node.id]
             t = self._concat_storage(cid)[off:off + max(node.size, 1)]
@@ -331,6 +337,89 @@ class Plan(object):
                 for inp, o in plan:
                     self.placed[inp.id] = (node.id, o)
                 self.inplace_concat.add(node.id)
+
+    # ---- data-parallel gradient buckets --------------------------------------------------------------------------------
+    # One flat fp32 buffer per optimiser (parameters replicated, gradients summed once per step).  Round 1
+    # packed the gradients into it with an extra kernel after the whole backward pass and all-reduced it in one exposed,
+    # eager NCCL call between two graph segments.  Now (a) every gradient whose only consumer is the optimiser is PRODUCED
+    # inside the buffer (the wgrad / bias-sum kernel writes there: no pack pass), (b) the buffer is laid out in the order the
+    # gradients become available and cut into GG_DP_BUCKETS ranges, each all-reduced as soon as its last producer has run —
+    # on a stream of its own inside the step's CUDA graph, beside the rest of the backward pass.
+    def _optimizer_ops(self, fetches):
+        out = []
+
+        def walk(op):
+            if op.kind == "group":
+                for sub in op.attrs["ops"]:
+                    walk(sub)
+            elif op.kind in ("adam", "rmsprop"):
+                out.append(op)
+        for f in fetches:
+            if isinstance(f, Operation):
+                walk(f)
+        return out
+
+    def _plan_grad_buckets(self, fetches):
+        torch = _torch()
+        self.placed_flat, self.flat, self.bucket_plan = {}, {}, {}
+        world = ggdist.world_size()
+        if world <= 1:
+            return
+        # readiness of a node = length of the longest dependency chain below it (tensor-core launches weigh ~6 glue
+        # launches): the toposort position is useless here — a depth-first order emits the deepest gradient's whole chain first
+        pos = {}
+        for n in self.order:
+            w = 6 if n.op in ("conv", "matmul") else (0 if n.op in ALIAS_OPS or not n.inputs else 1)
+            pos[n.id] = w + max([pos.get(i.id, 0) for i in n.inputs] or [0])
+        uses = {}
+        for n in self.order:
+            if n.id in self.fed:
+                continue
+            for i in n.inputs:
+                uses[i.id] = uses.get(i.id, 0) + 1
+        opts = self._optimizer_ops(fetches)
+        for f in fetches:
+            if isinstance(f, Tensor):
+                uses[f.id] = uses.get(f.id, 0) + 1
+        for op in opts:
+            for d in op.deps:
+                if d is not None:
+                    uses[d.id] = uses.get(d.id, 0) + 1
+        direct = os.environ.get("GG_DP_DIRECT", "1") != "0"
+        n_buckets = max(1, int(os.environ.get("GG_DP_BUCKETS", "2")))
+        for op in opts:
+            entries = []
+            for v, g in zip(op.attrs["vars"], op.deps):
+                if g is None:
+                    continue
+                own, ok = g, uses.get(g.id, 0) == 1
+                while own.op in ("reshape", "stop_gradient") and own.id not in self.fed:
+                    own = own.inputs[0]
+                    ok = ok and uses.get(own.id, 0) == 1
+                ok = ok and direct and own.op in self.OWN_OUTPUT_OPS and own.id not in self.fed and own.id not in self.placed \
+                    and own.id not in self.placed_flat and own.dtype == float32 and own.size == v.size
+                entries.append(dict(var=v, grad=g, own=own, direct=ok, ready=pos.get(own.id, 0)))
+            entries.sort(key=lambda e: e["ready"])
+            off = 0
+            for e in entries:
+                e["off"] = off
+                off += (e["var"].size + 63) & ~63                 # 256-byte aligned slots
+            total = max(off, 64)
+            self.flat[op.attrs["opt_id"]] = torch.zeros(total, dtype=torch.float32, device=self.rt.dev())
+            for e in entries:
+                if e["direct"]:
+                    self.placed_flat[e["own"].id] = (op.attrs["opt_id"], e["off"])
+            # cut into buckets of roughly equal bytes in readiness order
+            buckets, cur, acc, per = [], [], 0, total / float(n_buckets)
+            for e in entries:
+                cur.append(e)
+                acc += (e["var"].size + 63) & ~63
+                if acc >= per * (len(buckets) + 1) and len(buckets) < n_buckets - 1:
+                    buckets.append(cur)
+                    cur = []
+            if cur:
+                buckets.append(cur)
+            self.bucket_plan[op.attrs["opt_id"]] = (entries, buckets, total)
 
     def _concat_storage(self, cid):
         if cid not in self._concat_bufs:
@@ -628,6 +717,17 @@ class Plan(object):
             xp, gp, bp, yp, mp, rp = (t.data_ptr() for t in (x, gamma, beta, y, mean, rstd))
             self.steps.append(lambda st: cabi.call("gg_bn_fwd_fused", xp, gp, bp, eps, yp, mp, rp, R, Cc, act, alpha, st))
             return
+        arena = self._bn_dp_arena(R, Cc, world)
+        if arena is not None:
+            # SyncBN in ONE launch: the per-channel sums are totalled over the ranks inside the kernel (NVLink peer stores +
+            # epoch flags in the exchange arena); one region per call site
+            site = arena.alloc(cabi.lib.gg_bn_dp_site_bytes(Cc, world))
+            xp, gp, bp, yp, mp, rp = (t.data_ptr() for t in (x, gamma, beta, y, mean, rstd))
+            peers, rk = arena.peers, ggdist.rank()
+            fn = lambda st: cabi.call("gg_bn_fwd_fused_dp", xp, gp, bp, eps, yp, mp, rp, R, Cc, act, alpha, peers, rk, world, site, st)
+            fn.is_small_allreduce = True          # cross-rank rendezvous inside: same order on every rank, one at a time
+            self.steps.append(fn)
+            return
         S = cabi.lib.gg_bn_slices(R, Cc)
         part = self.rt.empty((S, 2, Cc))
         self.keep.append(part)
@@ -648,6 +748,13 @@ class Plan(object):
         return (world == 1 or not self.rt.sync_bn) and os.environ.get("GG_BN_FUSED", "1") != "0" and \
             cabi.lib.gg_bn_fused_supported(R, Cc) == 1
 
+    def _bn_dp_arena(self, R, Cc, world):
+        """the peer exchange arena when this batch norm can run as the one-launch data-parallel kernel, else None"""
+        if world <= 1 or not self.rt.sync_bn or os.environ.get("GG_BN_FUSED", "1") == "0" or \
+                cabi.lib.gg_bn_fused_supported(R, Cc) != 1:
+            return None
+        return ggdist.peer_arena()
+
     def _emit_bn_grad(self, node):
         gy, x, y, mean, rstd, gamma = (self._in(node, i) for i in range(6))
         dx = self._alloc(node)
@@ -661,6 +768,18 @@ class Plan(object):
             gyp, xp, yp, mp, rp, gp, dxp = (t.data_ptr() for t in (gy, x, y, mean, rstd, gamma, dx))
             dgp, dbp = dgb.data_ptr() + 4 * Cc, dgb.data_ptr()
             self.steps.append(lambda st: cabi.call("gg_bn_bwd_fused", gyp, xp, yp, mp, rp, gp, dxp, dgp, dbp, R, Cc, act, alpha, st))
+            return
+        world = ggdist.world_size()
+        arena = self._bn_dp_arena(R, Cc, world)
+        if arena is not None:
+            site = arena.alloc(cabi.lib.gg_bn_dp_site_bytes(Cc, world))
+            gyp, xp, yp, mp, rp, gp, dxp = (t.data_ptr() for t in (gy, x, y, mean, rstd, gamma, dx))
+            dgp, dbp = dgb.data_ptr() + 4 * Cc, dgb.data_ptr()
+            peers, rk = arena.peers, ggdist.rank()
+            fn = lambda st: cabi.call("gg_bn_bwd_fused_dp", gyp, xp, yp, mp, rp, gp, dxp, dgp, dbp, R, Cc, act, alpha, peers, rk,
+                                      world, site, st)
+            fn.is_small_allreduce = True
+            self.steps.append(fn)
             return
         S = cabi.lib.gg_bn_slices(R, Cc)
         part = self.rt.empty((S, 2, Cc))
@@ -696,19 +815,27 @@ class Plan(object):
 
     # ---- operations (train ops) ---------------------------------------------------------------
     def _emit_operation(self, op):
+        """emit a train op and its scheduling groups: the update itself is a barrier (it waits for everything before it and
+        everything after waits for it); the data-parallel gradient buckets in front of it are ordinary groups that depend
+        only on the kernels producing their gradients"""
         if op.kind == "group":
             for sub in op.attrs["ops"]:
                 self._emit_operation(sub)
-        elif op.kind == "noop":
-            pass
-        elif op.kind in ("adam", "rmsprop"):
+            return
+        if op.kind == "noop":
+            return
+        s0 = len(self.steps)
+        if op.kind in ("adam", "rmsprop"):
             self._emit_optimizer(op)
+            s0 = self._opt_update_start
         elif op.kind == "assign":
             var, val = op.attrs["var"], op.deps[0]
             vp, sp, n = self.rt.param_buffer(var).data_ptr(), self.buf[val.id].data_ptr(), var.size
             self.steps.append(lambda st: cabi.call("gg_unary", cabi.UNARY["copy"], sp, vp, n, 0.0, 0.0, st))
         else:
             raise NotImplementedError("operation %r" % op.kind)
+        if len(self.steps) > s0:
+            self._add_groups(s0, len(self.steps), set(), "op%d" % op.id, barrier=True)
 
     def _emit_optimizer(self, op):
         torch = _torch()
@@ -751,16 +878,30 @@ class Plan(object):
         gscale = 1.0
         adam_tab = tab
         if world > 1:
-            # one flat fp32 bucket per optimiser step: pack -> ONE NCCL all-reduce -> Adam reads the bucket
-            offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
-            flat = torch.empty(int(offs[-1]), dtype=torch.float32, device=rt.dev())
-            offs_d = torch.from_numpy(offs[:-1].copy()).to(rt.dev())
-            adam_tab = table([flat.data_ptr() + int(o) * 4 for o in offs[:-1]])
-            self.keep += [flat, offs_d, adam_tab]
-            ptab, pchk, poff, pflat = tab.data_ptr(), chk.data_ptr(), offs_d.data_ptr(), flat.data_ptr()
-            self.steps.append(lambda st: cabi.call("gg_pack_grads", ptab, pchk, n_chunks, poff, pflat, 1, st))
-            self.steps.append(self._collective(lambda st: ggdist.all_reduce_sum(flat)))
+            # gradients live in (or are copied into) the optimiser's flat buffer; one NCCL all-reduce per readiness bucket
+            entries, buckets, total = self.bucket_plan[op.attrs["opt_id"]]
+            flat = self.flat[op.attrs["opt_id"]]
+            off_of = {e["var"].id: e["off"] for e in entries}
+            adam_tab = table([flat.data_ptr() + 4 * off_of[v.id] for v, _ in pairs])
+            self.keep += [flat, adam_tab]
+            for bi, bucket in enumerate(buckets):
+                b0 = len(self.steps)
+                reads = set()
+                for e in bucket:
+                    reads |= self._owners(e["grad"])
+                    if not e["direct"]:
+                        sp_, dp_, n_ = self.buf[e["grad"].id].data_ptr(), flat.data_ptr() + 4 * e["off"], e["var"].size
+                        self.steps.append(lambda st, sp_=sp_, dp_=dp_, n_=n_: cabi.call("gg_unary", cabi.UNARY["copy"], sp_, dp_, n_, 0.0, 0.0, st))
+                lo = bucket[0]["off"]
+                hi = bucket[-1]["off"] + ((bucket[-1]["var"].size + 63) & ~63)
+                view = flat[lo:hi]
+                self.keep.append(view)
+                fn = self._collective(lambda st, view=view: ggdist.all_reduce_sum(view))
+                fn.cost_us = 25.0 + (hi - lo) * 4 / 3.0e5          # ~300 GB/s bus bandwidth + launch latency
+                self.steps.append(fn)
+                self._add_groups(b0, len(self.steps), reads, "bucket%d_%d" % (op.attrs["opt_id"], bi), barrier=False)
             gscale = 1.0 / world
+        self._opt_update_start = len(self.steps)
         tp, cp, sp = adam_tab.data_ptr(), chk.data_ptr(), state.data_ptr()
         a = op.attrs
         if op.kind == "adam":
@@ -797,6 +938,8 @@ class Plan(object):
         fixed ~10 us of pipeline fill + split-K exchange, element-wise glue by the ~2 us dependent-launch latency"""
         node = g.get("node")
         n_k = g["end"] - g["start"]
+        if g.get("collective"):
+            return float(getattr(self.steps[g["start"]], "cost_us", 60.0))
         if node is None:
             return 16.0 if g["barrier"] else 2.0          # optimiser update / rng tick
         mb = node.size * 4 / 1e6
@@ -836,16 +979,16 @@ class Plan(object):
         cost = {gi: self._group_cost(self.groups[gi]) for gi in idxs}
         # dependencies: producers of what the group reads; an optimiser step (barrier) waits for everything before it and
         # everything after it waits for the barrier
-        producer, deps, last_barrier, last_ordered, seen = {}, {}, None, None, []
+        producer, deps, last_barrier, last_ordered, seen = {}, {}, None, {}, []
         for gi in idxs:
             g = self.groups[gi]
             d = set(producer[o] for o in g["reads"] if o in producer)
             if last_barrier is not None:
                 d.add(last_barrier)
             if g.get("ordered"):
-                if last_ordered is not None:
-                    d.add(last_ordered)
-                last_ordered = gi
+                if g["ordered"] in last_ordered:
+                    d.add(last_ordered[g["ordered"]])
+                last_ordered[g["ordered"]] = gi
             if g["barrier"]:
                 d |= set(seen)
                 last_barrier = gi
@@ -983,7 +1126,7 @@ class Plan(object):
         segments, cur = [], []
         # GG_NCCL_IN_GRAPH=1: capture the NCCL all-reduce as a node of the step's graph (one graph launch per step, and the
         # scheduler can run independent kernels beside the exchange) instead of cutting the launch list around it
-        in_graph = os.environ.get("GG_NCCL_IN_GRAPH", "0") == "1"
+        in_graph = os.environ.get("GG_NCCL_IN_GRAPH", "1") == "1"
         for gi, grp in enumerate(self.groups):
             if grp["collective"] and not in_graph:
                 if cur:

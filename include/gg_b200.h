@@ -265,6 +265,23 @@ int gg_rng_categorical(int32_t* idx, int n, const float* probs, int K, uint64_t 
 size_t gg_comm_buffer_bytes(int max_floats);
 int gg_comm_alloc(int max_floats, void** buf_out, void* ipc_handle_out_64);
 int gg_comm_open(const void* ipc_handle_64, void** buf_out);
+/* zero-filled exchange arena of `bytes` (cudaMalloc + CUDA IPC handle), for the SyncBN call sites below */
+int gg_comm_alloc_bytes(size_t bytes, void** buf_out, void* ipc_handle_out_64);
+
+/* ---- data-parallel batch norm in ONE launch (SyncBN; tflib/ops/batchnorm.py:30,77-84 evaluated on the GLOBAL batch) -------
+ * Same arithmetic as gg_bn_fwd_fused / gg_bn_bwd_fused on this rank's R rows, with the per-channel sums totalled over the
+ * `world` ranks inside the kernel: every channel-group cluster writes its sums into all peers' arenas over NVLink and
+ * spins on the peers' epoch flags (csrc/gg_bn_fused.cu).  peer_arenas_host[r] = rank r's arena as mapped in THIS process
+ * (gg_comm_alloc_bytes / gg_comm_open); site_offset = this call site's region (gg_bn_dp_site_bytes(C, world) bytes,
+ * 128-byte aligned, the same offset on every rank, never shared between two call sites).  Every rank must launch the same
+ * call sites the same number of times.  dgamma / dbeta are the LOCAL sums (the gradient all-reduce totals them). */
+size_t gg_bn_dp_site_bytes(int C, int world);
+int gg_bn_fwd_fused_dp(const float* x, const float* gamma, const float* beta, float eps, float* y, float* mean_out,
+                       float* rstd_out, int R, int C, int act, float alpha, void* const* peer_arenas_host, int rank, int world,
+                       long long site_offset, void* stream);
+int gg_bn_bwd_fused_dp(const float* dy, const float* x, const float* y, const float* mean, const float* rstd, const float* gamma,
+                       float* dx, float* dgamma, float* dbeta, int R, int C, int act, float alpha,
+                       void* const* peer_arenas_host, int rank, int world, long long site_offset, void* stream);
 int gg_allreduce_small(const float* src, float* dst, int n, void* const* peer_bufs_host, int rank, int world,
                        int max_floats, void* epoch_counter, void* stream);
 

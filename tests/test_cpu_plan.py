@@ -141,26 +141,80 @@ def test_launch_list_uses_single_launch_batchnorm_and_fused_epilogues(cpu_device
     assert not [a for n, a in record if n == "gg_unary" and a[0] in act_codes]
 
 
-def test_data_parallel_plan_cuts_at_the_gradient_exchange_and_chains_statistic_exchanges(cpu_device, monkeypatch):
+class _FakeArena(object):
+    """host stand-in of gg.dist.PeerArena: bump allocation only"""
+    peers = None
+
+    def __init__(self):
+        self.off, self.sites = 0, []
+
+    def alloc(self, nbytes):
+        off = self.off
+        self.off += (int(nbytes) + 127) & ~127
+        self.sites.append((off, int(nbytes)))
+        return off
+
+
+def test_data_parallel_plan_buckets_gradients_by_readiness_and_fuses_syncbn(cpu_device, monkeypatch):
+    """world 2: (a) every batch norm is ONE launch with the cross-rank exchange inside (gg_bn_*_fused_dp), each call site with
+    its own arena region, chained in the same order on every rank; (b) parameter gradients are produced inside the
+    optimiser's flat buffer (no pack kernel) in readiness order; (c) one NCCL all-reduce per bucket, each depending only on
+    the kernels that produce its gradients, so the first bucket can overlap the rest of the backward pass; (d) the update is
+    the barrier behind all buckets and divides by the world size"""
     from gg import dist as ggdist
-
-    class FakeSmall(object):
-        MAX_FLOATS = 16384
-
-        def __call__(self, *a):
-            pass
+    arena = _FakeArena()
     monkeypatch.setattr(ggdist, "world_size", lambda: 2)
-    monkeypatch.setattr(ggdist, "small_all_reduce", lambda: FakeSmall())
-    gplan, dplan = _plans(_gmgan(32))
-    for plan in (gplan, dplan):
-        coll = [g for g in plan.groups if g["collective"]]
-        assert len(coll) == 1, "exactly ONE gradient all-reduce per optimiser step"
-        ordered = [i for i, g in enumerate(plan.groups) if g.get("ordered")]
-        assert len(ordered) >= 6                       # SyncBN statistic exchanges (+ the gradient exchange)
-        order, assign, waits, _ = plan._schedule_range([i for i, g in enumerate(plan.groups) if not g["collective"]], 6)
+    monkeypatch.setattr(ggdist, "rank", lambda: 1)
+    monkeypatch.setattr(ggdist, "peer_arena", lambda: arena)
+    monkeypatch.setenv("GG_DP_BUCKETS", "2")
+    g = _gmgan(32)
+    gplan, dplan = _plans(g)
+    names = [n for n, _ in cpu_device]
+    assert "gg_pack_grads" not in names and "gg_bn_stats" not in names
+    assert names.count("gg_bn_fwd_fused_dp") == 0          # launches are recorded at capture / run time, not at plan build
+    # (a) arena regions: disjoint, one per BN forward / backward call site of the two plans
+    assert len(arena.sites) >= 10
+    ends = [o + n for o, n in arena.sites]
+    assert all(arena.sites[i + 1][0] >= ends[i] for i in range(len(ends) - 1))
+    for plan, n_params in ((gplan, None), (dplan, None)):
+        coll = [gi for gi, grp in enumerate(plan.groups) if grp["collective"]]
+        assert len(coll) == 2, "one NCCL all-reduce per readiness bucket"
+        assert all(plan.groups[gi]["ordered"] == "nccl" and not plan.groups[gi]["barrier"] for gi in coll)
+        peer = [gi for gi, grp in enumerate(plan.groups) if grp.get("ordered") == "peer"]
+        if plan is gplan:
+            assert len(peer) >= 8                           # 5 BN layers forward + backward in G / E
+        # (b) most gradient bytes are produced in place
+        (entries, buckets, total), = plan.bucket_plan.values()
+        direct = sum(e["var"].size for e in entries if e["direct"])
+        assert direct > 0.95 * sum(e["var"].size for e in entries), (direct, total)
+        assert [e["off"] for e in entries] == sorted(e["off"] for e in entries)
+        assert [e["ready"] for e in entries] == sorted(e["ready"] for e in entries)
+        assert all(e["off"] % 64 == 0 for e in entries)
+        for e in entries:
+            if e["direct"]:
+                buf, (flat,) = plan.buf[e["own"].id], plan.flat.values()
+                assert buf.data_ptr() == flat.data_ptr() + 4 * e["off"]
+        # (c) dependencies of the first bucket do not include the last backward kernels
+        order, assign, waits, _ = plan._schedule_range(range(len(plan.groups)), 6)
         pos = {gi: i for i, gi in enumerate(order)}
-        seq = [gi for gi in order if plan.groups[gi].get("ordered")]
-        assert seq == sorted(seq, key=lambda gi: pos[gi]) and all(pos[a] < pos[b] for a, b in zip(seq, seq[1:]))
+        first, last = sorted(coll)
+        barrier = [gi for gi, grp in enumerate(plan.groups) if grp["barrier"]][-1]
+        assert pos[first] < pos[barrier] and pos[last] < pos[barrier]
+        deps = _group_deps(plan)
+
+        def closure(gi):
+            seen, stack = set(), [gi]
+            while stack:
+                for d in deps[stack.pop()]:
+                    if d not in seen:
+                        seen.add(d)
+                        stack.append(d)
+            return seen
+        c_first, c_last = closure(first), closure(last)
+        assert len(c_last - c_first) > 5, "the first bucket's all-reduce does not wait for the kernels that only the second needs"
+        # peer-exchange kernels keep one global order
+        seq = [gi for gi in order if plan.groups[gi].get("ordered") == "peer"]
+        assert seq == sorted(seq)
 
 
 ALL_SCRIPTS = {
