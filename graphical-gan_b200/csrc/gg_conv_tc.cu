@@ -18,7 +18,9 @@
 // Operands are fp32 in HBM; the tensor maps use CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 so the TMA unit rounds to tf32
 // (round-to-nearest, measured unbiased) on the way into shared memory; accumulation is fp32 in TMEM.
 //
-// Roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-9 = epilogue.  Round 2 (profiles/
+// Roles (352 threads): warps 0 and 10 = TMA producers (even / odd K blocks: the issue loop of ONE lane — barrier wait,
+// expect_tx, two tensor-map loads, ~400 cycles of dependent uniform-datapath latency — was still the pace of the main
+// loop at 0.21 us per block, above the tensor pipe's 0.135 us), warp 1 = MMA issuer, warps 2-9 = epilogue.  Round 2 (profiles/
 // timeline_conv_r2_baseline.txt) showed every phase of this kernel bound by instruction LATENCY of too few threads rather
 // than by bytes or flops: the producer / issuer loops cost ~0.3 us per 32-wide K block regardless of tile bytes (single
 // divergent lane, shared-memory addresses re-derived per instruction), the 4-warp epilogue took 1.7 us to move a 64 KB
@@ -43,7 +45,7 @@ constexpr int kMaxStages = 6;                  // 6 x 32 KB operand stages + sla
 constexpr int kABytes = 128 * 32 * 4;          // 16 KB: 128 rows (or 4 x 32 MN-blocks) of 32 fp32
 constexpr int kMaxNTile = 128;
 constexpr int kEpiThreads = 256;               // warps 2..9
-constexpr int kThreads = 64 + kEpiThreads;
+constexpr int kThreads = 64 + kEpiThreads + 32; // + warp 10: the second TMA producer
 constexpr int kMaxSplits = 8;                  // portable thread-block-cluster size
 constexpr int kMaxDynSmem = 227 * 1024 - 4096; // dynamic shared memory opt-in (the 227 KB limit includes ~3 KB of static)
 
@@ -241,10 +243,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (p.dbg && threadIdx.x == 0) atomicMin(reinterpret_cast<unsigned long long*>(p.dbg + 201), (unsigned long long)gtime());
 #endif
 
-  if (warp == 0) {
-    // =========================== TMA producer ===========================
+  if (warp == 0 || warp == 10) {
+    // =========================== TMA producers ===========================
     // The whole warp walks the loop (warp-uniform control flow and coordinates); one elected lane issues.  Coordinates
-    // advance incrementally: no integer divisions in the issue loop.
+    // advance incrementally: no integer divisions in the issue loop.  Warp 0 takes the even K blocks, warp 10 the odd ones.
+    const int prod = warp == 0 ? 0 : 1;
     int c_cb = 0, c_s = 0, c_r = 0;          // fwd / dgrad: channel block, tap column, tap row (dgrad: class-local)
     int px_w = 0, px_h = 0, px_b = 0;        // wgrad: pixel-block origin
     int qa_c[4], qa_w[4], qa_h[4];           // wgrad: loop-invariant (ci block, tap offsets) of the 4 A boxes
@@ -273,9 +276,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int xw0 = (MODE == 0) ? w0 * p.stride - p.pad_l : w0 + d_w;
     const int xh0 = (MODE == 0) ? h0 * p.stride - p.pad_t : h0 + d_h;
     const bool leader = elect_one();
-    int s = 0;
+#define GG_ADVANCE()                                                                                             \
+    do {                                                                                                         \
+      if (MODE == 2) {                                                                                           \
+        px_w += p.wt;                                                                                            \
+        if (px_w == p.PW) { px_w = 0; px_h += p.ht; if (px_h == p.PH) { px_h = 0; px_b += p.bt; } }              \
+      } else {                                                                                                   \
+        if (++c_cb == cblocks) {                                                                                 \
+          c_cb = 0;                                                                                              \
+          if (++c_s == row_len) { c_s = 0; ++c_r; }                                                              \
+        }                                                                                                        \
+      }                                                                                                          \
+    } while (0)
+    int s = prod;                                     // kStages >= 2
     uint32_t ph = 0;
-    for (int i = 0; i < nkb; ++i) {
+    if (prod == 1) GG_ADVANCE();
+    for (int i = prod; i < nkb; i += 2) {
       mbar_wait_a(empty0 + 8u * s, ph ^ 1);           // a fresh barrier passes a parity-1 wait: first lap never blocks
       if (leader) {
         const uint32_t sA = ring + (uint32_t)(s * stage_bytes), sB = sA + kABytes, fb = full0 + 8u * s;
@@ -294,17 +310,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tma_load_3d_a(sB, &tmB, fb, 0, (kb0 + i) * 32, n0 / 32);
         }
       }
-      if (MODE == 2) {
-        px_w += p.wt;
-        if (px_w == p.PW) { px_w = 0; px_h += p.ht; if (px_h == p.PH) { px_h = 0; px_b += p.bt; } }
-      } else {
-        if (++c_cb == cblocks) {
-          c_cb = 0;
-          if (++c_s == row_len) { c_s = 0; ++c_r; }
-        }
-      }
-      if (++s == kStages) { s = 0; ph ^= 1; }
+      GG_ADVANCE();
+      GG_ADVANCE();
+      s += 2;
+      if (s >= kStages) { s -= kStages; ph ^= 1; }
     }
+#undef GG_ADVANCE
     __syncwarp();
     if (cl) { cluster_wait(); cluster_arrive(); }      // phase 1 (start-up rendezvous) consumed; arrive for the exit rendezvous
   } else if (warp == 1) {
@@ -428,9 +439,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else {
       // ---- split-K inside the cluster -------------------------------------------------------------------
       // 1. park this CTA's partial tile in its own shared memory as [n_tile/4][128 rows] float4 (conflict-free for the
-      //    thread-per-row TMEM read-out; an owner's column slice is one contiguous block)
-      if (hcols >= 32) {
-        for (int c0 = cw0; c0 < cw0 + hcols; c0 += 32) {
+      //    thread-per-row TMEM read-out; an owner's column slice is one contiguous block) and
+      // 2. PUSH it chunk by chunk: as soon as the four quadrant warps of a column half have parked a 32- (16-) column chunk,
+      //    one of their lanes hands every peer the part of the chunk that lies in ITS slice to the copy engine, so the
+      //    transfer over the SM-to-SM network runs under the rest of the TMEM read-out
+      const int nc = p.n_tile / 4;
+      cbeg = (split * nc) / p.splits;
+      cend = ((split + 1) * nc) / p.splits;
+      const int ncols = cend - cbeg;
+      const uint32_t slot_bytes = (uint32_t)p.ncols_max * 2048u;
+      cluster_wait();                             // start-up rendezvous: every peer's cl_bar is initialised
+      if (et == 0) mbar_expect_tx_a(cl_a, (uint32_t)(p.splits - 1) * (uint32_t)ncols * 2048u);
+      const bool pusher = ((warp - 2) & 3) == 0 && lane == 0;
+      const int cw_chunk = hcols >= 32 ? 32 : 16;
+      for (int c0 = cw0; c0 < cw0 + hcols; c0 += cw_chunk) {
+        if (hcols >= 32) {
           float v[32];
           if (nkb > 0) tmem_ld_32x32(taddr + (uint32_t)c0, v);
           else {
@@ -440,38 +463,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 32; i += 4)
             sts128(ring + (uint32_t)(((c0 + i) >> 2) * 128 + m) * 16u, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
-        }
-      } else {
-        float v[16];
-        if (nkb > 0) tmem_ld_32x16(taddr + (uint32_t)cw0, v);
-        else {
+        } else {
+          float v[16];
+          if (nkb > 0) tmem_ld_32x16(taddr + (uint32_t)c0, v);
+          else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = 0.f;
-        }
+            for (int i = 0; i < 16; ++i) v[i] = 0.f;
+          }
 #pragma unroll
-        for (int i = 0; i < 16; i += 4)
-          sts128(ring + (uint32_t)(((cw0 + i) >> 2) * 128 + m) * 16u, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
-      }
-      fence_proxy_async();                        // generic-proxy writes -> visible to the copy engine
-      cluster_wait();                             // start-up rendezvous: every peer's cl_bar is initialised
-      epi_bar();
-      const int nc = p.n_tile / 4;
-      cbeg = (split * nc) / p.splits;
-      cend = ((split + 1) * nc) / p.splits;
-      const int ncols = cend - cbeg;
-      const uint32_t slot_bytes = (uint32_t)p.ncols_max * 2048u;
-      // 2. one elected thread: expect the peers' slices, push every peer ITS slice of this partial
-      if (et == 0) {
-        mbar_expect_tx_a(cl_a, (uint32_t)(p.splits - 1) * (uint32_t)ncols * 2048u);
-        for (int j = 0; j < p.splits; ++j) {
-          if (j == split) continue;
-          const int cb = (j * nc) / p.splits, ce = ((j + 1) * nc) / p.splits;
-          const int slot = split < j ? split : split - 1;             // slot of source `split` at owner j
-          const uint32_t dst = map_to_cta(ring + (uint32_t)p.land_off + (uint32_t)slot * slot_bytes, (uint32_t)j);
-          bulk_s2c(dst, ring + (uint32_t)cb * 2048u, (uint32_t)(ce - cb) * 2048u, map_to_cta(cl_a, (uint32_t)j));
+          for (int i = 0; i < 16; i += 4)
+            sts128(ring + (uint32_t)(((c0 + i) >> 2) * 128 + m) * 16u, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
         }
-        GG_DBG(129);
+        fence_proxy_async();                      // generic-proxy writes -> visible to the copy engine
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");   // the 4 quadrant warps of this column half
+        if (pusher) {
+          const int c4lo = c0 >> 2, c4hi = (c0 + cw_chunk) >> 2;
+          for (int j = 0; j < p.splits; ++j) {
+            if (j == split) continue;
+            const int cb = (j * nc) / p.splits, ce = ((j + 1) * nc) / p.splits;
+            const int lo = max(cb, c4lo), hi = min(ce, c4hi);
+            if (lo >= hi) continue;
+            const int slot = split < j ? split : split - 1;           // slot of source `split` at owner j
+            const uint32_t dst = map_to_cta(ring + (uint32_t)p.land_off + (uint32_t)slot * slot_bytes + (uint32_t)(lo - cb) * 2048u, (uint32_t)j);
+            bulk_s2c(dst, ring + (uint32_t)lo * 2048u, (uint32_t)(hi - lo) * 2048u, map_to_cta(cl_a, (uint32_t)j));
+          }
+        }
       }
+      if (et == 0) GG_DBG(129);
       // 3. wait for the (splits-1) incoming slices (complete_tx on this CTA's own barrier: the same visibility contract as
       //    a TMA load, so a CTA-scope wait suffices — a cluster-scope acquire would flush the L1), tell the cluster that
       //    nothing targets this CTA any more (exit rendezvous), then reduce the own slice in split order (deterministic)
