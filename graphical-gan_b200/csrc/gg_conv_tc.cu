@@ -217,6 +217,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int kb1 = min(kb_total, kb0 + kb_per);
   const int nkb = max(kb1 - kb0, 0);
 
+  // ---- producer start coordinates (integer divisions: computed by every thread BEFORE the setup barrier so that they overlap
+  //      barrier initialisation and the TMEM allocation instead of delaying the first TMA issue) --------------------------
+  int c_cb = 0, c_s = 0, c_r = 0;          // fwd / dgrad: channel block, tap column, tap row (dgrad: class-local)
+  int px_w = 0, px_h = 0, px_b = 0;        // wgrad: pixel-block origin
+  int qa_c[4], qa_w[4], qa_h[4];           // wgrad: loop-invariant (ci block, tap offsets) of the 4 A boxes
+  if (MODE == 2) {
+    px_w = (kb0 % p.tw) * p.wt;
+    px_h = ((kb0 / p.tw) % p.th) * p.ht;
+    px_b = (kb0 / (p.tw * p.th)) * p.bt;
+    const int qblocks = p.Ci / 32;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int q = mt * 4 + j;
+      if (q >= taps * qblocks) q = taps * qblocks - 1;        // padded rows: valid data, masked at the store
+      const int tap = q / qblocks;
+      qa_c[j] = (q % qblocks) * 32;
+      qa_w[j] = tap % p.k - p.pad_l;
+      qa_h[j] = tap / p.k - p.pad_t;
+    }
+  } else {
+    const int t0 = kb0 / cblocks;
+    c_cb = kb0 % cblocks;
+    const int row_len = (MODE == 0) ? p.k : ns;
+    c_r = t0 / row_len;
+    c_s = t0 % row_len;
+  }
+  const int row_len = (MODE == 0) ? p.k : ns;
+  const int xw0 = (MODE == 0) ? w0 * p.stride - p.pad_l : w0 + d_w;
+  const int xh0 = (MODE == 0) ? h0 * p.stride - p.pad_t : h0 + d_h;
+
   // ---- one-time setup ------------------------------------------------------------------------------------
   if (threadIdx.x == 0) {
     for (int s = 0; s < kMaxStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -248,33 +278,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // The whole warp walks the loop (warp-uniform control flow and coordinates); one elected lane issues.  Coordinates
     // advance incrementally: no integer divisions in the issue loop.  Warp 0 takes the even K blocks, warp 10 the odd ones.
     const int prod = warp == 0 ? 0 : 1;
-    int c_cb = 0, c_s = 0, c_r = 0;          // fwd / dgrad: channel block, tap column, tap row (dgrad: class-local)
-    int px_w = 0, px_h = 0, px_b = 0;        // wgrad: pixel-block origin
-    int qa_c[4], qa_w[4], qa_h[4];           // wgrad: loop-invariant (ci block, tap offsets) of the 4 A boxes
-    if (MODE == 2) {
-      px_w = (kb0 % p.tw) * p.wt;
-      px_h = ((kb0 / p.tw) % p.th) * p.ht;
-      px_b = (kb0 / (p.tw * p.th)) * p.bt;
-      const int qblocks = p.Ci / 32;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        int q = mt * 4 + j;
-        if (q >= taps * qblocks) q = taps * qblocks - 1;        // padded rows: valid data, masked at the store
-        const int tap = q / qblocks;
-        qa_c[j] = (q % qblocks) * 32;
-        qa_w[j] = tap % p.k - p.pad_l;
-        qa_h[j] = tap / p.k - p.pad_t;
-      }
-    } else {
-      const int t0 = kb0 / cblocks;
-      c_cb = kb0 % cblocks;
-      const int row_len = (MODE == 0) ? p.k : ns;
-      c_r = t0 / row_len;
-      c_s = t0 % row_len;
-    }
-    const int row_len = (MODE == 0) ? p.k : ns;
-    const int xw0 = (MODE == 0) ? w0 * p.stride - p.pad_l : w0 + d_w;
-    const int xh0 = (MODE == 0) ? h0 * p.stride - p.pad_t : h0 + d_h;
     const bool leader = elect_one();
 #define GG_ADVANCE()                                                                                             \
     do {                                                                                                         \
@@ -501,20 +504,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t land_a = ring + (uint32_t)p.land_off;
       // the split count is a compile-time constant inside the loop (the generic predicated form cost ~130 instructions per
       // float4 on 8 warps: 0.3 us per item on the timeline)
-#define GG_REDUCE_LOOP(NSP)                                                                                  \
-      for (int idx = et; idx < ncols * 128; idx += kEpiThreads) {                                            \
-        const int c = idx >> 7, row = idx & 127;                                                             \
-        const uint32_t own = ring + (uint32_t)((cbeg + c) * 128 + row) * 16u;                                \
-        const uint32_t inc = land_a + (uint32_t)(c * 128 + row) * 16u;                                       \
-        float4 t[NSP];                                                                                       \
-        _Pragma("unroll")                                                                                    \
-        for (int sp = 0; sp < NSP; ++sp)                                                                     \
-          t[sp] = lds128(sp == split ? own : inc + (uint32_t)(sp < split ? sp : sp - 1) * slot_bytes);       \
-        float4 o = t[0];                                                                                     \
-        _Pragma("unroll")                                                                                    \
-        for (int sp = 1; sp < NSP; ++sp) { o.x += t[sp].x; o.y += t[sp].y; o.z += t[sp].z; o.w += t[sp].w; } \
-        GG_FINISH4(o, (cbeg + c) * 4);                                                                       \
-        sts128(stage_a + (uint32_t)(row * ld + c * 4) * 4u, o);                                              \
+#define GG_REDUCE_LOOP(NSP)                                                                                    \
+      for (int idx = et; idx < ncols * 128; idx += 2 * kEpiThreads) {                                          \
+        const int idx2 = idx + kEpiThreads;                                                                    \
+        const bool two = idx2 < ncols * 128;                                                                   \
+        const int c = idx >> 7, row = idx & 127, c2 = two ? idx2 >> 7 : c, row2 = two ? idx2 & 127 : row;      \
+        const uint32_t own = ring + (uint32_t)((cbeg + c) * 128 + row) * 16u;                                  \
+        const uint32_t inc = land_a + (uint32_t)(c * 128 + row) * 16u;                                         \
+        const uint32_t own2 = ring + (uint32_t)((cbeg + c2) * 128 + row2) * 16u;                               \
+        const uint32_t inc2 = land_a + (uint32_t)(c2 * 128 + row2) * 16u;                                      \
+        float4 t[NSP], u[NSP];                                                                                 \
+        _Pragma("unroll")                                                                                      \
+        for (int sp = 0; sp < NSP; ++sp) {                                                                     \
+          const uint32_t so = (uint32_t)(sp < split ? sp : sp - 1) * slot_bytes;                               \
+          t[sp] = lds128(sp == split ? own : inc + so);                                                        \
+          u[sp] = lds128(sp == split ? own2 : inc2 + so);                                                      \
+        }                                                                                                      \
+        float4 o = t[0], o2 = u[0];                                                                            \
+        _Pragma("unroll")                                                                                      \
+        for (int sp = 1; sp < NSP; ++sp) {                                                                     \
+          o.x += t[sp].x; o.y += t[sp].y; o.z += t[sp].z; o.w += t[sp].w;                                      \
+          o2.x += u[sp].x; o2.y += u[sp].y; o2.z += u[sp].z; o2.w += u[sp].w;                                  \
+        }                                                                                                      \
+        GG_FINISH4(o, (cbeg + c) * 4);                                                                         \
+        GG_FINISH4(o2, (cbeg + c2) * 4);                                                                       \
+        sts128(stage_a + (uint32_t)(row * ld + c * 4) * 4u, o);                                                \
+        if (two) sts128(stage_a + (uint32_t)(row2 * ld + c2 * 4) * 4u, o2);                                    \
       }
       switch (p.splits) {
         case 2: GG_REDUCE_LOOP(2) break;

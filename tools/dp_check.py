@@ -59,6 +59,13 @@ if world > 1:
         torch.distributed.all_reduce(lo_, op=torch.distributed.ReduceOp.MIN)
         torch.distributed.all_reduce(hi_, op=torch.distributed.ReduceOp.MAX)
         assert torch.equal(lo_, hi_), "parameter %s diverged across ranks" % n
+    # in-graph random draws must differ per rank (the rank is mixed into the Philox key): each rank owns ITS slice of the
+    # global noise batch, not a copy of rank 0's
+    z = torch.from_numpy(np.ascontiguousarray(sess.run(g.hyper_p_z))).cuda()
+    zs = [torch.empty_like(z) for _ in range(world)]
+    torch.distributed.all_gather(zs, z)
+    for r in range(1, world):
+        assert not torch.equal(zs[0], zs[r]), "ranks 0 and %d drew identical in-graph noise" % r
 if rank == 0:
     np.savez(args.out, costs=np.array(costs), **snap, **{n.replace('.', '_'): v for n, v in params.items()})
     print("dp_check world=%d costs=%s" % (world, costs))
