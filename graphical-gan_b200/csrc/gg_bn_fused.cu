@@ -427,6 +427,11 @@ extern "C" int gg_bn_bwd_fused(const float* dy, const float* x, const float* y, 
   return bn_bwd_launch(dy, x, y, mean, rstd, gamma, dx, dgamma, dbeta, R, C, act, alpha, dp, stream, "gg_bn_bwd_fused");
 }
 
+extern "C" int gg_bn_fused_grid(int R, int C) {
+  const BnPlan pl = bn_plan(R, C);
+  return pl.ok ? pl.groups * pl.cs : 0;
+}
+
 extern "C" size_t gg_bn_dp_site_bytes(int C, int world) { return (dp_site_bytes(C, world < 1 ? 1 : world) + 127) & ~size_t(127); }
 
 extern "C" int gg_bn_fwd_fused_dp(const float* x, const float* gamma, const float* beta, float eps, float* y, float* mean_out,

@@ -94,6 +94,7 @@ SIGNATURES = {
     "gg_comm_open": (c_i, [c_p, C.POINTER(c_p)]),
     "gg_comm_alloc_bytes": (c_i, [c_sz, C.POINTER(c_p), c_p]),
     "gg_bn_dp_site_bytes": (c_sz, [c_i, c_i]),
+    "gg_bn_fused_grid": (c_i, [c_i, c_i]),
     "gg_bn_fwd_fused_dp": (c_i, [c_p, c_p, c_p, c_f, c_p, c_p, c_p, c_i, c_i, c_i, c_f, C.POINTER(c_p), c_i, c_i, c_ll, c_p]),
     "gg_bn_bwd_fused_dp": (c_i, [c_p] * 9 + [c_i, c_i, c_i, c_f, C.POINTER(c_p), c_i, c_i, c_ll, c_p]),
     "gg_allreduce_small": (c_i, [c_p, c_p, c_i, C.POINTER(c_p), c_i, c_i, c_i, c_p, c_p]),

@@ -725,7 +725,7 @@ class Plan(object):
             xp, gp, bp, yp, mp, rp = (t.data_ptr() for t in (x, gamma, beta, y, mean, rstd))
             peers, rk = arena.peers, ggdist.rank()
             fn = lambda st: cabi.call("gg_bn_fwd_fused_dp", xp, gp, bp, eps, yp, mp, rp, R, Cc, act, alpha, peers, rk, world, site, st)
-            fn.is_small_allreduce = True          # cross-rank rendezvous inside: same order on every rank, one at a time
+            fn.is_small_allreduce = self._bn_dp_ordered(R, Cc)
             self.steps.append(fn)
             return
         S = cabi.lib.gg_bn_slices(R, Cc)
@@ -747,6 +747,18 @@ class Plan(object):
     def _bn_fused(self, R, Cc, world):
         return (world == 1 or not self.rt.sync_bn) and os.environ.get("GG_BN_FUSED", "1") != "0" and \
             cabi.lib.gg_bn_fused_supported(R, Cc) == 1
+
+    @staticmethod
+    def _bn_dp_ordered(R, Cc):
+        """Must the one-launch SyncBN kernels run one at a time in list order (scheduler chain "peer")?  Every call site has
+        its own flags, so concurrent kernels cannot confuse each other; the only hazard is residency: rank A spinning in
+        kernel X while rank B's SMs are full of kernel Y's spinning CTAs.  A kernel of <= 148 CTAs (512 threads, 2+ CTAs per
+        SM) can never fill a GPU, and a training graph has at most two independent batch-norm chains (generator /
+        extractor), so small grids run unordered — chaining them serialised the two chains and cost ~0.2 ms per iteration
+        at N=2 (profiles/dp2_variants_r2.txt).  GG_BN_DP_ORDER=1 forces the chain."""
+        if os.environ.get("GG_BN_DP_ORDER", "0") == "1":
+            return True
+        return cabi.lib.gg_bn_fused_grid(R, Cc) > 148
 
     def _bn_dp_arena(self, R, Cc, world):
         """the peer exchange arena when this batch norm can run as the one-launch data-parallel kernel, else None"""
@@ -778,7 +790,7 @@ class Plan(object):
             peers, rk = arena.peers, ggdist.rank()
             fn = lambda st: cabi.call("gg_bn_bwd_fused_dp", gyp, xp, yp, mp, rp, gp, dxp, dgp, dbp, R, Cc, act, alpha, peers, rk,
                                       world, site, st)
-            fn.is_small_allreduce = True
+            fn.is_small_allreduce = self._bn_dp_ordered(R, Cc)
             self.steps.append(fn)
             return
         S = cabi.lib.gg_bn_slices(R, Cc)

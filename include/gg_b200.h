@@ -276,6 +276,8 @@ int gg_comm_alloc_bytes(size_t bytes, void** buf_out, void* ipc_handle_out_64);
  * 128-byte aligned, the same offset on every rank, never shared between two call sites).  Every rank must launch the same
  * call sites the same number of times.  dgamma / dbeta are the LOCAL sums (the gradient all-reduce totals them). */
 size_t gg_bn_dp_site_bytes(int C, int world);
+/* CTAs of the one-launch batch-norm kernels for an [R, C] input (0: unsupported shape) */
+int gg_bn_fused_grid(int R, int C);
 int gg_bn_fwd_fused_dp(const float* x, const float* gamma, const float* beta, float eps, float* y, float* mean_out,
                        float* rstd_out, int R, int C, int act, float alpha, void* const* peer_arenas_host, int rank, int world,
                        long long site_offset, void* stream);

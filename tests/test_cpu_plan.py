@@ -169,6 +169,12 @@ def test_data_parallel_plan_buckets_gradients_by_readiness_and_fuses_syncbn(cpu_
     monkeypatch.setenv("GG_DP_BUCKETS", "2")
     g = _gmgan(32)
     gplan, dplan = _plans(g)
+    # default: the SyncBN kernels of this model are small grids (<= 148 CTAs) and run UNordered — chaining them would
+    # serialise the generator's and the extractor's batch-norm chains
+    assert not [grp for grp in gplan.groups if grp.get("ordered") == "peer"]
+    monkeypatch.setenv("GG_BN_DP_ORDER", "1")
+    g = _gmgan(32)
+    gplan, dplan = _plans(g)
     names = [n for n, _ in cpu_device]
     assert "gg_pack_grads" not in names and "gg_bn_stats" not in names
     assert names.count("gg_bn_fwd_fused_dp") == 0          # launches are recorded at capture / run time, not at plan build

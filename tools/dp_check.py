@@ -71,4 +71,4 @@ if rank == 0:
     print("dp_check world=%d costs=%s" % (world, costs))
 if world > 1:
     torch.distributed.barrier()
-    torch.distributed.destroy_process_group()
+    ggdist.shutdown()      # drops the captured graphs (NCCL nodes inside) BEFORE the process group goes away

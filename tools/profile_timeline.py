@@ -15,6 +15,9 @@ from torch.profiler import profile, ProfilerActivity
 import tensorflow as tf
 import gmgan_inference_cifar10 as S
 from gg.executor import RT
+from gg import dist as ggdist, cabi
+
+rank, world = ggdist.init_from_env()     # under torchrun: the data-parallel step of THIS rank (rank 0 prints)
 
 which = sys.argv[1] if len(sys.argv) > 1 else "gen"
 np.random.seed(1234)
@@ -28,10 +31,22 @@ for i in range(6):
         RT.run(fet[k], {g.real_x_int: batches[i % 4]}, to_host=False)
 torch.cuda.synchronize()
 plan = RT.plans[[q for q in RT.plans if q[0][0] == fet[which][0].id][0]]
+def replay():
+    for seg in plan.graph:
+        if callable(seg):
+            seg(cabi.stream_ptr())
+        else:
+            seg.replay()
+
+
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     for r in range(3):
-        plan.graph[0].replay()
+        replay()
         torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+if rank != 0:
+    sys.exit(0)
 evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and "memcpy" not in e.name.lower() and "memset" not in e.name.lower()]
 evs.sort(key=lambda e: e.time_range.start)
 n = len(evs) // 3
