@@ -151,6 +151,10 @@ def shutdown():
     try:
         import torch
         from . import executor
+        for plan in executor.ALL_PLANS:      # module-level references to a Plan must not keep its graphs alive
+            plan.graph = None
+            plan.keep = []
+        del executor.ALL_PLANS[:]
         executor.RT.plans.clear()
         gc.collect()
         if torch.cuda.is_available():

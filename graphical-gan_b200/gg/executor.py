@@ -154,6 +154,7 @@ class Runtime(object):
 
 
 RT = Runtime()
+ALL_PLANS = []      # every Plan ever built: gg.dist.shutdown() drops their captured graphs before NCCL goes away
 
 
 def reset_runtime():
@@ -206,6 +207,7 @@ class Plan(object):
             if isinstance(f, Operation):
                 self._emit_operation(f)
         self.graph = None
+        ALL_PLANS.append(self)
         self.trace, self.trace_t0 = [], None
         self.kernel_launches = 0   # libgg_b200 kernels per run (counted at capture / eager launch)
         self.runs = 0
@@ -1023,10 +1025,19 @@ class Plan(object):
         free_at = [0.0] * n_streams
         finish, assign, waits, need_event, order, issued = {}, {}, {}, set(), [], {}
         sync_cost = 1.0                       # a cross-stream edge costs an event wait
+        # Streams are FIFOs and list scheduling cannot back-fill: a low-priority group (a gradient bucket's all-reduce has
+        # only the update behind it) is issued late and would queue behind whatever its stream already holds — the round-2
+        # timeline showed both bucket all-reduces starting after the LAST backward kernel.  Collectives therefore get a
+        # stream of their own: in the captured graph they depend on exactly their producers.
+        has_coll = any(self.groups[gi]["collective"] for gi in idxs)
+        comm_stream = n_streams - 1 if (has_coll and n_streams > 2) else None
         while ready:
             _, _, gi = heapq.heappop(ready)
             best = None
+            is_coll = self.groups[gi]["collective"]
             for s in range(n_streams):
+                if comm_stream is not None and (s == comm_stream) != bool(is_coll):
+                    continue
                 t = free_at[s]
                 for d in deps[gi]:
                     t = max(t, finish[d] + (0.0 if assign[d] == s else sync_cost))
