@@ -36,10 +36,10 @@ struct DpCtx {
   int rank, world;
   int C;                     // channels (layout of the region)
 };
-// region layout: [groups_max] epoch counters | [groups_max][world] flags | [2 parities][world][C] double2 sums
+// region layout: [groups_max] epoch counters | [2 parities][world][C][2] 8-byte words {fp32 payload, epoch}
 __host__ __device__ inline size_t dp_groups_max(int C) { return (size_t)(C + 3) / 4; }
 __host__ __device__ inline size_t dp_flags_off(int C) { return ((dp_groups_max(C) * 4 + 127) / 128) * 128; }
-__host__ __device__ inline size_t dp_data_off(int C, int world) { return dp_flags_off(C) + ((dp_groups_max(C) * world * 4 + 127) / 128) * 128; }
+__host__ __device__ inline size_t dp_data_off(int C, int world) { (void)world; return dp_flags_off(C); }
 __host__ __device__ inline size_t dp_site_bytes(int C, int world) { return dp_data_off(C, world) + (size_t)2 * world * C * 16; }
 
 struct BnPlan {
@@ -84,7 +84,14 @@ __device__ __forceinline__ double2 ld_dsmem_f64x2(const double* local_ptr, uint3
   return make_double2(ld_dsmem_f64(local_ptr, cta_rank), ld_dsmem_f64(local_ptr + 1, cta_rank));
 }
 
-// Cross-GPU total of the cluster totals held by threads 0..cw-1 of the cluster's rank-0 CTA (see the file header).
+// Cross-GPU total of the cluster totals held by threads 0..cw-1 of the cluster's rank-0 CTA.
+// Low-latency protocol (the idea of NCCL's LL): every 8-byte word carries 4 bytes of payload and the 4-byte epoch, and an
+// aligned 8-byte store is delivered whole over NVLink — so the data IS the flag: no system-scope fence, no separate flag
+// round trip (the fence + flag form measured +11.6 us per launch on 2 B200s, profiles/dp_bn_r2.txt; a kernel is only
+// 3-10 us long).  Thread t pushes {sum_t, e} and {sumsq_t, e} of its channel into slot [parity][my rank] of EVERY rank's
+// arena (fire and forget) and then polls the P x 2 words of its channel in its OWN arena until they carry epoch e.  The
+// sums travel as fp32 (the per-rank partials are exact to 6e-8 relative; they are totalled in double).  A slot is
+// rewritten two epochs later, which a peer can only reach after this rank has consumed the current one.
 __device__ __forceinline__ void dp_exchange(const DpCtx& dp, int group, int c0, int cw, double& ta, double& tb) {
   const int tid = threadIdx.x;            // called by warp 0 only (cw <= 32)
   const int P = dp.world;
@@ -98,36 +105,30 @@ __device__ __forceinline__ void dp_exchange(const DpCtx& dp, int group, int c0, 
   e = __shfl_sync(0xffffffffu, e, 0);
   const size_t par = (size_t)(e & 1u);
   const int ch = c0 + tid;
-  const bool ch_ok = tid < cw && ch < dp.C;
-  if (ch_ok) {
+  if (tid < cw && ch < dp.C) {
+    const uint2 wa = make_uint2(__float_as_uint((float)ta), e), wb = make_uint2(__float_as_uint((float)tb), e);
     for (int r = 0; r < P; ++r) {
-      double2* d = reinterpret_cast<double2*>(reinterpret_cast<uint8_t*>(dp.peer[r]) + dp.site_off + dp_data_off(dp.C, P)) +
-                   (par * P + dp.rank) * dp.C + ch;
-      *d = make_double2(ta, tb);
+      uint2* d = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(dp.peer[r]) + dp.site_off + dp_data_off(dp.C, P)) +
+                 ((par * P + dp.rank) * dp.C + ch) * 2;
+      asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(d), "r"(wa.x), "r"(wa.y) : "memory");
+      asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(d + 1), "r"(wb.x), "r"(wb.y) : "memory");
     }
-  }
-  __threadfence_system();
-  __syncwarp();
-  if (tid < P) {
-    unsigned* f = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(dp.peer[tid]) + dp.site_off + dp_flags_off(dp.C)) +
-                  (size_t)group * P + dp.rank;
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(e) : "memory");
-    const unsigned* w = reinterpret_cast<const unsigned*>(mine + dp_flags_off(dp.C)) + (size_t)group * P + tid;
-    unsigned seen, spins = 0;
-    do {
-      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(w) : "memory");
-      if ((int)(seen - e) < 0 && ++spins > (1u << 27)) __trap();
-    } while ((int)(seen - e) < 0);
-  }
-  __syncwarp();
-  if (ch_ok) {
-    const double2* d = reinterpret_cast<const double2*>(mine + dp_data_off(dp.C, P)) + par * P * dp.C + ch;
+    const uint2* src = reinterpret_cast<const uint2*>(mine + dp_data_off(dp.C, P)) + (par * P * dp.C + ch) * 2;
     ta = 0.0; tb = 0.0;
     for (int r = 0; r < P; ++r) {          // rank order: identical totals on every GPU
-      const double2 v = __ldcv(d + (size_t)r * dp.C);
-      ta += v.x; tb += v.y;
+      const uint2* w = src + (size_t)r * dp.C * 2;
+      uint2 va, vb;
+      unsigned spins = 0;
+      do {
+        asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(va.x), "=r"(va.y) : "l"(w) : "memory");
+        asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(vb.x), "=r"(vb.y) : "l"(w + 1) : "memory");
+        if ((va.y != e || vb.y != e) && ++spins > (1u << 27)) __trap();     // a lost peer traps instead of hanging the GPU
+      } while (va.y != e || vb.y != e);
+      ta += (double)__uint_as_float(va.x);
+      tb += (double)__uint_as_float(vb.x);
     }
   }
+  __syncwarp();
 }
 
 template <int Q>
