@@ -388,7 +388,7 @@ class Plan(object):
                 if d is not None:
                     uses[d.id] = uses.get(d.id, 0) + 1
         direct = os.environ.get("GG_DP_DIRECT", "1") != "0"
-        n_buckets = max(1, int(os.environ.get("GG_DP_BUCKETS", "2")))
+        n_buckets = max(1, int(os.environ.get("GG_DP_BUCKETS", "4")))
         for op in opts:
             entries = []
             for v, g in zip(op.attrs["vars"], op.deps):
