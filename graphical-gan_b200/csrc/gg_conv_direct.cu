@@ -25,6 +25,9 @@ int conv_small_fwd(const float* x, const float* w, const float* bias, float* y, 
                    int stride, int pad_t, int pad_l, int Ho, int Wo, int act, float alpha, cudaStream_t st, bool* handled);
 int conv_small_dgrad(const float* dy, const float* w, const float* bias, float* dx, int B, int H, int W, int Ci, int Co, int k,
                      int stride, int pad_t, int pad_l, int Ho, int Wo, int act, float alpha, cudaStream_t st, bool* handled);
+int conv_small_wgrad(const float* x, const float* dy, float* dw, int B, int H, int W, int Ci, int Co, int k, int stride, int pad_t,
+                     int pad_l, int Ho, int Wo, void* ws, size_t ws_bytes, cudaStream_t st, bool* handled);
+size_t conv_small_wgrad_workspace(int B, int H, int W, int Ci, int Co, int k, int stride, int Ho, int Wo);
 }  // namespace gg
 
 namespace {
@@ -430,6 +433,8 @@ extern "C" size_t gg_conv2d_wgrad_workspace(int B, int H, int W, int Ci, int Co,
   size_t tc = conv_tc_wgrad_workspace(B, H, W, Ci, Co, k, stride, Ho, Wo);
   SmallCi sc = smallci_plan(2, p);
   if (sc.ok && sc.tc_bytes + sc.p_bytes > tc) tc = sc.tc_bytes + sc.p_bytes;
+  size_t small = conv_small_wgrad_workspace(B, H, W, Ci, Co, k, stride, Ho, Wo);
+  if (small > tc) tc = small;
   return direct > tc ? direct : tc;
 }
 
@@ -470,6 +475,12 @@ extern "C" int gg_conv2d_wgrad(const float* x, const float* dy, float* dw, int B
   int rc = check_geom(p, "gg_conv2d_wgrad");
   if (rc) return rc;
   cudaStream_t st = as_stream(stream);
+  if (g_conv_backend != 1) {
+    bool handled = false;
+    rc = conv_small_wgrad(x, dy, dw, B, H, W, Ci, Co, k, stride, pad_t, pad_l, Ho, Wo, workspace, workspace_bytes, st, &handled);
+    if (rc) return rc;
+    if (handled) { g_last_backend = 0; return GG_OK; }
+  }
   {
     SmallCi sc = smallci_plan(2, p);
     if (sc.ok && workspace != nullptr && workspace_bytes >= sc.tc_bytes + sc.p_bytes) {

@@ -362,6 +362,259 @@ __global__ void __launch_bounds__(128) conv_small_dgrad_kernel(const float* __re
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// wgrad (filter gradient) for CI <= 4 input channels: ONE launch, no patch matrix
+// ---------------------------------------------------------------------------------------------------------------------
+// dw[(r*k+s)*CI+c][co] = sum over (b, ho, wo) of x[b, ho*st+r-pad_t, wo*st+s-pad_l, c] * dy[b, ho, wo, co]
+// (gradient of tf.nn.conv2d w.r.t. its HWIO filter, tflib/ops/conv2d.py:106).  K = k*k*CI <= 100 rows x Co columns is a tiny
+// output reduced over B*Ho*Wo = 10^4..10^5 pixels: 0.3 GFLOP against 10 MB of activations read ONCE.  It used to run as patch
+// matrix + tcgen05 GEMM with M = 75 of 128 rows used, a single output tile and hence at most 8 split-K CTAs: 14 + 26 us at the
+// tail of both steps (profiles/time_conv_r2.txt).  Here the PIXELS are split over the whole machine:
+//   unit    = RH output rows of one image; its x patch and dy rows are staged in shared memory once;
+//   thread  = 5 filter rows (tap, c) x 8 output channels = 40 fp32 accumulators held over every unit the CTA walks;
+//             per pixel 5 broadcast LDS.32 (x) + 2 LDS.128 (dy) feed 40 FMAs; the pixels of a unit are split over PS thread
+//             groups that are folded in a fixed order through shared memory;
+//   cluster = 8 CTAs fold their [K][Co] tiles through distributed shared memory (rank r owns an eighth of the floats and
+//             adds the eight copies in rank order), one partial per cluster goes to the L2 workspace, and the LAST cluster to
+//             arrive (self-resetting ticket at the start of the workspace) folds the partials in cluster order into dw.
+// Every sum has a fixed order: the result is bit-reproducible and independent of scheduling.
+constexpr int kWgTK = 5;            // filter rows per thread
+constexpr int kWgCL = 8;            // CTAs per cluster
+constexpr int kWgMaxClusters = 18;  // 18 x 8 = 144 of 148 SMs, one CTA per SM
+
+__device__ __forceinline__ uint32_t wg_cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t wg_cluster_id() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void wg_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float4 wg_ld_dsmem_f4(const float* local_ptr, uint32_t cta_rank) {
+  uint32_t local = (uint32_t)__cvta_generic_to_shared(local_ptr), remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(cta_rank));
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(remote) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t wg_ld_dsmem_u32(const uint32_t* local_ptr, uint32_t cta_rank) {
+  uint32_t local = (uint32_t)__cvta_generic_to_shared(local_ptr), remote, v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(cta_rank));
+  asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(remote) : "memory");
+  return v;
+}
+
+struct WgPlan {
+  bool ok;
+  int RH, units_per_img, units, PH, PW, NT, PS, threads, clusters;
+  size_t sx_floats, tile_floats, smem, ws_bytes;
+};
+
+template <int CI>
+__global__ void __launch_bounds__(512) conv_small_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                               float* __restrict__ dw, float* __restrict__ part,
+                                                               unsigned* __restrict__ ticket, SmallP p, int RH, int units_per_img,
+                                                               int units, int PH, int PW, int NT, int PS, int sx_floats) {
+  GG_PDL_ENTRY();
+  extern __shared__ __align__(16) float smem_f[];
+  __shared__ uint32_t s_last;
+  float* sx = smem_f;                                   // [PH][PW][CI] input patch, TF SAME padding as zeros
+  float* sdy = smem_f + sx_floats;                      // [RH*Wo][Co] dy rows of the unit; later the CTA's [K][Co] tile
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int K = p.k * p.k * CI, Co = p.Co, N = K * Co;
+  const int nq8 = Co >> 3;                              // channel octets: quads q and q + nq8
+  const int NPIX = RH * p.Wo;
+  const bool worker = tid < NT * PS;
+  const int ps = worker ? tid / NT : 0, tt = worker ? tid % NT : 0;
+  const int g = tt / nq8, q = tt % nq8;
+  int off[kWgTK];
+#pragma unroll
+  for (int j = 0; j < kWgTK; ++j) {
+    const int kk = g * kWgTK + j;
+    const int tap = kk / CI, c = kk % CI;
+    off[j] = (kk < K) ? ((tap / p.k) * PW + (tap % p.k)) * CI + c : 0;
+  }
+  float acc[kWgTK][8];
+#pragma unroll
+  for (int j = 0; j < kWgTK; ++j)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
+  const int PP = (NPIX + PS - 1) / PS;
+  const int p_lo = ps * PP, p_hi = min(NPIX, p_lo + PP);
+
+  for (int u = blockIdx.x; u < units; u += gridDim.x) {
+    const int b = u / units_per_img, ho0 = (u % units_per_img) * RH;
+    const int rows = min(RH, p.Ho - ho0);
+    if (u != (int)blockIdx.x) __syncthreads();          // previous unit's readers are done with the tiles
+    // x patch
+    const int hi0 = ho0 * p.stride - p.pad_t, wi0 = -p.pad_l;
+    const float* xb = x + (size_t)b * p.H * p.W * CI;
+    const int nx = PH * PW * CI;
+    for (int base = tid; base < nx; base += 4 * nthr) {
+      float v[4];
+#pragma unroll
+      for (int uu = 0; uu < 4; ++uu) {
+        const int i = base + uu * nthr;
+        const int c = i % CI, iw = (i / CI) % PW, ih = i / (CI * PW);
+        const int hi = hi0 + ih, wi = wi0 + iw;
+        v[uu] = 0.f;
+        if (i < nx && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W) v[uu] = xb[((size_t)hi * p.W + wi) * CI + c];
+      }
+#pragma unroll
+      for (int uu = 0; uu < 4; ++uu) {
+        const int i = base + uu * nthr;
+        if (i < nx) sx[i] = v[uu];
+      }
+    }
+    // dy rows ho0 .. ho0+rows-1 of image b are one contiguous run; rows past Ho are zeros
+    const float4* dsrc = reinterpret_cast<const float4*>(dy + ((size_t)b * p.Ho + ho0) * p.Wo * Co);
+    const int nvalid = rows * p.Wo * (Co >> 2), nall = NPIX * (Co >> 2);
+    float4* sdy4 = reinterpret_cast<float4*>(sdy);
+    for (int base = tid; base < nall; base += 8 * nthr) {
+      float4 v[8];
+#pragma unroll
+      for (int uu = 0; uu < 8; ++uu) {
+        const int i = base + uu * nthr;
+        v[uu] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < nvalid) v[uu] = dsrc[i];
+      }
+#pragma unroll
+      for (int uu = 0; uu < 8; ++uu) {
+        const int i = base + uu * nthr;
+        if (i < nall) sdy4[i] = v[uu];
+      }
+    }
+    __syncthreads();
+    if (worker) {
+      int pr = p_lo / p.Wo, wo = p_lo % p.Wo;
+      const float4* dq = sdy4 + q;
+      const int cq4 = Co >> 2;
+#pragma unroll 2
+      for (int pix = p_lo; pix < p_hi; ++pix) {
+        const float* xp = sx + ((pr * p.stride) * PW + wo * p.stride) * CI;
+        const float4 d0 = dq[pix * cq4], d1 = dq[pix * cq4 + nq8];
+        float xv[kWgTK];
+#pragma unroll
+        for (int j = 0; j < kWgTK; ++j) xv[j] = xp[off[j]];
+#pragma unroll
+        for (int j = 0; j < kWgTK; ++j) {
+          acc[j][0] = fmaf(xv[j], d0.x, acc[j][0]); acc[j][1] = fmaf(xv[j], d0.y, acc[j][1]);
+          acc[j][2] = fmaf(xv[j], d0.z, acc[j][2]); acc[j][3] = fmaf(xv[j], d0.w, acc[j][3]);
+          acc[j][4] = fmaf(xv[j], d1.x, acc[j][4]); acc[j][5] = fmaf(xv[j], d1.y, acc[j][5]);
+          acc[j][6] = fmaf(xv[j], d1.z, acc[j][6]); acc[j][7] = fmaf(xv[j], d1.w, acc[j][7]);
+        }
+        if (++wo == p.Wo) { wo = 0; ++pr; }
+      }
+    }
+  }
+  __syncthreads();
+  // fold the PS pixel groups into the CTA's [K][Co] tile (group order), aliased over the dy rows
+  float* sacc = sdy;
+  for (int i = tid; i < N; i += nthr) sacc[i] = 0.f;
+  for (int s = 0; s < PS; ++s) {
+    __syncthreads();
+    if (worker && ps == s) {
+#pragma unroll
+      for (int j = 0; j < kWgTK; ++j) {
+        const int kk = g * kWgTK + j;
+        if (kk < K) {
+          float4* r0 = reinterpret_cast<float4*>(sacc + kk * Co + q * 4);
+          float4* r1 = reinterpret_cast<float4*>(sacc + kk * Co + (q + nq8) * 4);
+          float4 a = *r0, c4 = *r1;
+          a.x += acc[j][0]; a.y += acc[j][1]; a.z += acc[j][2]; a.w += acc[j][3];
+          c4.x += acc[j][4]; c4.y += acc[j][5]; c4.z += acc[j][6]; c4.w += acc[j][7];
+          *r0 = a; *r1 = c4;
+        }
+      }
+    }
+  }
+  // cluster fold through distributed shared memory: rank r owns float4s [r*per, (r+1)*per)
+  const uint32_t rank = wg_cluster_ctarank(), cid = wg_cluster_id();
+  const int nclusters = gridDim.x / kWgCL;
+  const int n4 = N >> 2, per = (n4 + kWgCL - 1) / kWgCL;
+  const int lo4 = rank * per, hi4 = min(n4, lo4 + per);
+  wg_cluster_sync();
+  float4* out4 = reinterpret_cast<float4*>(nclusters == 1 ? dw : part + (size_t)cid * N);
+  for (int i = lo4 + tid; i < hi4; i += nthr) {
+    float4 t = wg_ld_dsmem_f4(sacc + i * 4, 0);
+#pragma unroll
+    for (uint32_t r = 1; r < (uint32_t)kWgCL; ++r) {
+      const float4 v = wg_ld_dsmem_f4(sacc + i * 4, r);
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    out4[i] = t;
+  }
+  if (nclusters == 1) {
+    wg_cluster_sync();                                  // peers may still be reading this CTA's tile
+    return;
+  }
+  __threadfence();
+  wg_cluster_sync();                                    // every rank's slice of the partial is written and fenced
+  if (rank == 0 && tid == 0) {
+    const unsigned t = atomicAdd(ticket, 1u);
+    const bool last = (t == (unsigned)nclusters - 1u);
+    if (last) *ticket = 0u;                             // self-resetting: the next launch starts from zero again
+    __threadfence();
+    s_last = last ? 1u : 0u;
+  }
+  wg_cluster_sync();
+  const uint32_t last = wg_ld_dsmem_u32(&s_last, 0);
+  wg_cluster_sync();                                    // rank 0 keeps its shared memory alive until every rank has read
+  if (!last) return;
+  __threadfence();
+  float4* dw4 = reinterpret_cast<float4*>(dw);
+  for (int i = lo4 + tid; i < hi4; i += nthr) {
+    float4 t = __ldcg(reinterpret_cast<const float4*>(part) + i);
+    for (int c = 1; c < nclusters; ++c) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(part + (size_t)c * N) + i);
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    dw4[i] = t;
+  }
+}
+
+WgPlan wgrad_plan(int B, int H, int W, int Ci, int Co, int k, int stride, int Ho, int Wo) {
+  WgPlan pl{};
+  pl.ok = false;
+  (void)H; (void)W;
+  if (Ci < 1 || Ci > 4 || Co % 8 != 0 || Co > 256 || k > 7 || stride < 1 || stride > 2 || B > (1 << 20)) return pl;
+  const int K = k * k * Ci;
+  if (K > 100) return pl;
+  int rh_max = 16384 / (Wo * Co);                       // dy rows of a unit: at most 64 KB of shared memory
+  if (rh_max < 1) return pl;
+  int RH = Ho < rh_max ? Ho : rh_max;
+  while (RH > 1 && (long long)B * ((Ho + RH - 1) / RH) < 128) RH = (RH + 1) / 2;
+  pl.RH = RH;
+  pl.units_per_img = (Ho + RH - 1) / RH;
+  pl.units = B * pl.units_per_img;
+  pl.PH = (RH - 1) * stride + k;
+  pl.PW = (Wo - 1) * stride + k;
+  pl.NT = ((K + kWgTK - 1) / kWgTK) * (Co / 8);
+  if (pl.NT > 512) return pl;
+  pl.PS = 512 / pl.NT;
+  if (pl.PS > 4) pl.PS = 4;
+  if (pl.PS > RH * Wo) pl.PS = RH * Wo;
+  pl.threads = ((pl.NT * pl.PS + 31) / 32) * 32;
+  if (pl.threads < 128) pl.threads = 128;
+  pl.sx_floats = (((size_t)pl.PH * pl.PW * Ci + 3) / 4) * 4;
+  const size_t tile = (size_t)RH * Wo * Co, accs = (size_t)K * Co;
+  pl.tile_floats = tile > accs ? tile : accs;
+  pl.smem = (pl.sx_floats + pl.tile_floats) * sizeof(float);
+  if (pl.smem > 200 * 1024) return pl;
+  int clusters = (pl.units + kWgCL - 1) / kWgCL;
+  if (clusters > kWgMaxClusters) clusters = kWgMaxClusters;
+  pl.clusters = clusters;
+  pl.ws_bytes = 256 + (size_t)clusters * accs * sizeof(float);
+  pl.ok = true;
+  return pl;
+}
+
 bool small_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -431,6 +684,69 @@ int conv_small_dgrad(const float* dy, const float* w, const float* bias, float* 
   }
   *handled = true;
   return check_launch("gg_conv2d_dgrad(small-channel)");
+}
+
+size_t conv_small_wgrad_workspace(int B, int H, int W, int Ci, int Co, int k, int stride, int Ho, int Wo) {
+  if (!small_enabled()) return 0;
+  const WgPlan pl = wgrad_plan(B, H, W, Ci, Co, k, stride, Ho, Wo);
+  return pl.ok ? pl.ws_bytes : 0;
+}
+
+// filter gradient of a conv with Ci <= 4.  The first 256 bytes of the workspace hold the arrival ticket: they must be zero
+// before the FIRST launch that uses the workspace (the kernel leaves them zero again).
+int conv_small_wgrad(const float* x, const float* dy, float* dw, int B, int H, int W, int Ci, int Co, int k, int stride, int pad_t,
+                     int pad_l, int Ho, int Wo, void* ws, size_t ws_bytes, cudaStream_t st, bool* handled) {
+  *handled = false;
+  if (!small_enabled()) return GG_OK;
+  const WgPlan pl = wgrad_plan(B, H, W, Ci, Co, k, stride, Ho, Wo);
+  if (!pl.ok || ws == nullptr || ws_bytes < pl.ws_bytes) return GG_OK;
+  SmallP p{B, H, W, Ci, Co, k, stride, pad_t, pad_l, Ho, Wo};
+  unsigned* ticket = reinterpret_cast<unsigned*>(ws);
+  float* part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + 256);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(pl.clusters * kWgCL));
+  cfg.blockDim = dim3((unsigned)pl.threads);
+  cfg.dynamicSmemBytes = pl.smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  attr[na].id = cudaLaunchAttributeClusterDimension;
+  attr[na].val.clusterDim.x = kWgCL;
+  attr[na].val.clusterDim.y = 1;
+  attr[na].val.clusterDim.z = 1;
+  ++na;
+  if (g_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  cudaError_t e = cudaSuccess;
+#define GG_WG(CI_)                                                                                                          \
+  do {                                                                                                                      \
+    static bool attr_set = false;                                                                                           \
+    if (!attr_set) {                                                                                                        \
+      e = cudaFuncSetAttribute(conv_small_wgrad_kernel<CI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);      \
+      attr_set = (e == cudaSuccess);                                                                                        \
+    }                                                                                                                       \
+    if (e == cudaSuccess)                                                                                                   \
+      e = cudaLaunchKernelEx(&cfg, conv_small_wgrad_kernel<CI_>, x, dy, dw, part, ticket, p, pl.RH, pl.units_per_img,       \
+                             pl.units, pl.PH, pl.PW, pl.NT, pl.PS, (int)pl.sx_floats);                                      \
+  } while (0)
+  switch (Ci) {
+    case 1: GG_WG(1); break;
+    case 2: GG_WG(2); break;
+    case 3: GG_WG(3); break;
+    default: GG_WG(4); break;
+  }
+#undef GG_WG
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(GG_ERR_CUDA_BASE + (int)e, "gg_conv2d_wgrad(small-channel): launch failed%s");
+  }
+  *handled = true;
+  return check_launch("gg_conv2d_wgrad(small-channel)");
 }
 
 }  // namespace gg

@@ -67,27 +67,103 @@ def emu_fwd(x,w,B,H,W,Ci,Co,k,s,pt,pl,Ho,Wo):
             if ho<Ho and wo<Wo: y[b,ho,wo]=acc
     assert not np.isnan(y).any()
     return y
+def wgrad_plan(B,H,W,Ci,Co,k,s,Ho,Wo):
+    """mirror of wgrad_plan() in csrc/gg_conv_small.cu"""
+    TK,CL,MAXC=5,8,18
+    K=k*k*Ci
+    assert 1<=Ci<=4 and Co%8==0 and K<=100
+    rh_max=16384//(Wo*Co); assert rh_max>=1
+    RH=min(Ho,rh_max)
+    while RH>1 and B*(-(-Ho//RH))<128: RH=(RH+1)//2
+    upi=-(-Ho//RH); units=B*upi
+    PH=(RH-1)*s+k; PW=(Wo-1)*s+k
+    NT=(-(-K//TK))*(Co//8); assert NT<=512
+    PS=min(512//NT,4,RH*Wo)
+    threads=max(128,-(-NT*PS//32)*32)
+    clusters=min(-(-units//CL),MAXC)
+    return dict(RH=RH,upi=upi,units=units,PH=PH,PW=PW,NT=NT,PS=PS,threads=threads,grid=clusters*CL,clusters=clusters)
+def emu_wgrad(x,dy,B,H,W,Ci,Co,k,s,pt,pl,Ho,Wo):
+    """thread-by-thread emulation of conv_small_wgrad_kernel: units, x patch / dy rows in 'shared memory', the (5 filter rows x
+    8 channels) register tile, pixel groups, the CTA fold, the cluster fold by float4 slices and the last-cluster fold"""
+    P=wgrad_plan(B,H,W,Ci,Co,k,s,Ho,Wo)
+    RH,upi,units,PH,PW,NT,PS,grid,ncl=P['RH'],P['upi'],P['units'],P['PH'],P['PW'],P['NT'],P['PS'],P['grid'],P['clusters']
+    K=k*k*Ci; N=K*Co; nq8=Co//8; NPIX=RH*Wo; PP=-(-NPIX//PS)
+    tiles=np.zeros((grid,N))
+    for cta in range(grid):
+        accs=np.zeros((NT*PS,5,8))
+        for u in range(cta,units,grid):
+            b=u//upi; ho0=(u%upi)*RH; rows=min(RH,Ho-ho0)
+            hi0=ho0*s-pt; wi0=-pl
+            sx=np.zeros(PH*PW*Ci)
+            for i in range(PH*PW*Ci):
+                c=i%Ci; iw=(i//Ci)%PW; ih=i//(Ci*PW); hi,wi=hi0+ih,wi0+iw
+                if 0<=hi<H and 0<=wi<W: sx[i]=x[b,hi,wi,c]
+            sdy=np.zeros(NPIX*Co)
+            flat=dy[b].reshape(-1)
+            nvalid=rows*Wo*Co
+            sdy[:nvalid]=flat[ho0*Wo*Co:ho0*Wo*Co+nvalid]
+            for tid in range(NT*PS):
+                ps,tt=tid//NT,tid%NT; g,q=tt//nq8,tt%nq8
+                off=[]
+                for j in range(5):
+                    kk=g*5+j; tap,c=kk//Ci,kk%Ci
+                    off.append(((tap//k)*PW+(tap%k))*Ci+c if kk<K else 0)
+                p_lo=ps*PP; p_hi=min(NPIX,p_lo+PP)
+                pr,wo=p_lo//Wo,p_lo%Wo
+                for pix in range(p_lo,p_hi):
+                    xo=((pr*s)*PW+wo*s)*Ci
+                    d0=sdy[pix*Co+q*4:pix*Co+q*4+4]; d1=sdy[pix*Co+(q+nq8)*4:pix*Co+(q+nq8)*4+4]
+                    for j in range(5):
+                        xv=sx[xo+off[j]]
+                        accs[tid,j,:4]+=xv*d0; accs[tid,j,4:]+=xv*d1
+                    wo+=1
+                    if wo==Wo: wo=0; pr+=1
+        for sgrp in range(PS):
+            for tid in range(NT*PS):
+                ps,tt=tid//NT,tid%NT; g,q=tt//nq8,tt%nq8
+                if ps!=sgrp: continue
+                for j in range(5):
+                    kk=g*5+j
+                    if kk<K:
+                        tiles[cta,kk*Co+q*4:kk*Co+q*4+4]+=accs[tid,j,:4]
+                        tiles[cta,kk*Co+(q+nq8)*4:kk*Co+(q+nq8)*4+4]+=accs[tid,j,4:]
+    n4=N//4; per=-(-n4//8)
+    part=np.full((ncl,N),np.nan)
+    for cid in range(ncl):
+        for rank in range(8):
+            lo4,hi4=rank*per,min(n4,rank*per+per)
+            for i in range(lo4,hi4):
+                part[cid,4*i:4*i+4]=sum(tiles[cid*8+r,4*i:4*i+4] for r in range(8))
+    assert not np.isnan(part).any()
+    return part.sum(0).reshape(k,k,Ci,Co)
 def case(B,H,W,Ci,Co,k,s,padding):
     if padding=='SAME':
         Ho=-(-H//s); Wo=-(-W//s); ph=max((Ho-1)*s+k-H,0); pw=max((Wo-1)*s+k-W,0); pt,pl=ph//2,pw//2
     else:
         Ho=(H-k)//s+1; Wo=(W-k)//s+1; ph=pw=0; pt=pl=0
     rs=np.random.RandomState(0)
-    x=torch.tensor(rs.randn(B,Ci,H,W),requires_grad=True); w=torch.tensor(rs.randn(k,k,Ci,Co))
+    x=torch.tensor(rs.randn(B,Ci,H,W),requires_grad=True); w=torch.tensor(rs.randn(k,k,Ci,Co),requires_grad=True)
     xp=F.pad(x,(pl,pw-pl,pt,ph-pt))
     y=F.conv2d(xp,w.permute(3,2,0,1),stride=s)
     gy=torch.tensor(rs.randn(*y.shape))
-    dx,=torch.autograd.grad(y,x,gy)
-    got=emu_dgrad(gy.permute(0,2,3,1).numpy(),w.numpy(),B,H,W,Ci,Co,k,s,pt,pl,Ho,Wo)
+    dx,=torch.autograd.grad(y,x,gy,retain_graph=True)
+    got=emu_dgrad(gy.permute(0,2,3,1).numpy(),w.detach().numpy(),B,H,W,Ci,Co,k,s,pt,pl,Ho,Wo)
     e1=np.abs(got-dx.permute(0,2,3,1).numpy()).max()
-    got2=emu_fwd(x.detach().permute(0,2,3,1).numpy(),w.numpy(),B,H,W,Ci,Co,k,s,pt,pl,Ho,Wo)
+    got2=emu_fwd(x.detach().permute(0,2,3,1).numpy(),w.detach().numpy(),B,H,W,Ci,Co,k,s,pt,pl,Ho,Wo)
     e2=np.abs(got2-y.detach().permute(0,2,3,1).numpy()).max()
     print((B,H,W,Ci,Co,k,s,padding),"dgrad err %.2e fwd err %.2e"%(e1,e2))
     assert e1<1e-9 and e2<1e-9
+    if Co%8==0:
+        dw,=torch.autograd.grad(y,w,gy)
+        got3=emu_wgrad(x.detach().permute(0,2,3,1).numpy(),gy.permute(0,2,3,1).numpy(),B,H,W,Ci,Co,k,s,pt,pl,Ho,Wo)
+        e3=np.abs(got3-dw.numpy()).max()
+        print("wgrad err %.2e"%e3)
+        assert e3<1e-9
 
 
 @pytest.mark.parametrize("geom", [(1, 32, 32, 3, 8, 5, 2, 'SAME'), (1, 28, 28, 1, 4, 5, 2, 'SAME'), (1, 14, 14, 2, 4, 5, 2, 'SAME'),
                                   (1, 7, 7, 3, 4, 5, 2, 'SAME'), (1, 16, 20, 3, 4, 3, 1, 'SAME'), (1, 9, 11, 4, 4, 4, 1, 'VALID'),
-                                  (1, 5, 6, 2, 4, 5, 2, 'SAME')])
+                                  (1, 5, 6, 2, 4, 5, 2, 'SAME'), (3, 12, 10, 3, 16, 5, 2, 'SAME'), (2, 9, 11, 1, 8, 4, 1, 'VALID'),
+                                  (150, 3, 4, 4, 8, 3, 1, 'SAME')])
 def test_small_channel_kernel_index_math(geom):
     case(*geom)
