@@ -186,7 +186,10 @@ __device__ __forceinline__ void reduce_channels(float (&a)[4], float (&b)[4], in
   }
 }
 
-template <int Q>
+// NI > 0: the rows of a thread (at most NI float4) stay in REGISTERS between the statistics pass and the normalise pass — x is
+// read once, all NI loads are in flight together (the streaming form below exposes an L2 round trip per 4 rows and reads x
+// twice: 9.3 us for [16384 x 64], profiles/time_bn_r2.txt).  NI = 0: streaming two-pass form for any R.
+template <int Q, int NI>
 __global__ void __launch_bounds__(kThreads) bn_fwd_fused_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                                 const float* __restrict__ beta, float eps,
                                                                 float* __restrict__ y, float* __restrict__ mean_out,
@@ -208,12 +211,28 @@ __global__ void __launch_bounds__(kThreads) bn_fwd_fused_kernel(const float* __r
   const int r_begin = rank * rows_per, r_end = min(R, r_begin + rows_per);
 
   float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+  float4 cache[NI > 0 ? NI : 1];
   if (c_ok) {
+    if (NI > 0) {
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const int r = r_begin + rl + i * RL;
+        cache[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < r_end) cache[i] = *reinterpret_cast<const float4*>(x + (size_t)r * C + c);
+      }
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {                         // rows past r_end are zeros: they add nothing
+        const float4 v = cache[i];
+        a[0] += v.x; a[1] += v.y; a[2] += v.z; a[3] += v.w;
+        b[0] += v.x * v.x; b[1] += v.y * v.y; b[2] += v.z * v.z; b[3] += v.w * v.w;
+      }
+    } else {
 #pragma unroll 4
-    for (int r = r_begin + rl; r < r_end; r += RL) {
-      const float4 v = *reinterpret_cast<const float4*>(x + (size_t)r * C + c);
-      a[0] += v.x; a[1] += v.y; a[2] += v.z; a[3] += v.w;
-      b[0] += v.x * v.x; b[1] += v.y * v.y; b[2] += v.z * v.z; b[3] += v.w * v.w;
+      for (int r = r_begin + rl; r < r_end; r += RL) {
+        const float4 v = *reinterpret_cast<const float4*>(x + (size_t)r * C + c);
+        a[0] += v.x; a[1] += v.y; a[2] += v.z; a[3] += v.w;
+        b[0] += v.x * v.x; b[1] += v.y * v.y; b[2] += v.z * v.z; b[3] += v.w * v.w;
+      }
     }
   }
   double ta, tb, la, lb;
@@ -239,20 +258,36 @@ __global__ void __launch_bounds__(kThreads) bn_fwd_fused_kernel(const float* __r
   if (!c_ok) return;
   const float4 sc = *reinterpret_cast<const float4*>(&s_scale[quad * 4]);
   const float4 sh = *reinterpret_cast<const float4*>(&s_shift[quad * 4]);
+  if (NI > 0) {
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int r = r_begin + rl + i * RL;
+      if (r < r_end) {
+        const float4 v = cache[i];
+        float4 o;
+        o.x = apply_act(v.x * sc.x + sh.x, act, alpha);
+        o.y = apply_act(v.y * sc.y + sh.y, act, alpha);
+        o.z = apply_act(v.z * sc.z + sh.z, act, alpha);
+        o.w = apply_act(v.w * sc.w + sh.w, act, alpha);
+        *reinterpret_cast<float4*>(y + (size_t)r * C + c) = o;
+      }
+    }
+  } else {
 #pragma unroll 4
-  for (int r = r_begin + rl; r < r_end; r += RL) {
-    const size_t i = (size_t)r * C + c;
-    const float4 v = *reinterpret_cast<const float4*>(x + i);
-    float4 o;
-    o.x = apply_act(v.x * sc.x + sh.x, act, alpha);
-    o.y = apply_act(v.y * sc.y + sh.y, act, alpha);
-    o.z = apply_act(v.z * sc.z + sh.z, act, alpha);
-    o.w = apply_act(v.w * sc.w + sh.w, act, alpha);
-    *reinterpret_cast<float4*>(y + i) = o;
+    for (int r = r_begin + rl; r < r_end; r += RL) {
+      const size_t i = (size_t)r * C + c;
+      const float4 v = *reinterpret_cast<const float4*>(x + i);
+      float4 o;
+      o.x = apply_act(v.x * sc.x + sh.x, act, alpha);
+      o.y = apply_act(v.y * sc.y + sh.y, act, alpha);
+      o.z = apply_act(v.z * sc.z + sh.z, act, alpha);
+      o.w = apply_act(v.w * sc.w + sh.w, act, alpha);
+      *reinterpret_cast<float4*>(y + i) = o;
+    }
   }
 }
 
-template <int Q>
+template <int Q, int NI>
 __global__ void __launch_bounds__(kThreads) bn_bwd_fused_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                                 const float* __restrict__ y, const float* __restrict__ mean,
                                                                 const float* __restrict__ rstd, const float* __restrict__ gamma,
@@ -280,7 +315,43 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_fused_kernel(const float* __r
     rs4 = *reinterpret_cast<const float4*>(rstd + c);
   }
   float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
-  if (c_ok) {
+  float4 cg[NI > 0 ? NI : 1], cxh[NI > 0 ? NI : 1];         // NI > 0: activation-masked gradient and x-hat kept in registers
+  if (c_ok && NI > 0) {
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int r = r_begin + rl + i * RL;
+      cg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      cxh[i] = m4;                                           // x := mean, i.e. x-hat = 0, for rows past r_end
+      if (r < r_end) {
+        const size_t idx = (size_t)r * C + c;
+        cg[i] = *reinterpret_cast<const float4*>(dy + idx);
+        cxh[i] = *reinterpret_cast<const float4*>(x + idx);
+      }
+    }
+    if (act != GG_ACT_NONE) {
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const int r = r_begin + rl + i * RL;
+        if (r < r_end) {
+          const float4 yv = *reinterpret_cast<const float4*>(y + (size_t)r * C + c);
+          float4 g = cg[i];
+          g.x = act_grad_from_out(yv.x, g.x, act, alpha); g.y = act_grad_from_out(yv.y, g.y, act, alpha);
+          g.z = act_grad_from_out(yv.z, g.z, act, alpha); g.w = act_grad_from_out(yv.w, g.w, act, alpha);
+          cg[i] = g;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const float4 g = cg[i];
+      float4 xh = cxh[i];
+      xh.x = (xh.x - m4.x) * rs4.x; xh.y = (xh.y - m4.y) * rs4.y; xh.z = (xh.z - m4.z) * rs4.z; xh.w = (xh.w - m4.w) * rs4.w;
+      cxh[i] = xh;
+      a[0] += g.x; a[1] += g.y; a[2] += g.z; a[3] += g.w;
+      b[0] += g.x * xh.x; b[1] += g.y * xh.y; b[2] += g.z * xh.z; b[3] += g.w * xh.w;
+    }
+  }
+  if (c_ok && NI == 0) {
 #pragma unroll 2
     for (int r = r_begin + rl; r < r_end; r += RL) {
       const size_t i = (size_t)r * C + c;
@@ -319,23 +390,47 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_fused_kernel(const float* __r
     const float4 gm = *reinterpret_cast<const float4*>(gamma + c);
     k4.x *= gm.x; k4.y *= gm.y; k4.z *= gm.z; k4.w *= gm.w;
   }
-#pragma unroll 2
-  for (int r = r_begin + rl; r < r_end; r += RL) {
-    const size_t i = (size_t)r * C + c;
-    float4 g = *reinterpret_cast<const float4*>(dy + i);
-    const float4 xv = *reinterpret_cast<const float4*>(x + i);
-    if (act != GG_ACT_NONE) {
-      const float4 yv = *reinterpret_cast<const float4*>(y + i);
-      g.x = act_grad_from_out(yv.x, g.x, act, alpha); g.y = act_grad_from_out(yv.y, g.y, act, alpha);
-      g.z = act_grad_from_out(yv.z, g.z, act, alpha); g.w = act_grad_from_out(yv.w, g.w, act, alpha);
+  if (NI > 0) {
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int r = r_begin + rl + i * RL;
+      if (r < r_end) {
+        const float4 g = cg[i], xh = cxh[i];
+        float4 o;
+        o.x = k4.x * (g.x - mg.x - xh.x * mgx.x);
+        o.y = k4.y * (g.y - mg.y - xh.y * mgx.y);
+        o.z = k4.z * (g.z - mg.z - xh.z * mgx.z);
+        o.w = k4.w * (g.w - mg.w - xh.w * mgx.w);
+        *reinterpret_cast<float4*>(dx + (size_t)r * C + c) = o;
+      }
     }
-    float4 o;
-    o.x = k4.x * (g.x - mg.x - (xv.x - m4.x) * rs4.x * mgx.x);
-    o.y = k4.y * (g.y - mg.y - (xv.y - m4.y) * rs4.y * mgx.y);
-    o.z = k4.z * (g.z - mg.z - (xv.z - m4.z) * rs4.z * mgx.z);
-    o.w = k4.w * (g.w - mg.w - (xv.w - m4.w) * rs4.w * mgx.w);
-    *reinterpret_cast<float4*>(dx + i) = o;
+  } else {
+#pragma unroll 2
+    for (int r = r_begin + rl; r < r_end; r += RL) {
+      const size_t i = (size_t)r * C + c;
+      float4 g = *reinterpret_cast<const float4*>(dy + i);
+      const float4 xv = *reinterpret_cast<const float4*>(x + i);
+      if (act != GG_ACT_NONE) {
+        const float4 yv = *reinterpret_cast<const float4*>(y + i);
+        g.x = act_grad_from_out(yv.x, g.x, act, alpha); g.y = act_grad_from_out(yv.y, g.y, act, alpha);
+        g.z = act_grad_from_out(yv.z, g.z, act, alpha); g.w = act_grad_from_out(yv.w, g.w, act, alpha);
+      }
+      float4 o;
+      o.x = k4.x * (g.x - mg.x - (xv.x - m4.x) * rs4.x * mgx.x);
+      o.y = k4.y * (g.y - mg.y - (xv.y - m4.y) * rs4.y * mgx.y);
+      o.z = k4.z * (g.z - mg.z - (xv.z - m4.z) * rs4.z * mgx.z);
+      o.w = k4.w * (g.w - mg.w - (xv.w - m4.w) * rs4.w * mgx.w);
+      *reinterpret_cast<float4*>(dx + i) = o;
+    }
   }
+}
+
+constexpr int kBnNI = 8;    // rows per thread the register-cached kernels hold
+
+bool bn_cached_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GG_BN_CACHED"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
 }
 
 template <typename Kern, typename... Args>
@@ -379,11 +474,16 @@ static int bn_fwd_launch(const float* x, const float* gamma, const float* beta, 
   const BnPlan pl = bn_plan(R, C);
   if (!pl.ok) return fail(GG_ERR_UNSUPPORTED, "%s: C must be a multiple of 4", what);
   cudaStream_t st = as_stream(stream);
-  if (pl.cw == 32)
-    return launch_clustered(bn_fwd_fused_kernel<8>, pl, st, what, x, gamma, beta, eps, y, mean_out, rstd_out, R, C, pl.cs, act, alpha, dp);
-  if (pl.cw == 8)
-    return launch_clustered(bn_fwd_fused_kernel<2>, pl, st, what, x, gamma, beta, eps, y, mean_out, rstd_out, R, C, pl.cs, act, alpha, dp);
-  return launch_clustered(bn_fwd_fused_kernel<1>, pl, st, what, x, gamma, beta, eps, y, mean_out, rstd_out, R, C, pl.cs, act, alpha, dp);
+  const int q = pl.cw / 4;
+  const int rows_per = (R + pl.cs - 1) / pl.cs, rl = kThreads / q;
+  const bool cached = bn_cached_enabled() && rows_per <= kBnNI * rl && rows_per >= 4 * rl;   // measured: wins from 4 rows per thread
+#define GG_BN_FWD(Q_, NI_) \
+  return launch_clustered(bn_fwd_fused_kernel<Q_, NI_>, pl, st, what, x, gamma, beta, eps, y, mean_out, rstd_out, R, C, pl.cs, act, alpha, dp)
+  if (pl.cw == 32) { if (cached) GG_BN_FWD(8, kBnNI); GG_BN_FWD(8, 0); }
+  if (pl.cw == 8) { if (cached) GG_BN_FWD(2, kBnNI); GG_BN_FWD(2, 0); }
+  if (cached) GG_BN_FWD(1, kBnNI);
+  GG_BN_FWD(1, 0);
+#undef GG_BN_FWD
 }
 
 static int bn_bwd_launch(const float* dy, const float* x, const float* y, const float* mean, const float* rstd, const float* gamma,
@@ -394,11 +494,16 @@ static int bn_bwd_launch(const float* dy, const float* x, const float* y, const 
   const BnPlan pl = bn_plan(R, C);
   if (!pl.ok) return fail(GG_ERR_UNSUPPORTED, "%s: C must be a multiple of 4", what);
   cudaStream_t st = as_stream(stream);
-  if (pl.cw == 32)
-    return launch_clustered(bn_bwd_fused_kernel<8>, pl, st, what, dy, x, y, mean, rstd, gamma, dx, dgamma, dbeta, R, C, pl.cs, act, alpha, dp);
-  if (pl.cw == 8)
-    return launch_clustered(bn_bwd_fused_kernel<2>, pl, st, what, dy, x, y, mean, rstd, gamma, dx, dgamma, dbeta, R, C, pl.cs, act, alpha, dp);
-  return launch_clustered(bn_bwd_fused_kernel<1>, pl, st, what, dy, x, y, mean, rstd, gamma, dx, dgamma, dbeta, R, C, pl.cs, act, alpha, dp);
+  const int q = pl.cw / 4;
+  const int rows_per = (R + pl.cs - 1) / pl.cs, rl = kThreads / q;
+  const bool cached = bn_cached_enabled() && dx != nullptr && rows_per <= kBnNI * rl && rows_per >= 4 * rl;
+#define GG_BN_BWD(Q_, NI_) \
+  return launch_clustered(bn_bwd_fused_kernel<Q_, NI_>, pl, st, what, dy, x, y, mean, rstd, gamma, dx, dgamma, dbeta, R, C, pl.cs, act, alpha, dp)
+  if (pl.cw == 32) { if (cached) GG_BN_BWD(8, kBnNI); GG_BN_BWD(8, 0); }
+  if (pl.cw == 8) { if (cached) GG_BN_BWD(2, kBnNI); GG_BN_BWD(2, 0); }
+  if (cached) GG_BN_BWD(1, kBnNI);
+  GG_BN_BWD(1, 0);
+#undef GG_BN_BWD
 }
 
 static int make_dp(DpCtx* dp, void* const* peer_arenas_host, int rank, int world, long long site_offset, int C, const char* what) {

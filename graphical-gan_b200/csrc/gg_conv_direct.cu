@@ -28,6 +28,8 @@ int conv_small_dgrad(const float* dy, const float* w, const float* bias, float* 
 int conv_small_wgrad(const float* x, const float* dy, float* dw, int B, int H, int W, int Ci, int Co, int k, int stride, int pad_t,
                      int pad_l, int Ho, int Wo, void* ws, size_t ws_bytes, cudaStream_t st, bool* handled);
 size_t conv_small_wgrad_workspace(int B, int H, int W, int Ci, int Co, int k, int stride, int Ho, int Wo);
+void conv_small_set_debug(void* p);
+int conv_small_wgrad_info(int B, int H, int W, int Ci, int Co, int k, int stride, int Ho, int Wo, int* out8);
 }  // namespace gg
 
 namespace {
@@ -457,6 +459,16 @@ extern "C" int gg_set_tc_max_ctas(int n) {
 extern "C" int gg_debug_set_buffer(void* device_buffer_256_int64) {
   conv_tc_set_debug(device_buffer_256_int64);
   return GG_OK;
+}
+
+extern "C" int gg_debug_set_small_buffer(void* device_buffer_int64) {
+  conv_small_set_debug(device_buffer_int64);
+  return GG_OK;
+}
+
+extern "C" int gg_debug_small_wgrad_info(int B, int H, int W, int Ci, int Co, int k, int stride, int Ho, int Wo, int* out8) {
+  if (!out8) return fail(GG_ERR_BAD_ARG, "gg_debug_small_wgrad_info: null output%s");
+  return conv_small_wgrad_info(B, H, W, Ci, Co, k, stride, Ho, Wo, out8);
 }
 
 extern "C" size_t gg_conv2d_workspace(int mode, int B, int H, int W, int Ci, int Co, int k, int stride, int Ho, int Wo) {

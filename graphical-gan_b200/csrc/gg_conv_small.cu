@@ -14,6 +14,9 @@
 // Arithmetic is plain fp32 FMA (exact parity class of the direct kernels in gg_conv_direct.cu: 1e-6 vs the oracle).
 #include "gg_common.cuh"
 
+#include <map>
+#include <tuple>
+
 using namespace gg;
 
 namespace {
@@ -132,117 +135,9 @@ __global__ void __launch_bounds__(256) conv_small_fwd_kernel(const float* __rest
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// forward, variant 2 (GG_CONV_SMALL_V2=1; NOT yet validated on a GPU — written after the round's GPU budget was spent, index
-// arithmetic pinned by tests/test_cpu_small_conv.py): 4 pixels x 8 channels per thread (32 accumulators) and the k x k tap
-// loop unrolled for k = 5, i.e. 2 weight LDS.128 + 4 input LDS.32 per 32 FMAs (73 % FMA density instead of 46 %).
-// Block = 128 threads = 8 channel octets x 16 pixel lanes over the same 8x8-pixel x 64-channel tile and smem layout.
-// ---------------------------------------------------------------------------------------------------------------------
-template <int CI, int KS>
-__global__ void __launch_bounds__(128) conv_small_fwd_v2_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                                const float* __restrict__ bias, float* __restrict__ y, SmallP p,
-                                                                int act, float alpha) {
-  GG_PDL_ENTRY();
-  extern __shared__ __align__(16) float smem_f[];
-  const int k = KS > 0 ? KS : p.k;
-  const int K = k * k * CI;
-  const int IW = (kTile - 1) * p.stride + k;
-  float* sw = smem_f;                                   // [K][64]
-  float* sx = smem_f + K * kChunk;                      // [IW][IW][CI]
-  const int tiles_w = (p.Wo + kTile - 1) / kTile;
-  const int ho0 = (blockIdx.x / tiles_w) * kTile, wo0 = (blockIdx.x % tiles_w) * kTile;
-  const int b = blockIdx.y;
-  const int co0 = blockIdx.z * kChunk;
-  const int nco = min(kChunk, p.Co - co0);
-  const int tid = threadIdx.x;
-  for (int base = tid; base < K * (kChunk / 4); base += 4 * 128) {
-    float4 v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = base + u * 128;
-      const int kk = i / (kChunk / 4), q = i % (kChunk / 4);
-      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (i < K * (kChunk / 4) && q * 4 < nco) v[u] = *reinterpret_cast<const float4*>(w + (size_t)kk * p.Co + co0 + q * 4);
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = base + u * 128;
-      if (i < K * (kChunk / 4)) *reinterpret_cast<float4*>(sw + (i / (kChunk / 4)) * kChunk + (i % (kChunk / 4)) * 4) = v[u];
-    }
-  }
-  const int hi0 = ho0 * p.stride - p.pad_t, wi0 = wo0 * p.stride - p.pad_l;
-  const float* xb = x + (size_t)b * p.H * p.W * CI;
-  for (int i = tid; i < IW * IW * CI; i += 128) {
-    const int c = i % CI, iw = (i / CI) % IW, ih = i / (CI * IW);
-    const int hi = hi0 + ih, wi = wi0 + iw;
-    float v = 0.f;
-    if (hi >= 0 && hi < p.H && wi >= 0 && wi < p.W) v = xb[((size_t)hi * p.W + wi) * CI + c];
-    sx[i] = v;
-  }
-  __syncthreads();
-
-  const int co8 = (tid & 7) * 8, pl = tid >> 3;         // channel octet, pixel lane (pixels pl, pl+16, pl+32, pl+48)
-  int xo[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int pix = pl + 16 * j, py = pix / kTile, px = pix % kTile;
-    xo[j] = ((py * p.stride) * IW + px * p.stride) * CI;
-  }
-  float acc[4][8];
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-#pragma unroll
-    for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
-  const float* swq = sw + co8;
-#pragma unroll
-  for (int r = 0; r < (KS > 0 ? KS : 1); ++r) {
-    for (int rr = (KS > 0 ? r : 0); rr < (KS > 0 ? r + 1 : k); ++rr) {        // KS == 0: runtime loop over all rows
-#pragma unroll
-      for (int s = 0; s < (KS > 0 ? KS : 1); ++s) {
-        for (int ss = (KS > 0 ? s : 0); ss < (KS > 0 ? s + 1 : k); ++ss) {
-          const int xoff = (rr * IW + ss) * CI;
-          const int kk0 = (rr * k + ss) * CI;
-#pragma unroll
-          for (int c = 0; c < CI; ++c) {
-            const float4 w0 = *reinterpret_cast<const float4*>(swq + (kk0 + c) * kChunk);
-            const float4 w1 = *reinterpret_cast<const float4*>(swq + (kk0 + c) * kChunk + 4);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float xv = sx[xo[j] + xoff + c];
-              acc[j][0] = fmaf(xv, w0.x, acc[j][0]); acc[j][1] = fmaf(xv, w0.y, acc[j][1]);
-              acc[j][2] = fmaf(xv, w0.z, acc[j][2]); acc[j][3] = fmaf(xv, w0.w, acc[j][3]);
-              acc[j][4] = fmaf(xv, w1.x, acc[j][4]); acc[j][5] = fmaf(xv, w1.y, acc[j][5]);
-              acc[j][6] = fmaf(xv, w1.z, acc[j][6]); acc[j][7] = fmaf(xv, w1.w, acc[j][7]);
-            }
-          }
-        }
-      }
-    }
-  }
-  if (co8 >= nco) return;                               // nco is a multiple of 4: the second quad of an octet may be outside
-  const bool hi_ok = co8 + 4 < nco;
-  float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-  if (bias) {
-    b0 = *reinterpret_cast<const float4*>(bias + co0 + co8);
-    if (hi_ok) b1 = *reinterpret_cast<const float4*>(bias + co0 + co8 + 4);
-  }
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int pix = pl + 16 * j, ho = ho0 + pix / kTile, wo = wo0 + pix % kTile;
-    if (ho < p.Ho && wo < p.Wo) {
-      float* o = y + (((size_t)b * p.Ho + ho) * p.Wo + wo) * p.Co + co0 + co8;
-      float4 v0, v1;
-      v0.x = apply_act(acc[j][0] + b0.x, act, alpha); v0.y = apply_act(acc[j][1] + b0.y, act, alpha);
-      v0.z = apply_act(acc[j][2] + b0.z, act, alpha); v0.w = apply_act(acc[j][3] + b0.w, act, alpha);
-      *reinterpret_cast<float4*>(o) = v0;
-      if (hi_ok) {
-        v1.x = apply_act(acc[j][4] + b1.x, act, alpha); v1.y = apply_act(acc[j][5] + b1.y, act, alpha);
-        v1.z = apply_act(acc[j][6] + b1.z, act, alpha); v1.w = apply_act(acc[j][7] + b1.w, act, alpha);
-        *reinterpret_cast<float4*>(o + 4) = v1;
-      }
-    }
-  }
-}
+// (A 4 pixel x 8 channel register-tile variant with the 5x5 tap loop unrolled was measured on the B200 and removed: 18.8 us
+// against 16.2 us for the kernel above at B=128 3->64, profiles/time_conv_r2.txt — the kernel is bound by its shared-memory
+// fills and the 8.4 MB output store, not by FMA issue density.)
 
 // ---------------------------------------------------------------------------------------------------------------------
 // dgrad (and Deconv2D forward) towards CI <= 4 channels
@@ -382,6 +277,11 @@ constexpr int kWgTK = 5;            // filter rows per thread
 constexpr int kWgCL = 8;            // CTAs per cluster
 constexpr int kWgMaxClusters = 18;  // 18 x 8 = 144 of 148 SMs, one CTA per SM
 
+__device__ __forceinline__ long long wg_gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ uint32_t wg_cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -412,24 +312,25 @@ __device__ __forceinline__ uint32_t wg_ld_dsmem_u32(const uint32_t* local_ptr, u
 
 struct WgPlan {
   bool ok;
-  int RH, units_per_img, units, PH, PW, NT, PS, threads, clusters;
+  int RH, PW, NT, PS, threads, clusters;
   size_t sx_floats, tile_floats, smem, ws_bytes;
 };
 
 template <int CI>
 __global__ void __launch_bounds__(512) conv_small_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                                float* __restrict__ dw, float* __restrict__ part,
-                                                               unsigned* __restrict__ ticket, SmallP p, int RH, int units_per_img,
-                                                               int units, int PH, int PW, int NT, int PS, int sx_floats) {
+                                                               unsigned* __restrict__ ticket, SmallP p, int RH, int PW, int NT,
+                                                               int PS, int sx_floats, long long* __restrict__ dbg) {
+#define GG_WG_STAMP(slot) do { if (dbg && threadIdx.x == 0) dbg[blockIdx.x * 8 + (slot)] = wg_gtime(); } while (0)
+  GG_WG_STAMP(0);
   GG_PDL_ENTRY();
   extern __shared__ __align__(16) float smem_f[];
   __shared__ uint32_t s_last;
-  float* sx = smem_f;                                   // [PH][PW][CI] input patch, TF SAME padding as zeros
-  float* sdy = smem_f + sx_floats;                      // [RH*Wo][Co] dy rows of the unit; later the CTA's [K][Co] tile
+  float* sx = smem_f;                                   // [(rows-1)*stride+k][PW][CI] input patch, TF SAME padding as zeros
+  float* sdy = smem_f + sx_floats;                      // [rows*Wo][Co] dy rows of the unit; later the CTA's [K][Co] tile
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int K = p.k * p.k * CI, Co = p.Co, N = K * Co;
   const int nq8 = Co >> 3;                              // channel octets: quads q and q + nq8
-  const int NPIX = RH * p.Wo;
   const bool worker = tid < NT * PS;
   const int ps = worker ? tid / NT : 0, tt = worker ? tid % NT : 0;
   const int g = tt / nq8, q = tt % nq8;
@@ -445,21 +346,39 @@ __global__ void __launch_bounds__(512) conv_small_wgrad_kernel(const float* __re
   for (int j = 0; j < kWgTK; ++j)
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
-  const int PP = (NPIX + PS - 1) / PS;
-  const int p_lo = ps * PP, p_hi = min(NPIX, p_lo + PP);
-
-  for (int u = blockIdx.x; u < units; u += gridDim.x) {
-    const int b = u / units_per_img, ho0 = (u % units_per_img) * RH;
-    const int rows = min(RH, p.Ho - ho0);
-    if (u != (int)blockIdx.x) __syncthreads();          // previous unit's readers are done with the tiles
+  // the B*Ho output rows are dealt to the CTAs as contiguous, equal ranges (a 8-CTA cluster needs its SMs inside one GPC: the
+  // device keeps only 15 of them resident, so a grid of "one image per CTA" ran its 16th cluster as a second wave, profiles/
+  // timeline_small_wgrad_r2.txt); a range is walked in units of at most RH rows of ONE image
+  const long long total_rows = (long long)p.B * p.Ho;
+  const long long g_lo = total_rows * blockIdx.x / gridDim.x, g_hi = total_rows * (blockIdx.x + 1) / gridDim.x;
+  for (long long g0 = g_lo; g0 < g_hi;) {
+    const int b = (int)(g0 / p.Ho), ho0 = (int)(g0 % p.Ho);
+    int rows = p.Ho - ho0;
+    if (rows > RH) rows = RH;
+    if ((long long)rows > g_hi - g0) rows = (int)(g_hi - g0);
+    if (g0 != g_lo) __syncthreads();                    // previous unit's readers are done with the tiles
+    g0 += rows;
+    const int npix = rows * p.Wo;
+    const int PP = (npix + PS - 1) / PS;
+    const int p_lo = min(npix, ps * PP), p_hi = min(npix, p_lo + PP);
+    // dy rows ho0 .. ho0+rows-1 of image b are one contiguous run: asynchronous 16-byte copies, all in flight at once,
+    // overlapped with the index arithmetic of the x patch fill below
+    const float4* dsrc = reinterpret_cast<const float4*>(dy + ((size_t)b * p.Ho + ho0) * p.Wo * Co);
+    const int nvalid = npix * (Co >> 2);
+    float4* sdy4 = reinterpret_cast<float4*>(sdy);
+    for (int i = tid; i < nvalid; i += nthr) {
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sdy4 + i);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(dsrc + i) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
     // x patch
     const int hi0 = ho0 * p.stride - p.pad_t, wi0 = -p.pad_l;
     const float* xb = x + (size_t)b * p.H * p.W * CI;
-    const int nx = PH * PW * CI;
-    for (int base = tid; base < nx; base += 4 * nthr) {
-      float v[4];
+    const int nx = ((rows - 1) * p.stride + p.k) * PW * CI;
+    for (int base = tid; base < nx; base += 8 * nthr) {
+      float v[8];
 #pragma unroll
-      for (int uu = 0; uu < 4; ++uu) {
+      for (int uu = 0; uu < 8; ++uu) {
         const int i = base + uu * nthr;
         const int c = i % CI, iw = (i / CI) % PW, ih = i / (CI * PW);
         const int hi = hi0 + ih, wi = wi0 + iw;
@@ -467,33 +386,17 @@ __global__ void __launch_bounds__(512) conv_small_wgrad_kernel(const float* __re
         if (i < nx && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W) v[uu] = xb[((size_t)hi * p.W + wi) * CI + c];
       }
 #pragma unroll
-      for (int uu = 0; uu < 4; ++uu) {
+      for (int uu = 0; uu < 8; ++uu) {
         const int i = base + uu * nthr;
         if (i < nx) sx[i] = v[uu];
       }
     }
-    // dy rows ho0 .. ho0+rows-1 of image b are one contiguous run; rows past Ho are zeros
-    const float4* dsrc = reinterpret_cast<const float4*>(dy + ((size_t)b * p.Ho + ho0) * p.Wo * Co);
-    const int nvalid = rows * p.Wo * (Co >> 2), nall = NPIX * (Co >> 2);
-    float4* sdy4 = reinterpret_cast<float4*>(sdy);
-    for (int base = tid; base < nall; base += 8 * nthr) {
-      float4 v[8];
-#pragma unroll
-      for (int uu = 0; uu < 8; ++uu) {
-        const int i = base + uu * nthr;
-        v[uu] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < nvalid) v[uu] = dsrc[i];
-      }
-#pragma unroll
-      for (int uu = 0; uu < 8; ++uu) {
-        const int i = base + uu * nthr;
-        if (i < nall) sdy4[i] = v[uu];
-      }
-    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
+    GG_WG_STAMP(1);                                     // tiles of the (last) unit staged
     if (worker) {
       int pr = p_lo / p.Wo, wo = p_lo % p.Wo;
-      const float4* dq = sdy4 + q;
+      const float4* dq = reinterpret_cast<const float4*>(sdy) + q;
       const int cq4 = Co >> 2;
 #pragma unroll 2
       for (int pix = p_lo; pix < p_hi; ++pix) {
@@ -514,6 +417,7 @@ __global__ void __launch_bounds__(512) conv_small_wgrad_kernel(const float* __re
     }
   }
   __syncthreads();
+  GG_WG_STAMP(2);                                       // FMA loops done
   // fold the PS pixel groups into the CTA's [K][Co] tile (group order), aliased over the dy rows
   float* sacc = sdy;
   for (int i = tid; i < N; i += nthr) sacc[i] = 0.f;
@@ -540,6 +444,7 @@ __global__ void __launch_bounds__(512) conv_small_wgrad_kernel(const float* __re
   const int n4 = N >> 2, per = (n4 + kWgCL - 1) / kWgCL;
   const int lo4 = rank * per, hi4 = min(n4, lo4 + per);
   wg_cluster_sync();
+  GG_WG_STAMP(3);                                       // CTA tiles folded, cluster rendezvous passed
   float4* out4 = reinterpret_cast<float4*>(nclusters == 1 ? dw : part + (size_t)cid * N);
   for (int i = lo4 + tid; i < hi4; i += nthr) {
     float4 t = wg_ld_dsmem_f4(sacc + i * 4, 0);
@@ -556,7 +461,9 @@ __global__ void __launch_bounds__(512) conv_small_wgrad_kernel(const float* __re
   }
   __threadfence();
   wg_cluster_sync();                                    // every rank's slice of the partial is written and fenced
+  GG_WG_STAMP(4);                                       // cluster partial in L2
   if (rank == 0 && tid == 0) {
+    __threadfence();                                    // the ranks' fenced writes are ordered before the ticket (cumulative)
     const unsigned t = atomicAdd(ticket, 1u);
     const bool last = (t == (unsigned)nclusters - 1u);
     if (last) *ticket = 0u;                             // self-resetting: the next launch starts from zero again
@@ -566,17 +473,26 @@ __global__ void __launch_bounds__(512) conv_small_wgrad_kernel(const float* __re
   wg_cluster_sync();
   const uint32_t last = wg_ld_dsmem_u32(&s_last, 0);
   wg_cluster_sync();                                    // rank 0 keeps its shared memory alive until every rank has read
+  GG_WG_STAMP(5);                                       // ticket taken, flag read
   if (!last) return;
   __threadfence();
   float4* dw4 = reinterpret_cast<float4*>(dw);
   for (int i = lo4 + tid; i < hi4; i += nthr) {
-    float4 t = __ldcg(reinterpret_cast<const float4*>(part) + i);
-    for (int c = 1; c < nclusters; ++c) {
-      const float4 v = __ldcg(reinterpret_cast<const float4*>(part + (size_t)c * N) + i);
-      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    float4 v[kWgMaxClusters];
+#pragma unroll
+    for (int c = 0; c < kWgMaxClusters; ++c) {              // every partial of this float4 in flight together
+      v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < nclusters) v[c] = __ldcg(reinterpret_cast<const float4*>(part + (size_t)c * N) + i);
+    }
+    float4 t = v[0];
+#pragma unroll
+    for (int c = 1; c < kWgMaxClusters; ++c) {              // cluster order; absent clusters add +0
+      t.x += v[c].x; t.y += v[c].y; t.z += v[c].z; t.w += v[c].w;
     }
     dw4[i] = t;
   }
+  GG_WG_STAMP(6);                                       // last cluster: dw written
+#undef GG_WG_STAMP
 }
 
 WgPlan wgrad_plan(int B, int H, int W, int Ci, int Co, int k, int stride, int Ho, int Wo) {
@@ -586,31 +502,26 @@ WgPlan wgrad_plan(int B, int H, int W, int Ci, int Co, int k, int stride, int Ho
   if (Ci < 1 || Ci > 4 || Co % 8 != 0 || Co > 256 || k > 7 || stride < 1 || stride > 2 || B > (1 << 20)) return pl;
   const int K = k * k * Ci;
   if (K > 100) return pl;
-  int rh_max = 16384 / (Wo * Co);                       // dy rows of a unit: at most 64 KB of shared memory
+  const int rh_max = 16384 / (Wo * Co);                 // dy rows of a unit: at most 64 KB of shared memory
   if (rh_max < 1) return pl;
-  int RH = Ho < rh_max ? Ho : rh_max;
-  while (RH > 1 && (long long)B * ((Ho + RH - 1) / RH) < 128) RH = (RH + 1) / 2;
-  pl.RH = RH;
-  pl.units_per_img = (Ho + RH - 1) / RH;
-  pl.units = B * pl.units_per_img;
-  pl.PH = (RH - 1) * stride + k;
+  pl.RH = Ho < rh_max ? Ho : rh_max;
   pl.PW = (Wo - 1) * stride + k;
   pl.NT = ((K + kWgTK - 1) / kWgTK) * (Co / 8);
   if (pl.NT > 512) return pl;
   pl.PS = 512 / pl.NT;
   if (pl.PS > 4) pl.PS = 4;
-  if (pl.PS > RH * Wo) pl.PS = RH * Wo;
   pl.threads = ((pl.NT * pl.PS + 31) / 32) * 32;
   if (pl.threads < 128) pl.threads = 128;
-  pl.sx_floats = (((size_t)pl.PH * pl.PW * Ci + 3) / 4) * 4;
-  const size_t tile = (size_t)RH * Wo * Co, accs = (size_t)K * Co;
+  pl.sx_floats = (((size_t)((pl.RH - 1) * stride + k) * pl.PW * Ci + 3) / 4) * 4;
+  const size_t tile = (size_t)pl.RH * Wo * Co, accs = (size_t)K * Co;
   pl.tile_floats = tile > accs ? tile : accs;
   pl.smem = (pl.sx_floats + pl.tile_floats) * sizeof(float);
   if (pl.smem > 200 * 1024) return pl;
-  int clusters = (pl.units + kWgCL - 1) / kWgCL;
+  const long long total_rows = (long long)B * Ho;
+  long long clusters = (total_rows + 2 * kWgCL - 1) / (2 * kWgCL);     // at least two output rows per CTA
   if (clusters > kWgMaxClusters) clusters = kWgMaxClusters;
-  pl.clusters = clusters;
-  pl.ws_bytes = 256 + (size_t)clusters * accs * sizeof(float);
+  pl.clusters = (int)clusters;                          // upper bound; the launch caps it at what the device keeps resident
+  pl.ws_bytes = 256 + (size_t)kWgMaxClusters * accs * sizeof(float);
   pl.ok = true;
   return pl;
 }
@@ -638,22 +549,6 @@ int conv_small_fwd(const float* x, const float* w, const float* bias, float* y, 
   const size_t smem = ((size_t)k * k * Ci * kChunk + (size_t)IW * IW * Ci) * sizeof(float);
   if (smem > 48 * 1024 || B > 65535) return GG_OK;
   dim3 grid(ceil_div(Ho, kTile) * ceil_div(Wo, kTile), B, ceil_div(Co, kChunk));
-  static int v2 = -1;
-  if (v2 < 0) { const char* e = getenv("GG_CONV_SMALL_V2"); v2 = (e && e[0] == '1') ? 1 : 0; }
-  if (v2) {
-#define GG_V2(CI_)                                                                                                        \
-    if (k == 5) GG_LAUNCH((conv_small_fwd_v2_kernel<CI_, 5>), grid, 128, smem, st, x, w, bias, y, p, act, alpha);                    \
-    else GG_LAUNCH((conv_small_fwd_v2_kernel<CI_, 0>), grid, 128, smem, st, x, w, bias, y, p, act, alpha)
-    switch (Ci) {
-      case 1: GG_V2(1); break;
-      case 2: GG_V2(2); break;
-      case 3: GG_V2(3); break;
-      default: GG_V2(4); break;
-    }
-#undef GG_V2
-    *handled = true;
-    return check_launch("gg_conv2d_fwd(small-channel v2)");
-  }
   switch (Ci) {
     case 1: GG_LAUNCH((conv_small_fwd_kernel<1>), grid, 256, smem, st, x, w, bias, y, p, act, alpha); break;
     case 2: GG_LAUNCH((conv_small_fwd_kernel<2>), grid, 256, smem, st, x, w, bias, y, p, act, alpha); break;
@@ -686,6 +581,44 @@ int conv_small_dgrad(const float* dy, const float* w, const float* bias, float* 
   return check_launch("gg_conv2d_dgrad(small-channel)");
 }
 
+// 8-CTA clusters of this kernel the device can keep resident at once (cudaOccupancyMaxActiveClusters; cached per configuration).
+// Also opts the kernel into > 48 KB of dynamic shared memory.
+int wg_resident_clusters(int Ci, int threads, size_t smem) {
+  static std::map<std::tuple<int, int, size_t>, int> cache;
+  const auto key = std::make_tuple(Ci, threads, smem);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(kNumSMs / kWgCL * kWgCL));
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kWgCL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  cudaError_t e = cudaSuccess;
+#define GG_WG_OCC(CI_)                                                                                                      \
+  e = cudaFuncSetAttribute(conv_small_wgrad_kernel<CI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);          \
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, conv_small_wgrad_kernel<CI_>, &cfg)
+  switch (Ci) {
+    case 1: GG_WG_OCC(1); break;
+    case 2: GG_WG_OCC(2); break;
+    case 3: GG_WG_OCC(3); break;
+    default: GG_WG_OCC(4); break;
+  }
+#undef GG_WG_OCC
+  if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
+  cache[key] = n;
+  return n;
+}
+
+long long* g_small_dbg = nullptr;   // gg_debug_set_small_buffer: per-CTA %globaltimer stamps of the small-channel wgrad kernel
+void conv_small_set_debug(void* p) { g_small_dbg = reinterpret_cast<long long*>(p); }
+
 size_t conv_small_wgrad_workspace(int B, int H, int W, int Ci, int Co, int k, int stride, int Ho, int Wo) {
   if (!small_enabled()) return 0;
   const WgPlan pl = wgrad_plan(B, H, W, Ci, Co, k, stride, Ho, Wo);
@@ -703,8 +636,11 @@ int conv_small_wgrad(const float* x, const float* dy, float* dw, int B, int H, i
   SmallP p{B, H, W, Ci, Co, k, stride, pad_t, pad_l, Ho, Wo};
   unsigned* ticket = reinterpret_cast<unsigned*>(ws);
   float* part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + 256);
+  int clusters = pl.clusters;
+  const int resident = wg_resident_clusters(Ci, pl.threads, pl.smem);
+  if (resident > 0 && clusters > resident) clusters = resident;      // one wave: a second wave would double the launch
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(pl.clusters * kWgCL));
+  cfg.gridDim = dim3((unsigned)(clusters * kWgCL));
   cfg.blockDim = dim3((unsigned)pl.threads);
   cfg.dynamicSmemBytes = pl.smem;
   cfg.stream = st;
@@ -724,16 +660,8 @@ int conv_small_wgrad(const float* x, const float* dy, float* dw, int B, int H, i
   cfg.numAttrs = na;
   cudaError_t e = cudaSuccess;
 #define GG_WG(CI_)                                                                                                          \
-  do {                                                                                                                      \
-    static bool attr_set = false;                                                                                           \
-    if (!attr_set) {                                                                                                        \
-      e = cudaFuncSetAttribute(conv_small_wgrad_kernel<CI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);      \
-      attr_set = (e == cudaSuccess);                                                                                        \
-    }                                                                                                                       \
-    if (e == cudaSuccess)                                                                                                   \
-      e = cudaLaunchKernelEx(&cfg, conv_small_wgrad_kernel<CI_>, x, dy, dw, part, ticket, p, pl.RH, pl.units_per_img,       \
-                             pl.units, pl.PH, pl.PW, pl.NT, pl.PS, (int)pl.sx_floats);                                      \
-  } while (0)
+  e = cudaLaunchKernelEx(&cfg, conv_small_wgrad_kernel<CI_>, x, dy, dw, part, ticket, p, pl.RH, pl.PW, pl.NT, pl.PS,        \
+                         (int)pl.sx_floats, g_small_dbg)
   switch (Ci) {
     case 1: GG_WG(1); break;
     case 2: GG_WG(2); break;
@@ -747,6 +675,20 @@ int conv_small_wgrad(const float* x, const float* dy, float* dw, int B, int H, i
   }
   *handled = true;
   return check_launch("gg_conv2d_wgrad(small-channel)");
+}
+
+// launch plan of the small-channel wgrad kernel for a geometry (development aid): out8 = {ok, max rows per unit, B*Ho rows,
+// threads, pixel groups, clusters launched, dynamic shared memory bytes, clusters the device keeps resident at once}
+int conv_small_wgrad_info(int B, int H, int W, int Ci, int Co, int k, int stride, int Ho, int Wo, int* out8) {
+  const WgPlan pl = wgrad_plan(B, H, W, Ci, Co, k, stride, Ho, Wo);
+  for (int i = 0; i < 8; ++i) out8[i] = 0;
+  if (!pl.ok) return GG_OK;
+  const int resident = wg_resident_clusters(Ci, pl.threads, pl.smem);
+  out8[0] = 1; out8[1] = pl.RH; out8[2] = B * Ho; out8[3] = pl.threads; out8[4] = pl.PS;
+  out8[5] = (resident > 0 && pl.clusters > resident) ? resident : pl.clusters;
+  out8[6] = (int)pl.smem;
+  out8[7] = resident;
+  return GG_OK;
 }
 
 }  // namespace gg

@@ -110,6 +110,46 @@ __global__ void __launch_bounds__(256) gemm_splitk_finish(const float* __restric
   C[i] = apply_act(v, act, alpha);
 }
 
+// ---- the thin products of the hot path --------------------------------------------------------------------------------------
+// The critic's last layer and its gradients ([128 x 512] @ [512 x 1], its outer-product dgrad with K = 1, the [512 x 1] wgrad) and
+// the mixture-prior lookups ([64 x 30] @ [30 x 128] and its transpose) are 10^4..10^5 MACs: the tiled split-K kernel above spends
+// 8-12 us on them (two launches, 16 CTAs, a shared-memory round trip per 16-wide K tile; profiles/launches_r2_eager.csv) and four
+// of them sit on the step's critical path.  They get one flat launch each:
+//   gemm_rowdot_kernel   N <= 4, A row-major: one warp per output element, lanes stride K (coalesced), shuffle reduction;
+//   gemm_smallk_kernel   K <= 128 and <= 2^20 MACs (or K <= 4): one thread per output element, sequential fp32 FMA over K.
+template <int TB>
+__global__ void __launch_bounds__(256) gemm_rowdot_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                          const float* __restrict__ bias, float* __restrict__ C, int M, int N, int K,
+                                                          int act, float alpha) {
+  GG_PDL_ENTRY();
+  const int w = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (w >= M * N) return;
+  const int m = w / N, n = w % N;
+  const float* a = A + (long long)m * K;
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) acc = fmaf(a[k], TB ? B[(long long)n * K + k] : B[(long long)k * N + n], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) C[(long long)m * N + n] = apply_act(acc + (bias ? bias[n] : 0.f), act, alpha);
+}
+
+template <int TA, int TB>
+__global__ void __launch_bounds__(256) gemm_smallk_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                          const float* __restrict__ bias, float* __restrict__ C, int M, int N, int K,
+                                                          int act, float alpha) {
+  GG_PDL_ENTRY();
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)M * N) return;
+  const int m = (int)(i / N), n = (int)(i % N);
+  float acc = 0.f;
+#pragma unroll 4
+  for (int k = 0; k < K; ++k) {
+    const float a = TA ? A[(long long)k * M + m] : A[(long long)m * K + k];
+    const float b = TB ? B[(long long)n * K + k] : B[(long long)k * N + n];
+    acc = fmaf(a, b, acc);
+  }
+  C[i] = apply_act(acc + (bias ? bias[n] : 0.f), act, alpha);
+}
+
 int choose_splits(int M, int N, int K) {
   int tiles = ceil_div(M, TM) * ceil_div(N, TN);
   int splits = ceil_div(2 * kNumSMs, tiles);
@@ -154,6 +194,26 @@ extern "C" int gg_gemm(const float* A, const float* Bm, const float* bias, float
       rc = conv_tc_wgrad(A, Bm, C, K, 1, 1, M, N, 1, 1, 0, 0, 1, 1, workspace, workspace_bytes, st, &handled);
     if (rc) return rc;
     if (handled) { g_last_backend = 1; return GG_OK; }
+  }
+  static int thin = -1;
+  if (thin < 0) { const char* e = getenv("GG_GEMM_THIN"); thin = (e && e[0] == '0') ? 0 : 1; }
+  if (thin && N <= 4 && !ta) {
+    g_last_backend = 0;
+    const long long threads = (long long)M * N * 32;
+    if (tb) GG_LAUNCH((gemm_rowdot_kernel<1>), ceil_div(threads, 256), 256, 0, st, A, Bm, bias, C, M, N, K, act, alpha);
+    else GG_LAUNCH((gemm_rowdot_kernel<0>), ceil_div(threads, 256), 256, 0, st, A, Bm, bias, C, M, N, K, act, alpha);
+    return check_launch("gg_gemm(rowdot)");
+  }
+  if (thin && (K <= 4 || (K <= 128 && (long long)M * N * K <= (1 << 20)))) {
+    g_last_backend = 0;
+    const int blocks = ceil_div((long long)M * N, 256);
+#define GG_LAUNCH_SMALLK(TA, TB) GG_LAUNCH((gemm_smallk_kernel<TA, TB>), blocks, 256, 0, st, A, Bm, bias, C, M, N, K, act, alpha)
+    if (!ta && !tb) GG_LAUNCH_SMALLK(0, 0);
+    else if (ta && !tb) GG_LAUNCH_SMALLK(1, 0);
+    else if (!ta && tb) GG_LAUNCH_SMALLK(0, 1);
+    else GG_LAUNCH_SMALLK(1, 1);
+#undef GG_LAUNCH_SMALLK
+    return check_launch("gg_gemm(small-K)");
   }
   int splits = choose_splits(M, N, K);
   if (splits > 1 && (workspace == nullptr || workspace_bytes < (size_t)splits * M * N * sizeof(float))) splits = 1;

@@ -43,6 +43,8 @@ SIGNATURES = {
     "gg_set_tc_max_ctas": (c_i, [c_i]),
     "gg_set_tc_stages": (c_i, [c_i]),
     "gg_last_tc_info": (c_i, [C.POINTER(c_i)]),
+    "gg_debug_set_small_buffer": (c_i, [c_p]),
+    "gg_debug_small_wgrad_info": (c_i, [c_i] * 9 + [C.POINTER(c_i)]),
     "gg_conv2d_fwd": (c_i, [c_p, c_p, c_p, c_p] + [c_i] * 11 + [c_i, c_f, c_p, c_sz, c_p]),
     "gg_conv2d_dgrad": (c_i, [c_p, c_p, c_p, c_p] + [c_i] * 11 + [c_i, c_f, c_p, c_sz, c_p]),
     "gg_conv2d_wgrad": (c_i, [c_p, c_p, c_p] + [c_i] * 11 + [c_p, c_sz, c_p]),

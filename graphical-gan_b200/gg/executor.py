@@ -33,6 +33,7 @@ class Runtime(object):
         self.param_nodes = {}  # node.id -> node
         self.consts = {}
         self.feeds = {}        # node.id -> (device tensor, pinned host tensor)
+        self.stage = {}        # key -> ring of pinned staging slots [tensor, event of the last copy, pending Deferred]
         self.slots = {}        # (optimizer id, param id) -> (m, v)
         self.opt_state = {}    # optimizer id -> device state tensor {b1^t, b2^t, t}
         self.plans = {}
@@ -100,6 +101,23 @@ class Runtime(object):
             self.feeds[key] = (torch.zeros(n, dtype=torch.uint8, device=self.dev()), torch.zeros(n, dtype=torch.uint8).pin_memory())
         return self.feeds[key]
 
+    def stage_slot(self, key, n, dtype):
+        """next pinned staging slot of a ring of FETCH_RING (host->device feeds, device->host fetches): with deferred fetches
+        the host runs ahead of the device, so a slot is reused only after the copy that last used it has completed"""
+        torch = _torch()
+        ring = self.stage.get(key)
+        if ring is None:
+            ring = self.stage[key] = {"next": 0, "slots": [[torch.zeros(max(n, 1), dtype=dtype).pin_memory(), None, None]
+                                                             for _ in range(FETCH_RING)]}
+        slot = ring["slots"][ring["next"]]
+        ring["next"] = (ring["next"] + 1) % FETCH_RING
+        if slot[2] is not None:
+            slot[2].result()                 # a Deferred nobody has read yet still points at this slot: settle it first
+            slot[2] = None
+        if slot[1] is not None:
+            slot[1].synchronize()
+        return slot
+
     def feed_buffer(self, node):
         torch = _torch()
         if node.id not in self.feeds:
@@ -123,8 +141,9 @@ class Runtime(object):
         torch = _torch()
         self.param_buffer(node).copy_(torch.from_numpy(np.ascontiguousarray(value, dtype=np.float32).reshape(-1)))
 
-    def run(self, fetches, feed_dict=None, to_host=True):
-        """to_host=False: enqueue the step and return its Plan without any device->host read (kernel-only timing)"""
+    def run(self, fetches, feed_dict=None, to_host=True, deferred=False):
+        """to_host=False: enqueue the step and return its Plan without any device->host read (kernel-only timing).
+        deferred=True: return Deferred values (device->host copies enqueued, not awaited)."""
         single = isinstance(fetches, (Tensor, Operation)) or fetches is None
         flist = [fetches] if single else list(fetches)
         flat = []
@@ -141,7 +160,7 @@ class Runtime(object):
         if plan is None:
             plan = Plan(self, flat, list(feed_dict.keys()))
             self.plans[key] = plan
-        results = plan.run(feed_dict, to_host=to_host)
+        results = plan.run(feed_dict, to_host=to_host, deferred=deferred)
         if not to_host:
             return plan
 
@@ -151,6 +170,68 @@ class Runtime(object):
             return results[s]
         out = [rebuild(s) for s in structure]
         return out[0] if single else out
+
+
+FETCH_RING = 4      # pinned host slots per fetched tensor / per fed placeholder: how far the host may run ahead of the device
+
+
+class Deferred(object):
+    """Value of a fetched tensor whose device->host copy is enqueued but not yet awaited (Session(deferred_fetches=True)).
+
+    The reference loop only logs the costs `session.run` returns (gmgan_inference_cifar10.py:483-494), so nothing on the
+    host has to wait for a step before it feeds the next one.  A Deferred converts to its numpy value on first use
+    (float(), np.asarray(), arithmetic, comparison, formatting, any numpy attribute): that is the moment the host waits for the
+    copy's CUDA event.  The copy itself is enqueued by EVERY run, into pinned memory."""
+    __slots__ = ("_h", "_ev", "_shape", "_val")
+
+    def __init__(self, h, ev, shape):
+        self._h, self._ev, self._shape, self._val = h, ev, tuple(shape), None
+
+    def result(self):
+        if self._val is None:
+            self._ev.synchronize()
+            arr = self._h.numpy().reshape(self._shape).copy()
+            self._val = arr[()] if len(self._shape) == 0 else arr
+            self._h = self._ev = None
+        return self._val
+
+    def done(self):
+        return self._val is not None or self._ev.query()
+
+    def __array__(self, dtype=None, copy=None):
+        a = np.asarray(self.result())
+        return a.astype(dtype) if dtype is not None and a.dtype != dtype else a
+
+    def __getattr__(self, name):            # .shape, .dtype, .item(), .mean(), ... of the numpy value
+        return getattr(self.result(), name)
+
+    def __float__(self): return float(self.result())
+    def __int__(self): return int(self.result())
+    def __bool__(self): return bool(self.result())
+    def __len__(self): return len(self.result())
+    def __getitem__(self, i): return self.result()[i]
+    def __iter__(self): return iter(self.result())
+    def __repr__(self): return repr(self.result())
+    def __str__(self): return str(self.result())
+    def __format__(self, spec): return format(self.result(), spec)
+    def __neg__(self): return -self.result()
+    def __abs__(self): return abs(self.result())
+    def __add__(self, o): return self.result() + o
+    def __radd__(self, o): return o + self.result()
+    def __sub__(self, o): return self.result() - o
+    def __rsub__(self, o): return o - self.result()
+    def __mul__(self, o): return self.result() * o
+    def __rmul__(self, o): return o * self.result()
+    def __truediv__(self, o): return self.result() / o
+    def __rtruediv__(self, o): return o / self.result()
+    def __pow__(self, o): return self.result() ** o
+    def __lt__(self, o): return self.result() < o
+    def __le__(self, o): return self.result() <= o
+    def __gt__(self, o): return self.result() > o
+    def __ge__(self, o): return self.result() >= o
+    def __eq__(self, o): return self.result() == o
+    def __ne__(self, o): return self.result() != o
+    __hash__ = None
 
 
 RT = Runtime()
@@ -1166,10 +1247,10 @@ class Plan(object):
         self.kernel_launches = cabi.lib.gg_launch_count() - before
         return out
 
-    def run(self, feed_dict, to_host=True):
+    def run(self, feed_dict, to_host=True, deferred=False):
         torch = _torch()
         for node, value in feed_dict.items():
-            d, h = self.rt.feed_buffer(node)
+            d, _h = self.rt.feed_buffer(node)
             if isinstance(value, torch.Tensor):
                 d.copy_(value.reshape(-1), non_blocking=True)   # already-resident input (kernel-only timing)
             else:
@@ -1177,15 +1258,21 @@ class Plan(object):
                 if arr.size != node.size:
                     raise ValueError("feed for %s has %d elements, expected %s" % (node.name, arr.size, tuple(node.shape)))
                 if arr.dtype == np.uint8 and node.dtype == int32:
-                    d8, h8 = self.rt.feed_buffer_u8(node)
-                    h8.copy_(torch.from_numpy(np.ascontiguousarray(arr.reshape(-1))))
-                    d8.copy_(h8, non_blocking=True)
+                    d8, _h8 = self.rt.feed_buffer_u8(node)
+                    slot = self.rt.stage_slot(("h2d8", node.id), node.size, torch.uint8)
+                    slot[0].copy_(torch.from_numpy(np.ascontiguousarray(arr.reshape(-1))))
+                    d8.copy_(slot[0], non_blocking=True)
+                    slot[1] = torch.cuda.Event()
+                    slot[1].record()
                     cabi.call("gg_widen_u8_i32", d8.data_ptr(), d.data_ptr(), node.size, cabi.stream_ptr())
                     self.h2d_bytes = getattr(self, "h2d_bytes", 0) + arr.size
                     continue
                 self.h2d_bytes = getattr(self, "h2d_bytes", 0) + arr.size * 4
-                h.copy_(torch.from_numpy(np.ascontiguousarray(arr.reshape(-1).astype(node.dtype.as_numpy_dtype, copy=False))))
-                d.copy_(h, non_blocking=True)
+                slot = self.rt.stage_slot(("h2d", node.id), node.size, d.dtype)
+                slot[0].copy_(torch.from_numpy(np.ascontiguousarray(arr.reshape(-1).astype(node.dtype.as_numpy_dtype, copy=False))))
+                d.copy_(slot[0], non_blocking=True)
+                slot[1] = torch.cuda.Event()
+                slot[1].record()
         self.runs += 1
         if self.rt.use_cuda_graph:
             if self.graph is None:
@@ -1204,14 +1291,25 @@ class Plan(object):
             self.kernel_launches = cabi.lib.gg_launch_count() - before
         if not to_host:
             return None
+        # device -> host: every fetched tensor is copied into a pinned slot by THIS run; the host waits for the copy's event
+        # here (TensorFlow's semantics) or, with deferred fetches, when the value is first used
         out = []
         for f in self.fetches:
             if isinstance(f, Tensor):
                 t = self.buf[f.id][:max(f.size, 1)]
-                arr = t.cpu().numpy().reshape(f.shape)
-                out.append(arr[()] if len(f.shape) == 0 else arr)
+                slot = self.rt.stage_slot(("d2h", id(self), f.id), t.numel(), t.dtype)
+                slot[0].copy_(t, non_blocking=True)
+                slot[1] = torch.cuda.Event()
+                slot[1].record()
+                self.d2h_bytes = getattr(self, "d2h_bytes", 0) + t.numel() * t.element_size()
+                val = Deferred(slot[0], slot[1], f.shape)
+                if deferred:
+                    slot[2] = val
+                out.append(val)
             else:
                 out.append(None)
+        if not deferred:
+            out = [v.result() if v is not None else None for v in out]
         return out
 
     def launches_per_run(self):

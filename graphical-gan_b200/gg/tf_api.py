@@ -511,8 +511,12 @@ train = _Train()
 
 
 class Session(object):
-    def __init__(self, *_, **__):
-        pass
+    """tf.Session over the plan compiler.  `deferred_fetches=True` (an extension; also settable as an attribute) makes
+    `run` return executor.Deferred values: the device->host copy of every fetch is still enqueued by the call, but the host
+    waits for it only when the value is first used, so the loop can feed step i+1 while step i executes."""
+
+    def __init__(self, *_, **kw):
+        self.deferred_fetches = bool(kw.get("deferred_fetches", False))
 
     def __enter__(self):
         return self
@@ -522,7 +526,7 @@ class Session(object):
 
     def run(self, fetches, feed_dict=None):
         from .executor import RT
-        return RT.run(fetches, feed_dict)
+        return RT.run(fetches, feed_dict, deferred=self.deferred_fetches)
 
     def close(self):
         pass

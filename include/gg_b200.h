@@ -302,6 +302,13 @@ int gg_probe_umma_tf32(const float* A, const float* Bm, float* D, int N, int K, 
  * %globaltimer timeline (slot 0 start, 1+i TMA issue of k-block i, 64+i operands landed, 128 accumulator ready,
  * 129 partial written, 131 epilogue done).  NULL disables it. */
 int gg_debug_set_buffer(void* device_buffer_256_int64);
+/* development aid for the one-launch small-channel filter gradient (gg_conv2d_wgrad with Ci <= 4): when set to a device buffer
+ * of >= 8 * 160 int64, CTA b writes %globaltimer stamps at [8*b + s]: s = 0 entry, 1 tiles staged, 2 FMA loops done,
+ * 3 cluster rendezvous, 4 cluster partial in L2, 5 ticket taken, 6 (last cluster) dw written.  NULL disables it. */
+int gg_debug_set_small_buffer(void* device_buffer_int64);
+/* its launch plan for a geometry: out8 = {served, rows per unit, units, threads, pixel groups, clusters, dynamic smem bytes,
+ * clusters of 8 CTAs the device keeps resident at once (cudaOccupancyMaxActiveClusters)} */
+int gg_debug_small_wgrad_info(int B, int H, int W, int Ci, int Co, int k, int stride, int Ho, int Wo, int* out8);
 
 /* ---- tooling: timed event nodes inside a captured CUDA graph (tools/trace_step.py) ------ */
 int gg_trace_event_create(void** event_out);

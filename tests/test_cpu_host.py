@@ -156,3 +156,22 @@ def test_gmgan_graph_builds_with_reference_parameter_inventory():
     assert rec_src.id not in reach and fake_src.id in reach
     # ... and the discriminator reads the generator's NHWC output directly: the NCHW view of fake_x is never materialised
     assert g.fake_x.inputs[0].id not in reach
+
+
+def test_deferred_value_waits_once_and_acts_like_numpy():
+    """executor.Deferred (Session(deferred_fetches=True)): the host waits for the copy's event on first use only, and the
+    value then behaves like the numpy result TensorFlow's session.run returns"""
+    import torch
+    from gg.executor import Deferred
+
+    class Ev(object):
+        def __init__(self): self.waits = 0
+        def synchronize(self): self.waits += 1
+        def query(self): return True
+    ev = Ev()
+    d = Deferred(torch.tensor([2.5]), ev, ())
+    assert ev.waits == 0 and d.done()
+    assert float(d) == 2.5 and d + 1 == 3.5 and 2 * d == 5.0 and d > 2 and "%.2f" % d == "2.50" and ev.waits == 1
+    assert np.mean([d, d]) == 2.5 and np.asarray(d).shape == ()
+    m = Deferred(torch.arange(6, dtype=torch.float32), Ev(), (2, 3))
+    assert m.shape == (2, 3) and m[1][2] == 5.0 and np.array_equal(np.asarray(m), np.arange(6, dtype=np.float32).reshape(2, 3))

@@ -67,48 +67,52 @@ def emu_fwd(x,w,B,H,W,Ci,Co,k,s,pt,pl,Ho,Wo):
             if ho<Ho and wo<Wo: y[b,ho,wo]=acc
     assert not np.isnan(y).any()
     return y
-def wgrad_plan(B,H,W,Ci,Co,k,s,Ho,Wo):
-    """mirror of wgrad_plan() in csrc/gg_conv_small.cu"""
+def wgrad_plan(B,H,W,Ci,Co,k,s,Ho,Wo,resident=15):
+    """mirror of wgrad_plan() + the resident-cluster cap of conv_small_wgrad() in csrc/gg_conv_small.cu"""
     TK,CL,MAXC=5,8,18
     K=k*k*Ci
     assert 1<=Ci<=4 and Co%8==0 and K<=100
     rh_max=16384//(Wo*Co); assert rh_max>=1
     RH=min(Ho,rh_max)
-    while RH>1 and B*(-(-Ho//RH))<128: RH=(RH+1)//2
-    upi=-(-Ho//RH); units=B*upi
-    PH=(RH-1)*s+k; PW=(Wo-1)*s+k
+    PW=(Wo-1)*s+k
     NT=(-(-K//TK))*(Co//8); assert NT<=512
-    PS=min(512//NT,4,RH*Wo)
+    PS=min(512//NT,4)
     threads=max(128,-(-NT*PS//32)*32)
-    clusters=min(-(-units//CL),MAXC)
-    return dict(RH=RH,upi=upi,units=units,PH=PH,PW=PW,NT=NT,PS=PS,threads=threads,grid=clusters*CL,clusters=clusters)
+    clusters=min(-(-(B*Ho)//(2*CL)),MAXC,resident)
+    return dict(RH=RH,PW=PW,NT=NT,PS=PS,threads=threads,grid=clusters*CL,clusters=clusters)
 def emu_wgrad(x,dy,B,H,W,Ci,Co,k,s,pt,pl,Ho,Wo):
-    """thread-by-thread emulation of conv_small_wgrad_kernel: units, x patch / dy rows in 'shared memory', the (5 filter rows x
-    8 channels) register tile, pixel groups, the CTA fold, the cluster fold by float4 slices and the last-cluster fold"""
+    """thread-by-thread emulation of conv_small_wgrad_kernel: equal contiguous row ranges per CTA walked in units of <= RH rows
+    of one image, x patch / dy rows in 'shared memory', the (5 filter rows x 8 channels) register tile, pixel groups, the CTA
+    fold, the cluster fold by float4 slices and the last-cluster fold"""
     P=wgrad_plan(B,H,W,Ci,Co,k,s,Ho,Wo)
-    RH,upi,units,PH,PW,NT,PS,grid,ncl=P['RH'],P['upi'],P['units'],P['PH'],P['PW'],P['NT'],P['PS'],P['grid'],P['clusters']
-    K=k*k*Ci; N=K*Co; nq8=Co//8; NPIX=RH*Wo; PP=-(-NPIX//PS)
+    RH,PW,NT,PS,grid,ncl=P['RH'],P['PW'],P['NT'],P['PS'],P['grid'],P['clusters']
+    K=k*k*Ci; N=K*Co; nq8=Co//8
     tiles=np.zeros((grid,N))
+    total=B*Ho; seen=np.zeros(total,int)
     for cta in range(grid):
         accs=np.zeros((NT*PS,5,8))
-        for u in range(cta,units,grid):
-            b=u//upi; ho0=(u%upi)*RH; rows=min(RH,Ho-ho0)
+        g_lo,g_hi=total*cta//grid,total*(cta+1)//grid
+        g0=g_lo
+        while g0<g_hi:
+            b,ho0=g0//Ho,g0%Ho
+            rows=min(Ho-ho0,RH,g_hi-g0)
+            seen[g0:g0+rows]+=1
+            g0+=rows
+            npix=rows*Wo; PP=-(-npix//PS)
             hi0=ho0*s-pt; wi0=-pl
-            sx=np.zeros(PH*PW*Ci)
-            for i in range(PH*PW*Ci):
+            nx=((rows-1)*s+k)*PW*Ci
+            sx=np.zeros(nx)
+            for i in range(nx):
                 c=i%Ci; iw=(i//Ci)%PW; ih=i//(Ci*PW); hi,wi=hi0+ih,wi0+iw
                 if 0<=hi<H and 0<=wi<W: sx[i]=x[b,hi,wi,c]
-            sdy=np.zeros(NPIX*Co)
-            flat=dy[b].reshape(-1)
-            nvalid=rows*Wo*Co
-            sdy[:nvalid]=flat[ho0*Wo*Co:ho0*Wo*Co+nvalid]
+            sdy=dy[b].reshape(-1)[ho0*Wo*Co:(ho0+rows)*Wo*Co]
             for tid in range(NT*PS):
                 ps,tt=tid//NT,tid%NT; g,q=tt//nq8,tt%nq8
                 off=[]
                 for j in range(5):
                     kk=g*5+j; tap,c=kk//Ci,kk%Ci
                     off.append(((tap//k)*PW+(tap%k))*Ci+c if kk<K else 0)
-                p_lo=ps*PP; p_hi=min(NPIX,p_lo+PP)
+                p_lo=min(npix,ps*PP); p_hi=min(npix,p_lo+PP)
                 pr,wo=p_lo//Wo,p_lo%Wo
                 for pix in range(p_lo,p_hi):
                     xo=((pr*s)*PW+wo*s)*Ci
@@ -127,6 +131,7 @@ def emu_wgrad(x,dy,B,H,W,Ci,Co,k,s,pt,pl,Ho,Wo):
                     if kk<K:
                         tiles[cta,kk*Co+q*4:kk*Co+q*4+4]+=accs[tid,j,:4]
                         tiles[cta,kk*Co+(q+nq8)*4:kk*Co+(q+nq8)*4+4]+=accs[tid,j,4:]
+    assert (seen==1).all()
     n4=N//4; per=-(-n4//8)
     part=np.full((ncl,N),np.nan)
     for cid in range(ncl):

@@ -104,6 +104,9 @@ GEMM_CASES = [
     (4608, 512, 64, 1, 0),   # dW = X^T dY
     (64, 4608, 512, 0, 1),   # dX = dY W^T
     (50, 33, 77, 0, 0), (33, 50, 77, 1, 1),   # ragged
+    # the thin products served by gemm_rowdot_kernel / gemm_smallk_kernel (critic output layer and its gradients, prior lookups)
+    (128, 1, 512, 0, 0), (128, 512, 1, 0, 1), (512, 1, 128, 1, 0), (64, 128, 30, 0, 0), (30, 128, 64, 1, 0), (128, 3, 200, 0, 1),
+    (7, 5, 3, 1, 1), (19, 2, 1000, 0, 0),
 ]
 
 

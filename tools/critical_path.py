@@ -43,9 +43,9 @@ cabi.call = _fake_call
 # kernels each C-ABI entry point may launch (prefix match on the ncu kernel name)
 KERNELS = {
     "gg_gemm": ("gemm_kernel", "gemm_splitk_finish", "conv_tc_kernel", "im2col", "col2im"),
-    "gg_conv2d_fwd": ("conv_tc_kernel<0>", "im2col_kernel", "conv_fwd_kernel"),
-    "gg_conv2d_dgrad": ("conv_tc_kernel<1>", "col2im_kernel", "conv_dgrad_kernel"),
-    "gg_conv2d_wgrad": ("conv_tc_kernel<2>", "im2col_kernel", "conv_wgrad_kernel", "wgrad_finish"),
+    "gg_conv2d_fwd": ("conv_tc_kernel<0>", "im2col_kernel", "conv_fwd_kernel", "conv_small_fwd_kernel"),
+    "gg_conv2d_dgrad": ("conv_tc_kernel<1>", "col2im_kernel", "conv_dgrad_kernel", "conv_small_dgrad_kernel"),
+    "gg_conv2d_wgrad": ("conv_tc_kernel<2>", "im2col_kernel", "conv_wgrad_kernel", "wgrad_finish", "conv_small_wgrad_kernel"),
     "gg_reduce_ws": ("reduce_cols_sliced_kernel", "reduce_cols_kernel", "reduce_rows_kernel"),
     "gg_reduce": ("reduce_cols_kernel", "reduce_rows_kernel", "reduce_all"),
     "gg_adam_multi": ("adam_tick_kernel", "adam_multi_kernel"),
@@ -62,7 +62,7 @@ def load_launches(path):
     out = []
     for r in rows[hdr + 1:]:
         if len(r) > vi and r[0].isdigit():
-            name = r[ki].replace("void ", "").replace("gg::", "").replace("<unnamed>::", "")
+            name = r[ki].replace("void ", "").replace("gg::", "").replace("<unnamed>::", "").replace("(anonymous namespace)::", "")
             out.append((name, float(r[vi]) / 1e3))
     return out
 
@@ -82,6 +82,8 @@ def match(calls, launches, pos):
                         and not got[-1][0].startswith("im2col"):
                     break
                 if got and name.startswith("gg_conv2d") and launches[pos][0].startswith("im2col") :
+                    break
+                if got and got[-1][0].startswith("conv_small"):      # the one-launch small-channel kernels stand alone
                     break
                 if got and name.startswith("gg_conv2d") and launches[pos][0].startswith("conv_tc") and got[-1][0].startswith("conv_tc"):
                     break
