@@ -428,6 +428,20 @@ extern "C" int gg_adam_multi(const gg_adam_entry* table, const gg_adam_chunk* ch
   return check_launch("gg_adam_multi");
 }
 
+// the two halves of gg_adam_multi as separate entry points: a step whose update is split by gradient readiness advances the
+// bias-correction state once (gg_adam_tick) and applies the update to disjoint parameter sets at different times (gg_adam_apply)
+extern "C" int gg_adam_tick(void* state, float beta1, float beta2, void* stream) {
+  GG_LAUNCH(adam_tick_kernel, 1, 32, 0, as_stream(stream), reinterpret_cast<AdamState*>(state), (double)beta1, (double)beta2);
+  return check_launch("gg_adam_tick");
+}
+extern "C" int gg_adam_apply(const gg_adam_entry* table, const gg_adam_chunk* chunks, int n_chunks, const void* state, float lr,
+                             float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  if (n_chunks <= 0) return GG_OK;
+  GG_LAUNCH(adam_multi_kernel, n_chunks, 256, 0, as_stream(stream), table, chunks, n_chunks,
+            reinterpret_cast<const AdamState*>(state), lr, beta1, beta2, eps, grad_scale);
+  return check_launch("gg_adam_apply");
+}
+
 __global__ void __launch_bounds__(256) rmsprop_multi_kernel(const gg_adam_entry* __restrict__ table,
                                                             const gg_adam_chunk* __restrict__ chunks, int n_chunks, float lr,
                                                             float decay, float eps, float gscale) {

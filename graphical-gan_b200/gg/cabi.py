@@ -84,6 +84,8 @@ SIGNATURES = {
     "gg_dist_mean": (c_i, [c_p, c_p, c_ll, c_i, c_f, c_p, c_i, c_p]),
     "gg_gp_slope_penalty": (c_i, [c_p, c_i, c_i, c_f, c_p, c_p, c_p]),
     "gg_adam_multi": (c_i, [c_p, c_p, c_i, c_p, c_f, c_f, c_f, c_f, c_f, c_p]),
+    "gg_adam_tick": (c_i, [c_p, c_f, c_f, c_p]),
+    "gg_adam_apply": (c_i, [c_p, c_p, c_i, c_p, c_f, c_f, c_f, c_f, c_f, c_p]),
     "gg_rmsprop_multi": (c_i, [c_p, c_p, c_i, c_f, c_f, c_f, c_f, c_p]),
     "gg_pack_grads": (c_i, [c_p, c_p, c_i, c_p, c_p, c_i, c_p]),
     "gg_rng_tick": (c_i, [c_p, c_p]),

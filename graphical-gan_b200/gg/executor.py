@@ -446,14 +446,15 @@ class Plan(object):
         torch = _torch()
         self.placed_flat, self.flat, self.bucket_plan = {}, {}, {}
         world = ggdist.world_size()
-        if world <= 1:
-            return
         # readiness of a node = length of the longest dependency chain below it (tensor-core launches weigh ~6 glue
         # launches): the toposort position is useless here — a depth-first order emits the deepest gradient's whole chain first
         pos = {}
         for n in self.order:
             w = 6 if n.op in ("conv", "matmul") else (0 if n.op in ALIAS_OPS or not n.inputs else 1)
             pos[n.id] = w + max([pos.get(i.id, 0) for i in n.inputs] or [0])
+        self.ready_pos = pos
+        if world <= 1:
+            return
         uses = {}
         for n in self.order:
             if n.id in self.fed:
@@ -492,9 +493,14 @@ class Plan(object):
             for e in entries:
                 if e["direct"]:
                     self.placed_flat[e["own"].id] = (op.attrs["opt_id"], e["off"])
-            # cut into buckets of roughly equal bytes in readiness order
+            # cut into buckets of roughly equal bytes in readiness order; the gradients that become ready LAST (split update,
+            # _late_vars) form a small bucket of their own, so that the exchange exposed after the last backward kernel is a
+            # few KB instead of a quarter of the model
+            late = self._late_vars([(e["var"], e["own"]) for e in entries])
+            main = [e for e in entries if e["var"].id not in late]
+            tail = [e for e in entries if e["var"].id in late]
             buckets, cur, acc, per = [], [], 0, total / float(n_buckets)
-            for e in entries:
+            for e in main:
                 cur.append(e)
                 acc += (e["var"].size + 63) & ~63
                 if acc >= per * (len(buckets) + 1) and len(buckets) < n_buckets - 1:
@@ -502,7 +508,30 @@ class Plan(object):
                     cur = []
             if cur:
                 buckets.append(cur)
+            if tail:
+                buckets.append(tail)
             self.bucket_plan[op.attrs["opt_id"]] = (entries, buckets, total)
+
+    def _late_vars(self, pairs):
+        """ids of the variables whose gradients become ready last (within one tensor-core launch of the deepest one): the
+        optimiser update is split so that only THEIR update waits for the end of the backward pass; every other parameter is
+        updated as soon as its own gradient and the last kernel reading it are done.  OPT-IN (GG_SPLIT_UPDATE=1): measured on the
+        B200 the early update (87-114 MB of L2 traffic) slows the last backward kernels it overlaps by more than it saves — 0.888
+        vs 0.874 ms per iteration (profiles/sched_variants_r2.txt)."""
+        if os.environ.get("GG_SPLIT_UPDATE", "0") != "1" or len(pairs) < 2:
+            return set()
+        pos = getattr(self, "ready_pos", {})
+        ready = {}
+        for v, g in pairs:
+            own = g
+            while own.op in ("reshape", "stop_gradient") and own.id not in self.fed and own.inputs:
+                own = own.inputs[0]
+            ready[v.id] = pos.get(own.id, 0)
+        top = max(ready.values())
+        late = set(vid for vid, r in ready.items() if r > top - 6)
+        if len(late) == len(pairs):
+            return set()
+        return late
 
     def _concat_storage(self, cid):
         if cid not in self._concat_bufs:
@@ -960,9 +989,17 @@ class Plan(object):
         state = rt.opt_state[op.attrs["opt_id"]]
         sizes = [v.size for v, _ in pairs]
         world = ggdist.world_size()
-        chunks = b"".join(struct.pack("<iiq", ti, 0, off) for ti, n in enumerate(sizes) for off in range(0, n, cabi.GG_ADAM_CHUNK))
-        n_chunks = len(chunks) // 16
-        chk = torch.frombuffer(bytearray(chunks), dtype=torch.uint8).to(rt.dev())
+        # split update: the variables whose gradients arrive last (`late`) are updated by the barrier launch at the end of
+        # the step; all others by an earlier launch that waits only for their own gradients and for the kernels reading them
+        late = self._late_vars(pairs) if op.kind == "adam" else set()
+
+        def chunk_table(sel):
+            raw = b"".join(struct.pack("<iiq", ti, 0, off) for ti, n in enumerate(sizes) if sel(pairs[ti][0].id)
+                           for off in range(0, n, cabi.GG_ADAM_CHUNK))
+            return len(raw) // 16, torch.frombuffer(bytearray(raw) or bytearray(16), dtype=torch.uint8).to(rt.dev())
+        n_chunks, chk = chunk_table(lambda vid: vid not in late)           # the early set (everything when there is no split)
+        n_late, chk_late = chunk_table(lambda vid: vid in late)
+        self.keep.append(chk_late)
 
         def table(gptrs):
             raw = b"".join(struct.pack("<QQQQq", p.data_ptr(), gp, m.data_ptr(), v.data_ptr(), n)
@@ -996,9 +1033,43 @@ class Plan(object):
                 self.steps.append(fn)
                 self._add_groups(b0, len(self.steps), reads, "bucket%d_%d" % (op.attrs["opt_id"], bi), barrier=False)
             gscale = 1.0 / world
-        self._opt_update_start = len(self.steps)
         tp, cp, sp = adam_tab.data_ptr(), chk.data_ptr(), state.data_ptr()
         a = op.attrs
+        if op.kind == "adam" and late:
+            lr, b1, b2, eps = a["lr"], a["beta1"], a["beta2"], a["eps"]
+            # (1) the state advance: no dependencies, any time before the updates
+            t0 = len(self.steps)
+            self.steps.append(lambda st: cabi.call("gg_adam_tick", sp, b1, b2, st))
+            tick_id = "op%d_tick" % op.id
+            self._add_groups(t0, len(self.steps), set(), tick_id, barrier=False)
+            # (2) the early update: after the gradients of its variables (their all-reduced buckets under data parallelism)
+            # and after the LAST kernel group of every node that reads one of those variables
+            early_vars = set(v.id for v, _ in pairs if v.id not in late)
+            reads = {tick_id}
+            if world > 1:
+                for bi, bucket in enumerate(buckets):
+                    if any(e["var"].id in early_vars for e in bucket):
+                        reads.add("bucket%d_%d" % (op.attrs["opt_id"], bi))
+            else:
+                for v, g in pairs:
+                    if v.id in early_vars:
+                        reads |= self._owners(g)
+            for gi, grp in enumerate(self.groups):
+                if grp["part"][0] == 0 and (grp["reads"] & early_vars):
+                    reads.add(self.groups[gi + grp["part"][1] - 1]["writes"])
+            e0 = len(self.steps)
+            fn = lambda st: cabi.call("gg_adam_apply", tp, cp, n_chunks, sp, lr, b1, b2, eps, gscale, st)
+            fn.cost_us = 3.0 + n_chunks * cabi.GG_ADAM_CHUNK * 28 / 5.5e6      # 28 B per parameter at ~5.5 TB/s (L2-resident)
+            self.steps.append(fn)
+            self._add_groups(e0, len(self.steps), reads, "op%d_early" % op.id, barrier=False)
+            # (3) the late update: the step's barrier
+            self._opt_update_start = len(self.steps)
+            cl = chk_late.data_ptr()
+            fn = lambda st: cabi.call("gg_adam_apply", tp, cl, n_late, sp, lr, b1, b2, eps, gscale, st)
+            fn.cost_us = 3.0 + n_late * cabi.GG_ADAM_CHUNK * 28 / 5.5e6
+            self.steps.append(fn)
+            return
+        self._opt_update_start = len(self.steps)
         if op.kind == "adam":
             lr, b1, b2, eps = a["lr"], a["beta1"], a["beta2"], a["eps"]
             self.steps.append(lambda st: cabi.call("gg_adam_multi", tp, cp, n_chunks, sp, lr, b1, b2, eps, gscale, st))
@@ -1035,8 +1106,8 @@ class Plan(object):
         n_k = g["end"] - g["start"]
         if g.get("collective"):
             return float(getattr(self.steps[g["start"]], "cost_us", 60.0))
-        if node is None:
-            return 16.0 if g["barrier"] else 2.0          # optimiser update / rng tick
+        if node is None:                                   # optimiser update (whole / early / late part) / rng tick
+            return float(getattr(self.steps[g["start"]], "cost_us", 16.0 if g["barrier"] else 2.0))
         mb = node.size * 4 / 1e6
         op = node.op
         if op == "conv":
@@ -1101,7 +1172,19 @@ class Plan(object):
             return self._schedule_in_order(idxs, deps, n_streams)
         import heapq
         indeg = {gi: len(deps[gi]) for gi in idxs}
-        ready = [(-bottom[gi], pos[gi], gi) for gi in idxs if indeg[gi] == 0]
+        # Issue order.  "heft": longest remaining chain first — the critical chain gets its streams, but every group with a
+        # short tail (weight gradients, bias-gradient reductions: only the update waits for them) is issued LAST, i.e. queued
+        # behind everything its stream already holds although it was ready long before (profiles/timeline_disc_r2.txt: ~40
+        # glue kernels after the last backward kernel).  "asap": earliest possible start first (ties: longest chain), so
+        # that such groups fill the idle streams while the chain runs.
+        mode = os.environ.get("GG_SCHED", "asap")
+        est = {}
+        for gi in idxs:
+            est[gi] = max([est[d] + cost[d] for d in deps[gi]] or [0.0])
+
+        def prio(gi):
+            return (est[gi], -bottom[gi], pos[gi], gi) if mode == "asap" else (-bottom[gi], pos[gi], 0, gi)
+        ready = [prio(gi) for gi in idxs if indeg[gi] == 0]
         heapq.heapify(ready)
         free_at = [0.0] * n_streams
         finish, assign, waits, need_event, order, issued = {}, {}, {}, set(), [], {}
@@ -1112,12 +1195,23 @@ class Plan(object):
         # stream of their own: in the captured graph they depend on exactly their producers.
         has_coll = any(self.groups[gi]["collective"] for gi in idxs)
         comm_stream = n_streams - 1 if (has_coll and n_streams > 2) else None
+        # Stream classes (GG_PRIO=1, >= 4 streams): groups that can slip by `slack` without moving the end of the step — weight
+        # gradients, bias-gradient reductions — go to LOW-priority streams, everything near the critical chain to HIGH-priority
+        # ones (_stream_priorities): a 128-CTA weight-gradient launch then no longer holds the SMs the chain's next launch
+        # needs; the block scheduler hands freed SMs to the pending high-priority grid first.
+        prio_on = os.environ.get("GG_PRIO", "1") == "1" and n_streams >= 4
+        pr = self._stream_priorities(n_streams, comm_stream is not None) if prio_on else None
+        makespan = max([est[gi] + bottom[gi] for gi in idxs] or [0.0])
+        slack_min = float(os.environ.get("GG_PRIO_SLACK_US", "40"))
+        low_cls = {gi: (makespan - (est[gi] + bottom[gi]) > slack_min) for gi in idxs}
         while ready:
-            _, _, gi = heapq.heappop(ready)
+            gi = heapq.heappop(ready)[-1]
             best = None
             is_coll = self.groups[gi]["collective"]
             for s in range(n_streams):
                 if comm_stream is not None and (s == comm_stream) != bool(is_coll):
+                    continue
+                if pr is not None and not is_coll and (pr[s] == 0) != low_cls[gi]:
                     continue
                 t = free_at[s]
                 for d in deps[gi]:
@@ -1143,10 +1237,18 @@ class Plan(object):
             for c in succ[gi]:
                 indeg[c] -= 1
                 if indeg[c] == 0:
-                    heapq.heappush(ready, (-bottom[c], pos[c], c))
+                    heapq.heappush(ready, prio(c))
         assert len(order) == len(idxs)
         self.sched_estimate_us = max(finish.values()) if finish else 0.0
         return order, assign, waits, need_event
+
+    @staticmethod
+    def _stream_priorities(n_streams, has_comm):
+        """priority of each stream of a captured step: 0 = low (the capture's own stream, index 0, and the last side streams),
+        -1 = high (side streams 1..h and, under data parallelism, the collectives' stream)"""
+        n_side = n_streams - 1 - (1 if has_comm else 0)
+        n_low_side = max(1, n_side // 3)
+        return [0] + [-1] * (n_side - n_low_side) + [0] * n_low_side + ([-1] if has_comm else [])
 
     def _schedule_in_order(self, idxs, deps, n_streams):
         """the plan's own topological order; a group continues the stream of its most recent producer when that producer is
@@ -1173,7 +1275,12 @@ class Plan(object):
         torch = _torch()
         order, assign, waits, need_event = self._schedule_range(idxs, n_streams)
         g = torch.cuda.CUDAGraph()
-        side = [torch.cuda.Stream() for _ in range(max(n_streams - 1, 0))]
+        has_comm = any(self.groups[gi]["collective"] for gi in idxs) and n_streams > 2
+        if os.environ.get("GG_PRIO", "1") == "1" and n_streams >= 4:
+            pr = self._stream_priorities(n_streams, has_comm)
+            side = [torch.cuda.Stream(priority=pr[i + 1]) for i in range(n_streams - 1)]   # kernel nodes inherit the priority
+        else:
+            side = [torch.cuda.Stream() for _ in range(max(n_streams - 1, 0))]
         self.keep.append(side)
         trace = os.environ.get("GG_TRACE", "0") == "1"      # tools/trace_step.py: timed event nodes around every group
         with torch.cuda.graph(g):

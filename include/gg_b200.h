@@ -238,6 +238,12 @@ typedef struct { int tensor; int pad; long long offset; } gg_adam_chunk;
 int gg_adam_multi(const gg_adam_entry* table, const gg_adam_chunk* chunks, int n_chunks, void* state,
                   float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
 /* RMSProp (tf.train.RMSPropOptimizer defaults decay .9 momentum 0 eps 1e-10; gan_inference.py:8-13): ms in m */
+/* gg_adam_multi = gg_adam_tick (advance {b1^t, b2^t, t} once per step) + gg_adam_apply (the update of the listed tensors with
+ * the CURRENT state).  A step may apply disjoint tensor sets at different times: parameters whose gradients are ready early are
+ * updated while the last backward kernels still run (gg/executor.py _emit_optimizer). */
+int gg_adam_tick(void* state, float beta1, float beta2, void* stream);
+int gg_adam_apply(const gg_adam_entry* table, const gg_adam_chunk* chunks, int n_chunks, const void* state,
+                  float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
 int gg_rmsprop_multi(const gg_adam_entry* table, const gg_adam_chunk* chunks, int n_chunks,
                      float lr, float decay, float eps, float grad_scale, void* stream);
 /* multi-tensor gather/scatter between a table of tensors and one flat bucket (gradient all-reduce staging) */
