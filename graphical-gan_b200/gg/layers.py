@@ -33,6 +33,34 @@ def conv2d_nhwc(x, filters, stride, padding, bias=None):
     return O.conv("fwd", x, filters, conv_geometry(B, H, W, Ci, Co, k, stride, padding), bias)
 
 
+def conv3d_ndhwc(x, filters, stride_len, stride, padding):
+    """tf.nn.conv3d(x [N,L,H,W,Ci], filters [fl,k,k,Ci,Co], strides [1,stride_len,stride,stride,1], 'SAME', 'NDHWC')
+    (tflib/ops/conv3d.py:33-39) as ONE 2-D convolution: the fl depth taps of every output depth index are laid side by side
+    along the channel axis (x' [Lo*N, H, W, fl*Ci], zero slices where TF's SAME padding reaches outside the clip) and the
+    filter's depth taps are concatenated the same way (w' [k, k, fl*Ci, Co]).  Same FLOPs as the 3-D form, and every piece is
+    a graph op with a gradient rule, so first- and second-order gradients come with it."""
+    N, L, H, W, Ci = x.shape
+    fl, k, k2, Ci2, Co = filters.shape
+    if k != k2 or Ci != Ci2:
+        raise ValueError("filter %s does not match input %s" % (tuple(filters.shape), tuple(x.shape)))
+    if padding != 'SAME':
+        raise NotImplementedError("conv3d padding %r (the reference only uses 'SAME', conv3d.py:37)" % (padding,))
+    Lo = -(-L // stride_len)
+    pad_total = max((Lo - 1) * stride_len + fl - L, 0)
+    before = pad_total // 2                                   # TF SAME: the smaller half in front
+    xp = O.pad_axis(x, 1, before, L + pad_total) if pad_total else x
+    frames = []
+    for lo in range(Lo):
+        taps = [O.getitem(xp, (slice(None), lo * stride_len + t)) for t in range(fl)]          # fl x [N, H, W, Ci]
+        frames.append(O.concat(taps, 3))
+    xcat = O.concat(frames, 0)                                                                   # [Lo*N, H, W, fl*Ci], lo-major
+    wcat = O.concat([O.getitem(filters, t) for t in range(fl)], 2)                             # [k, k, fl*Ci, Co]
+    y = conv2d_nhwc(xcat, wcat, stride, 'SAME')                                                  # [Lo*N, Ho, Wo, Co]
+    _, Ho, Wo, _ = y.shape
+    y = O.transpose(O.reshape(y, [Lo, N, Ho * Wo * Co]), (1, 0, 2))
+    return O.reshape(y, [N, Lo, Ho, Wo, Co])
+
+
 def conv2d_nchw(x, filters, stride, padding, bias=None):
     return O.to_nchw(conv2d_nhwc(O.to_nhwc(x), filters, stride, padding, bias))
 

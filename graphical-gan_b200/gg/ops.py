@@ -69,6 +69,20 @@ def transpose(x, perm):
         comp = tuple(inner[p] for p in perm)
         return transpose(x.inputs[0], comp)
     shape = tuple(x.shape[p] for p in perm)
+    if len(perm) > 4:
+        # the layout kernels take rank <= 4: input axes that stay adjacent and in order travel as ONE axis
+        # (tf.transpose(x, [0, 1, 3, 4, 2]) of the SSGAN 3dcnn critic, ssgan_inference_moving_mnist.py:356, is [NL, C, HW] -> [NL, HW, C])
+        groups = []
+        for q in perm:
+            if groups and groups[-1][-1] + 1 == q:
+                groups[-1].append(q)
+            else:
+                groups.append([q])
+        if len(groups) > 4:
+            raise NotImplementedError("transpose %s of a rank-%d tensor does not reduce to rank <= 4" % (perm, len(perm)))
+        in_order = sorted(range(len(groups)), key=lambda g: groups[g][0])
+        merged = reshape(x, [prod(x.shape[a] for a in groups[g]) for g in in_order])
+        return reshape(transpose(merged, [in_order.index(g) for g in range(len(groups))]), shape)
     return Tensor("transpose", (x,), {"perm": perm}, shape, x.dtype)
 
 

@@ -359,6 +359,13 @@ class _NN(object):
         return conv2d_nhwc(input, filter, strides[1], padding)
 
     @staticmethod
+    def conv3d(input=None, filter=None, strides=None, padding="SAME", data_format="NDHWC", **_):   # noqa: A002
+        from .layers import conv3d_ndhwc
+        if data_format != "NDHWC" or strides[2] != strides[3] or strides[0] != 1 or strides[4] != 1:
+            raise NotImplementedError("tf.nn.conv3d: NDHWC with strides [1, sl, s, s, 1] (tflib/ops/conv3d.py:33-39)")
+        return conv3d_ndhwc(input, filter, int(strides[1]), int(strides[2]), padding)
+
+    @staticmethod
     def conv2d_transpose(value=None, filter=None, output_shape=None, strides=None, padding="SAME", **_):   # noqa: A002
         from .layers import conv2d_transpose_nhwc
         return conv2d_transpose_nhwc(value, filter, list(output_shape), strides[1], padding)

@@ -20,8 +20,9 @@ import gan_inference_svhn as _base
 from gan_inference_svhn import SUPPORTED, tf, lib
 
 
-def build_graph(MODE='ali', BATCH_SIZE=64, DIM=64, LR=2e-4):
-    return _base.build_graph(MODE=MODE, BATCH_SIZE=BATCH_SIZE, DIM=DIM, LR=LR, BN_FLAG=MODE not in ('vegan', 'vegan-wgan-gp'))
+def build_graph(MODE='ali', BATCH_SIZE=64, DIM=64, LR=2e-4, Z_SAMPLES=100):
+    bn = MODE not in ('vegan', 'vegan-wgan-gp', 'vegan-kl', 'vegan-jsd', 'vegan-ikl')        # :72-77
+    return _base.build_graph(MODE=MODE, BATCH_SIZE=BATCH_SIZE, DIM=DIM, LR=LR, BN_FLAG=bn, Z_SAMPLES=Z_SAMPLES)
 
 
 def main(argv=None):
@@ -51,12 +52,16 @@ def main(argv=None):
         for iteration in range(args.iters):                                                  # :440-470
             start_time = time.time()
             if iteration > 0:
-                session.run([g.gen_cost, g.gen_train_op], feed_dict={g.real_x_int: next(gen)})
+                gc, _ = session.run([g.gen_cost, g.gen_train_op], feed_dict={g.real_x_int: next(gen)})
             for i in range(g.CRITIC_ITERS):
                 dc, _ = session.run([g.disc_cost, g.disc_train_op], feed_dict={g.real_x_int: next(gen)})
                 if g.clip_disc_weights is not None:
                     session.run(g.clip_disc_weights)
-            lib.plot.plot('train disc cost', dc)
+            if g.CRITIC_ITERS == 0:                                                          # no-discriminator modes
+                if iteration > 0:
+                    lib.plot.plot('train gen cost ', gc)
+            else:
+                lib.plot.plot('train disc cost', dc)
             lib.plot.plot('time', time.time() - start_time)
             if (iteration < 5) or (iteration % 100 == 99):
                 lib.plot.flush()

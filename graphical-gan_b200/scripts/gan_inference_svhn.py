@@ -25,25 +25,35 @@ import tflib.ops.conv2d
 import tflib.ops.batchnorm
 import tflib.ops.deconv2d
 import tflib.objs.gan_inference
+import tflib.objs.kl_aggregated
+import tflib.objs.mmd
 import tflib.utils.distance
 import tflib.plot
 
-SUPPORTED = ['ali', 'alice', 'alice-z', 'alice-x', 'vegan', 'vegan-wgan-gp', 'wali', 'wali-gp']
+NO_DISC = ['vegan-mmd', 'vegan-kl', 'vegan-ikl', 'vegan-jsd']                                # :46-47 CRITIC_ITERS = 0
+SUPPORTED = ['ali', 'alice', 'alice-z', 'alice-x', 'vegan', 'vegan-wgan-gp', 'wali', 'wali-gp'] + NO_DISC
 
 
-def build_graph(MODE='ali', BATCH_SIZE=64, DIM=64, LR=2e-4, BN_FLAG=None):
+def build_graph(MODE='ali', BATCH_SIZE=64, DIM=64, LR=2e-4, BN_FLAG=None, Z_SAMPLES=100):
+    if MODE == 'vae':
+        # the reference builds this mode with rec_x_mean = rec_x_std = None (its Generator returns (x, None, None), :147) and
+        # lib.objs.kl.vae(real_x, None, None, ...) fails at graph construction: there is no behaviour to reproduce
+        raise NotImplementedError("MODE 'vae' does not build in the reference either (Generator returns no mean / std, :147)")
     if MODE not in SUPPORTED:
-        raise NotImplementedError("MODE %r has no discriminator (VAE / MMD / KL baselines are off the adversarial hot path)" % MODE)
+        raise NotImplementedError("unknown MODE %r" % (MODE,))
+    TYPE_Q = 'learn_std' if MODE in ['vegan-kl', 'vegan-ikl', 'vegan-jsd'] else 'no_std'     # :32-41 (TYPE_P is never read)
     DISTANCE_X = 'l2'
-    CRITIC_ITERS = 5 if MODE in ['vegan', 'vegan-wgan-gp', 'wali', 'wali-gp'] else 1        # :46-51
+    CRITIC_ITERS = 0 if MODE in NO_DISC else (5 if MODE in ['vegan', 'vegan-wgan-gp', 'wali', 'wali-gp'] else 1)   # :46-51
     LAMBDA, BETA1, OUTPUT_DIM = 1., .5, 3072
     # :64-69: False in every branch of gan_inference_svhn.py; gan_inference_cifar10.py (same networks) passes True for the
     # non-vegan modes (its :72-77).  The critics themselves carry no batch norm when BN_FLAG is off.
     BN_FLAG = bool(BN_FLAG) if BN_FLAG is not None else False
-    DIM_LATENT = 8 if MODE in ['vegan', 'vegan-wgan-gp'] else 128
+    DIM_LATENT = 8 if MODE in ['vegan', 'vegan-wgan-gp', 'vegan-kl', 'vegan-jsd', 'vegan-ikl'] else 128   # :64-69
     N_VIS = BATCH_SIZE * 2
     DR_RATE = .2
+    STD = .1                                                                                 # :43, for fix_std
     ns = types.SimpleNamespace(MODE=MODE, BATCH_SIZE=BATCH_SIZE, DIM_LATENT=DIM_LATENT, CRITIC_ITERS=CRITIC_ITERS, noise_layers=[])
+    unit_std_z = tf.constant((STD * np.ones(shape=(BATCH_SIZE, DIM_LATENT))).astype('float32'))   # :87
 
     def LeakyReLU(x, alpha=0.2):
         return tf.maximum(alpha * x, x)
@@ -84,10 +94,21 @@ def build_graph(MODE='ali', BATCH_SIZE=64, DIM=64, LR=2e-4, BN_FLAG=None):
             output = lib.ops.batchnorm.Batchnorm('Extractor.BN3', [0, 2, 3], output)
         output = LeakyReLU(output)
         output = tf.reshape(output, [-1, 4 * 4 * 4 * DIM])
+        std = mean = None
+        if TYPE_Q == 'learn_std':                                                           # :164-166
+            log_std = lib.ops.linear.Linear('Extractor.Std', 4 * 4 * 4 * DIM, DIM_LATENT, output)
+            std = tf.exp(log_std)
         output = lib.ops.linear.Linear('Extractor.Output', 4 * 4 * 4 * DIM, DIM_LATENT, output)
-        return tf.reshape(output, [-1, DIM_LATENT]), None, None
+        if TYPE_Q == 'learn_std':                                                           # :175-178 reparameterised code
+            epsilon = tf.random_normal(unit_std_z.shape)
+            ns.noise_layers.append(epsilon)
+            mean = output
+            output = tf.add(mean, tf.multiply(epsilon, std))
+        return tf.reshape(output, [-1, DIM_LATENT]), mean, std
 
-    if MODE in ['vegan', 'vegan-wgan-gp']:
+    if MODE in NO_DISC:
+        Discriminator = None                                                                # :213-214 no discriminator
+    elif MODE in ['vegan', 'vegan-wgan-gp']:
         def Discriminator(z):                                                               # :184-209 critic on the code
             output = GaussianNoiseLayer(z, std=.3)
             output = lib.ops.linear.Linear('Discriminator.Input', DIM_LATENT, 1024, output)
@@ -137,13 +158,19 @@ def build_graph(MODE='ali', BATCH_SIZE=64, DIM=64, LR=2e-4, BN_FLAG=None):
     # ---- losses (:246-360) ----
     real_x_int = tf.placeholder(tf.int32, shape=[BATCH_SIZE, OUTPUT_DIM])
     real_x = 2 * ((tf.cast(real_x_int, tf.float32) / 255.) - .5)
-    q_z, _, _ = Extractor(real_x)
+    q_z, q_z_mean, q_z_std = Extractor(real_x)
     rec_x, _, _ = Generator(q_z)
     p_z = tf.random_normal([BATCH_SIZE, DIM_LATENT])
     fake_x, _, _ = Generator(p_z)
     rec_z, _, _ = Extractor(fake_x)
+    if MODE in ['vegan-kl', 'vegan-ikl', 'vegan-jsd']:                                       # :263-265 prior of the MC estimate
+        p_z_mean = tf.constant((np.zeros(shape=(Z_SAMPLES, DIM_LATENT))).astype('float32'))
+        p_z_std = tf.constant((np.ones(shape=(Z_SAMPLES, DIM_LATENT))).astype('float32'))
 
-    if MODE in ['vegan', 'vegan-wgan-gp']:
+    disc_real = disc_fake = None
+    if MODE in NO_DISC:
+        pass
+    elif MODE in ['vegan', 'vegan-wgan-gp']:
         disc_real = Discriminator(p_z)
         disc_fake = Discriminator(q_z)
     else:
@@ -190,6 +217,21 @@ def build_graph(MODE='ali', BATCH_SIZE=64, DIM=64, LR=2e-4, BN_FLAG=None):
         slopes = tf.sqrt(tf.reduce_sum(tf.square(gradients), reduction_indices=[1]))
         gradient_penalty = 10. * (tf.reduce_mean((slopes - 1.) ** 2))
         costs = gi.wali_gp(disc_fake, disc_real, gradient_penalty, ge, disc_params)
+    elif MODE in NO_DISC:                                                                   # :322-336 generator objective only
+        rec_penalty = 1. * lib.utils.distance.distance(real_x, rec_x, DISTANCE_X)
+        ka = lib.objs.kl_aggregated
+        if MODE == 'vegan-mmd':
+            gc, gop = lib.objs.mmd.vegan_mmd(q_z, p_z, rec_penalty, ge, BATCH_SIZE, LAMBDA, lr=LR, beta1=BETA1)
+        elif MODE == 'vegan-kl':
+            gc, gop = ka.vegan_kl(q_z_mean, q_z_std, p_z_mean, p_z_std, rec_penalty, ge, Z_SAMPLES, BATCH_SIZE, DIM_LATENT, LAMBDA,
+                                  lr=LR, beta1=BETA1)
+        elif MODE == 'vegan-ikl':
+            gc, gop = ka.vegan_ikl(q_z_mean, q_z_std, p_z_mean, p_z_std, rec_penalty, ge, Z_SAMPLES, DIM_LATENT, LAMBDA,
+                                   lr=LR, beta1=BETA1)
+        else:
+            gc, gop = ka.vegan_jsd(q_z_mean, q_z_std, p_z_mean, p_z_std, rec_penalty, ge, Z_SAMPLES, BATCH_SIZE, DIM_LATENT, LAMBDA,
+                                   lr=LR, beta1=BETA1)
+        costs = (gc, None, gop, None)
     gen_cost, disc_cost, gen_train_op, disc_train_op = costs
 
     np_fixed = np.random.normal(size=(N_VIS, DIM_LATENT)).astype('float32')
@@ -226,7 +268,11 @@ def main(argv=None):
                 _disc_cost, _ = session.run([g.disc_cost, g.disc_train_op], feed_dict={g.real_x_int: next(gen)})
                 if args.mode == 'wali':
                     session.run(g.clip_disc_weights)
-            lib.plot.plot('train disc cost', _disc_cost)
+            if g.CRITIC_ITERS == 0:                                                          # no-discriminator modes
+                if iteration > 0:
+                    lib.plot.plot('train gen cost ', _gen_cost)
+            else:
+                lib.plot.plot('train disc cost', _disc_cost)
             lib.plot.plot('time', time.time() - start_time)
             if (iteration < 5) or (iteration % 100 == 99):
                 lib.plot.flush(outf, logfile)

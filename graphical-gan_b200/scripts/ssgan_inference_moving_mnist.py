@@ -5,8 +5,10 @@ State-space latent: z_l^1 -> ImplicitOperator (3-layer MLP with a residual conne
 times, :134-141) -> z_l^{1:T}; the frame generator / extractor / discriminator run on B*LEN images folded into the batch
 dimension (:170-224, :267-311); LEN-1 pairwise latent discriminators + a z_g discriminator + the frame discriminator feed
 weighted_local_epce with ratio = [1]*(LEN-1)+[1,LEN] normalised by 2*LEN (:78-79, :547).  Line numbers refer to
-/root/reference/ssgan_inference_moving_mnist.py.  The ALI / 3dcnn discriminators (:352-498) are non-default branches and
-are not ported (Conv3D is off the hot path).
+/root/reference/ssgan_inference_moving_mnist.py.  MODE 'ali' / 'alice-z' (:351-498, :541-547) replace the LEN+1 local
+discriminators by ONE critic on (clip, all latents), in the three ALI_MODE variants of the reference: 'concat_x' (frames as
+channels, Cin = LEN), 'concat_z' (per-frame trunk + 4x4 VALID conv, codes concatenated) and '3dcnn' (four Conv3D layers,
+tflib/ops/conv3d.py; clips of LEN 4 or 16 as in the reference).
 """
 import os
 import sys
@@ -30,14 +32,18 @@ import tflib.utils.distance
 import tflib.plot
 
 
-def build_graph(MODE='local_ep', BATCH_SIZE=50, LEN=16, DIM=32, DIM_OP=256, LR=1e-4, BN_FLAG=False):
-    if MODE not in ('local_ep', 'local_epce-z'):
-        raise NotImplementedError("MODE %r: only the graphical (local) modes are on the hot path" % MODE)
+def build_graph(MODE='local_ep', BATCH_SIZE=50, LEN=16, DIM=32, DIM_OP=256, LR=1e-4, BN_FLAG=False, ALI_MODE='concat_x'):
+    if MODE not in ('local_ep', 'local_epce-z', 'ali', 'alice-z'):
+        raise NotImplementedError("unknown MODE %r" % (MODE,))                              # :497-498 raise('NotImplementedError')
+    if MODE in ('ali', 'alice-z') and ALI_MODE not in ('concat_x', 'concat_z', '3dcnn'):
+        raise NotImplementedError("unknown ALI_MODE %r" % (ALI_MODE,))                      # :494-495
+    if MODE in ('ali', 'alice-z') and ALI_MODE == '3dcnn' and LEN not in (4, 16):
+        raise NotImplementedError("the 3dcnn critic is defined for LEN 4 and 16 only (:367-370, :382-385)")
     DIM_LATENT_G, DIM_LATENT_L, N_C = 128, 8, 10
     DIM_LATENT_T = DIM_LATENT_L
     OUTPUT_SHAPE = [1, 64, 64]
     OUTPUT_DIM = int(np.prod(OUTPUT_SHAPE))
-    LAMBDA, BETA1 = 0.1, .5
+    LAMBDA, BETA1, BETA2 = 0.1, .5, .999
     BN_FLAG_G = BN_FLAG_E = BN_FLAG_D = BN_FLAG
     ratio = [1.0, ] * (LEN - 1) + [1, LEN]
     ratio = np.asarray(ratio) * 1.0 / (len(ratio) + LEN - 1)                                 # :78-79
@@ -133,6 +139,56 @@ def build_graph(MODE='local_ep', BATCH_SIZE=50, LEN=16, DIM=32, DIM_OP=256, LR=1
         output = lib.ops.linear.Linear('Discriminator.Output', 512, 1, output)
         return tf.reshape(output, [BATCH_SIZE * LEN, ])
 
+    def _ali_inputs(x, z_g, z_l, labels):
+        z_l = tf.reshape(z_l, [BATCH_SIZE, LEN * DIM_LATENT_L])
+        z_g = tf.reshape(z_g, [BATCH_SIZE, DIM_LATENT_G])
+        labels = tf.reshape(labels, [BATCH_SIZE, N_C])
+        return tf.concat([z_g, z_l, labels], axis=-1), labels
+
+    def _ali_head(output, z, n_feat, extra=()):
+        z_output = LeakyReLU(lib.ops.linear.Linear('Discriminator.z1', DIM_LATENT_G + DIM_LATENT_L * LEN + N_C, 512, z))
+        output = tf.concat([output, z_output] + list(extra), 1)
+        n_in = n_feat + 512 + sum(int(e.shape[1]) for e in extra)
+        output = LeakyReLU(lib.ops.linear.Linear('Discriminator.zx1', n_in, 512, output))
+        output = lib.ops.linear.Linear('Discriminator.Output', 512, 1, output)
+        return tf.reshape(output, [BATCH_SIZE, ])
+
+    def Discriminator3D(x, z_g, z_l, labels):                                                # :354-404 ALI_MODE '3dcnn'
+        import tflib.ops.conv3d
+        output = tf.reshape(x, [-1, LEN] + OUTPUT_SHAPE)
+        output = tf.transpose(output, [0, 1, 3, 4, 2])                                       # NLHWC
+        z, _ = _ali_inputs(x, z_g, z_l, labels)
+        output = LeakyReLU(lib.ops.conv3d.Conv3D('Discriminator.1', 4, 1, DIM, 4, output, stride=2, stride_len=2))
+        output = lib.ops.conv3d.Conv3D('Discriminator.2', 4, DIM, 2 * DIM, 4, output, stride=2, stride_len=1 if LEN == 4 else 2)
+        if BN_FLAG_D:
+            output = lib.ops.batchnorm.Batchnorm('Discriminator.BN2', [0, 1, 2, 3], output)
+        output = LeakyReLU(output)
+        output = lib.ops.conv3d.Conv3D('Discriminator.3', 4, 2 * DIM, 4 * DIM, 4, output, stride=2, stride_len=2)
+        if BN_FLAG_D:
+            output = lib.ops.batchnorm.Batchnorm('Discriminator.BN3', [0, 1, 2, 3], output)
+        output = LeakyReLU(output)
+        output = lib.ops.conv3d.Conv3D('Discriminator.4', 4, 4 * DIM, 8 * DIM, 4, output, stride=2, stride_len=1 if LEN == 4 else 2)
+        if BN_FLAG_D:
+            output = lib.ops.batchnorm.Batchnorm('Discriminator.BN4', [0, 1, 2, 3], output)
+        output = LeakyReLU(output)
+        output = tf.reshape(output, [BATCH_SIZE, 4 * 4 * 8 * DIM])
+        return _ali_head(output, z, 4 * 4 * 8 * DIM)
+
+    def DiscriminatorConcatX(x, z_g, z_l, labels):                                           # :407-446 frames as channels
+        output = tf.reshape(x, [BATCH_SIZE, LEN, 64, 64])
+        z, _ = _ali_inputs(x, z_g, z_l, labels)
+        output = _conv_trunk('Discriminator.', output, LEN, BN_FLAG_D)
+        output = tf.reshape(output, [BATCH_SIZE, 4 * 4 * 8 * DIM])
+        return _ali_head(output, z, 4 * 4 * 8 * DIM)
+
+    def DiscriminatorConcatZ(x, z_g, z_l, labels):                                           # :448-492 per-frame codes
+        output = tf.reshape(x, [BATCH_SIZE * LEN, -1, 64, 64])
+        z, labels = _ali_inputs(x, z_g, z_l, labels)
+        output = _conv_trunk('Discriminator.', output, 1, BN_FLAG_D)
+        output = lib.ops.conv2d.Conv2D('Discriminator.5', 8 * DIM, DIM_LATENT_G, 4, output, stride=1, padding='VALID')
+        output = tf.reshape(output, [BATCH_SIZE, LEN * DIM_LATENT_G])
+        return _ali_head(output, z, LEN * DIM_LATENT_G, extra=(labels,))
+
     def _mlp_disc(prefix, x, n_in):
         output = LeakyReLU(lib.ops.linear.Linear(prefix + '.Input', n_in, 512, x))
         output = LeakyReLU(lib.ops.linear.Linear(prefix + '.2', 512, 512, output))
@@ -164,23 +220,34 @@ def build_graph(MODE='local_ep', BATCH_SIZE=50, LEN=16, DIM=32, DIM_OP=256, LR=1
     p_y = tf.one_hot(indices=p_y_idx, depth=N_C)
     fake_x = Generator(p_z_g, p_z_l, p_y)
 
-    disc_fake, disc_real = [], []
-    for i in range(LEN - 1):
-        disc_fake.append(DynamicDiscrminator(p_z_l[:, i, :], p_z_l[:, i + 1, :]))
-        disc_real.append(DynamicDiscrminator(q_z_l[:, i, :], q_z_l[:, i + 1, :]))
-    disc_fake.append(ZGDiscrminator(p_z_g))
-    disc_real.append(ZGDiscrminator(q_z_g))
-    disc_fake.append(Discriminator(fake_x, p_z_g, p_z_l, p_y))
-    disc_real.append(Discriminator(real_x, q_z_g, q_z_l, real_y))
-
-    gen_params = lib.params_with_name('Generator')
-    ext_params = lib.params_with_name('Extractor')
-    disc_params = lib.params_with_name('Discriminator')
+    gen_params_of = lambda: (lib.params_with_name('Generator'), lib.params_with_name('Extractor'), lib.params_with_name('Discriminator'))
     rec_penalty = None
-    if MODE == 'local_epce-z':
-        rec_penalty = LAMBDA * lib.utils.distance.distance(real_x, rec_x, 'l2')
-    gen_cost, disc_cost, _, _, gen_train_op, disc_train_op = lib.objs.gan_inference.weighted_local_epce(
-        disc_fake, disc_real, ratio, gen_params + ext_params, disc_params, lr=LR, beta1=BETA1, rec_penalty=rec_penalty)
+    if MODE in ('local_ep', 'local_epce-z'):
+        disc_fake, disc_real = [], []
+        for i in range(LEN - 1):
+            disc_fake.append(DynamicDiscrminator(p_z_l[:, i, :], p_z_l[:, i + 1, :]))
+            disc_real.append(DynamicDiscrminator(q_z_l[:, i, :], q_z_l[:, i + 1, :]))
+        disc_fake.append(ZGDiscrminator(p_z_g))
+        disc_real.append(ZGDiscrminator(q_z_g))
+        disc_fake.append(Discriminator(fake_x, p_z_g, p_z_l, p_y))
+        disc_real.append(Discriminator(real_x, q_z_g, q_z_l, real_y))
+        gen_params, ext_params, disc_params = gen_params_of()
+        if MODE == 'local_epce-z':
+            rec_penalty = LAMBDA * lib.utils.distance.distance(real_x, rec_x, 'l2')
+        gen_cost, disc_cost, _, _, gen_train_op, disc_train_op = lib.objs.gan_inference.weighted_local_epce(
+            disc_fake, disc_real, ratio, gen_params + ext_params, disc_params, lr=LR, beta1=BETA1, rec_penalty=rec_penalty)
+    else:                                                                                    # :537-547 one critic on everything
+        critic = {'3dcnn': Discriminator3D, 'concat_x': DiscriminatorConcatX, 'concat_z': DiscriminatorConcatZ}[ALI_MODE]
+        disc_real = critic(real_x, q_z_g, q_z_l, real_y)
+        disc_fake = critic(fake_x, p_z_g, p_z_l, p_y)
+        gen_params, ext_params, disc_params = gen_params_of()
+        if MODE == 'ali':
+            gen_cost, disc_cost, gen_train_op, disc_train_op = lib.objs.gan_inference.ali(
+                disc_fake, disc_real, gen_params + ext_params, disc_params, lr=LR, beta1=BETA1, beta2=BETA2)
+        else:
+            rec_penalty = LAMBDA * lib.utils.distance.distance(real_x, rec_x, 'l2')
+            gen_cost, disc_cost, gen_train_op, disc_train_op = lib.objs.gan_inference.alice(
+                disc_fake, disc_real, rec_penalty, gen_params + ext_params, disc_params, lr=LR, beta1=BETA1)
     ns.__dict__.update(real_x_unit=real_x_unit, real_y=real_y, real_x=real_x, q_z_l=q_z_l, q_z_g=q_z_g, p_z_l_0=p_z_l_0, p_z_l=p_z_l,
                        p_z_g=p_z_g, p_y_idx=p_y_idx, fake_x=fake_x, rec_x=rec_x, disc_fake=disc_fake, disc_real=disc_real, gen_params=gen_params,
                        ext_params=ext_params, disc_params=disc_params, gen_cost=gen_cost, disc_cost=disc_cost,

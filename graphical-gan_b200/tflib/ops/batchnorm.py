@@ -42,5 +42,11 @@ def Batchnorm(name, axes, inputs, is_training=None, stats_iter=None, update_movi
         if nd == 2 and list(axes) == [0]:
             # moments over the batch + batch_normalization(eps=1e-5): the fused [rows, C] kernel
             return _O.batchnorm(inputs, scale, offset, 1e-5)
+        if nd > 2 and list(axes) == list(range(nd - 1)):
+            # channels-last statistics over every other axis (Batchnorm(..., [0,1,2,3], ndhwc) in the SSGAN 3dcnn critic,
+            # ssgan_inference_moving_mnist.py:372): the same kernel on the [rows, C] view
+            C = int(inputs.get_shape()[-1])
+            flat = _O.batchnorm(tf.reshape(inputs, [-1, C]), tf.reshape(scale, [C]), tf.reshape(offset, [C]), 1e-5)
+            return tf.reshape(flat, [int(d) for d in inputs.get_shape()])
         mean, var = tf.nn.moments(inputs, axes, keep_dims=True)
         return tf.nn.batch_normalization(inputs, mean, var, offset, scale, 1e-5)

@@ -4,6 +4,7 @@ No kernels run here; what is pinned is that the launch list the plan compiler em
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
 from graph_interp import Interp
 
@@ -245,3 +246,78 @@ def test_objs_mmd_matches_numpy_and_autograd():
     assert abs(float(it.run(biased)) - float(ref_b.detach())) < 1e-10
     assert abs(float(it.run(unbiased)) - float(ref_u.detach())) < 1e-10
     assert np.abs(it.run(gx) - rg.numpy()).max() < 1e-10
+
+
+def _tf_same_pad(n, k, s):
+    out = -(-n // s)
+    total = max((out - 1) * s + k - n, 0)
+    return total // 2, total - total // 2
+
+
+@pytest.mark.parametrize("geom", [(2, 4, 8, 8, 3, 5, 4, 4, 2, 2), (2, 4, 8, 8, 4, 6, 4, 4, 2, 1), (1, 16, 8, 8, 2, 4, 4, 4, 2, 2),
+                                  (2, 5, 6, 7, 3, 4, 3, 3, 1, 2), (1, 3, 5, 5, 2, 3, 2, 3, 2, 3)])
+def test_conv3d_matches_torch_conv3d_with_tf_same_padding(geom):
+    """tflib.ops.conv3d.Conv3D (tflib/ops/conv3d.py:6-51; NDHWC, filter (fl,k,k,Ci,Co), strides [1,sl,s,s,1], SAME) through the
+    graph IR — depth taps folded into channels + one 2-D convolution — against torch.nn.functional.conv3d with TensorFlow's
+    asymmetric SAME padding: the output and the gradients w.r.t. input, filter and bias."""
+    import tensorflow as tf
+    import tflib as lib
+    import tflib.ops.conv3d
+    from gg import ops as O
+    N, L, H, W, Ci, Co, fl, k, s, sl = geom
+    tf.reset_default_graph()
+    lib.delete_all_params()
+    np.random.seed(5)
+    x = tf.placeholder(tf.float32, shape=[N, L, H, W, Ci])
+    y = lib.ops.conv3d.Conv3D('C3', fl, Ci, Co, k, x, stride=s, stride_len=sl)
+    w, b = lib.params_with_name('C3.Filters')[0], lib.params_with_name('C3.Biases')[0]
+    assert tuple(w.shape) == (fl, k, k, Ci, Co) and tuple(b.shape) == (1, 1, 1, 1, Co)
+    rs = np.random.RandomState(2)
+    xv, wv, bv = rs.randn(N, L, H, W, Ci), rs.randn(fl, k, k, Ci, Co), rs.randn(1, 1, 1, 1, Co)
+    gy = rs.randn(*y.shape)
+    loss = tf.reduce_sum(y * tf.constant(gy.astype(np.float32)))
+    gx, gw, gb = O.gradients(loss, [x, w, b])
+    it = Interp({x: xv}, params={w.id: wv, b.id: bv})
+    tx, tw, tb = (torch.tensor(v, requires_grad=True) for v in (xv, wv, bv))
+    pd, ph, pw = _tf_same_pad(L, fl, sl), _tf_same_pad(H, k, s), _tf_same_pad(W, k, s)
+    xin = F.pad(tx.permute(0, 4, 1, 2, 3), (pw[0], pw[1], ph[0], ph[1], pd[0], pd[1]))
+    ref = F.conv3d(xin, tw.permute(4, 3, 0, 1, 2), stride=(sl, s, s)).permute(0, 2, 3, 4, 1) + tb
+    assert tuple(ref.shape) == tuple(y.shape)
+    rx, rw, rb = torch.autograd.grad((ref * torch.tensor(gy.astype(np.float32).astype(np.float64))).sum(), [tx, tw, tb])
+    for got, want, name in ((y, ref.detach(), "y"), (gx, rx, "dx"), (gw, rw, "dw"), (gb, rb, "db")):
+        g, r = it.run(got), want.numpy()
+        assert np.abs(g - r.reshape(g.shape)).max() <= 1e-10 * (np.abs(r).max() + 1e-30) + 1e-12, (name, geom)
+
+
+def test_ssgan_3dcnn_critic_trunk_builds_and_reduces_to_4x4():
+    """the four Conv3D layers + Batchnorm([0,1,2,3]) of the reference's 3dcnn critic (ssgan_inference_moving_mnist.py:356-389),
+    LEN = 4 and LEN = 16: the clip collapses to one 4x4x(8 DIM) map, and the batch norm over every axis but the channel one is
+    the fused [rows, C] kernel's graph op"""
+    import tensorflow as tf
+    import tflib as lib
+    import tflib.ops.conv3d
+    import tflib.ops.batchnorm
+    DIM, B = 4, 2
+    for LEN in (4, 16):
+        tf.reset_default_graph()
+        lib.delete_all_params()
+        np.random.seed(1)
+        x = tf.placeholder(tf.float32, shape=[B, LEN, 4096])
+        out = tf.transpose(tf.reshape(x, [-1, LEN, 1, 64, 64]), [0, 1, 3, 4, 2])                   # NLHWC (:355-356)
+        out = lib.ops.conv3d.Conv3D('D.1', 4, 1, DIM, 4, out, stride=2, stride_len=2)
+        out = lib.ops.conv3d.Conv3D('D.2', 4, DIM, 2 * DIM, 4, out, stride=2, stride_len=1 if LEN == 4 else 2)
+        out = lib.ops.batchnorm.Batchnorm('D.BN2', [0, 1, 2, 3], out)
+        out = lib.ops.conv3d.Conv3D('D.3', 4, 2 * DIM, 4 * DIM, 4, out, stride=2, stride_len=2)
+        out = lib.ops.conv3d.Conv3D('D.4', 4, 4 * DIM, 8 * DIM, 4, out, stride=2, stride_len=1 if LEN == 4 else 2)
+        assert tuple(out.shape) == (B, 1, 4, 4, 8 * DIM)
+        flat = tf.reshape(out, [B, 4 * 4 * 8 * DIM])
+        rs = np.random.RandomState(0)
+        val = Interp({x: rs.rand(B, LEN, 4096)}).run(flat)
+        assert val.shape == (B, 4 * 4 * 8 * DIM) and np.isfinite(val).all() and np.abs(val).max() > 0
+        bn = [n for n in O_toposort([flat]) if n.op == "bn"]
+        assert len(bn) == 1 and len(bn[0].shape) == 2 and bn[0].shape[1] == 2 * DIM
+
+
+def O_toposort(roots):
+    from gg.ops import toposort
+    return toposort(roots)

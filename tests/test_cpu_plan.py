@@ -237,7 +237,17 @@ ALL_SCRIPTS = {
     "gan_inference_cifar10:alice": dict(BATCH_SIZE=4, MODE='alice'),
     "gan_inference_svhn:wali": dict(BATCH_SIZE=4, MODE='wali'),
     "gan_inference_face": dict(BATCH_SIZE=2),
+    # the discriminator-free VEGAN variants: generator objective only, CRITIC_ITERS = 0
+    "gan_inference_mnist:vegan-kl": dict(BATCH_SIZE=4, MODE='vegan-kl', Z_SAMPLES=8),
+    "gan_inference_mnist:vegan-jsd": dict(BATCH_SIZE=4, MODE='vegan-jsd', Z_SAMPLES=8),
+    "gan_inference_svhn:vegan-ikl": dict(BATCH_SIZE=4, MODE='vegan-ikl', Z_SAMPLES=8),
+    "gan_inference_cifar10:vegan-mmd": dict(BATCH_SIZE=4, MODE='vegan-mmd'),
     "ssgan_inference_moving_mnist": dict(BATCH_SIZE=2, LEN=4),
+    # the SSGAN scripts' ALI mode: one critic on (clip, all latents) — Conv3D trunk / frames as channels / per-frame codes
+    "ssgan_inference_moving_mnist:ali-3dcnn": dict(BATCH_SIZE=2, LEN=4, MODE='ali', ALI_MODE='3dcnn'),
+    "ssgan_inference_moving_mnist:ali-3dcnn-bn": dict(BATCH_SIZE=2, LEN=4, MODE='ali', ALI_MODE='3dcnn', BN_FLAG=True),
+    "ssgan_inference_moving_mnist:alice-z-concat_z": dict(BATCH_SIZE=2, LEN=4, MODE='alice-z', ALI_MODE='concat_z'),
+    "ssgan_inference_moving_mnist:ali-concat_x": dict(BATCH_SIZE=2, LEN=4, MODE='ali', ALI_MODE='concat_x'),
     "ssgan_inference_chairs": dict(BATCH_SIZE=2, LEN=4),
     "ssgan_inference_chairs:local_epce-z": dict(BATCH_SIZE=2, LEN=3, MODE='local_epce-z'),
 }
@@ -258,6 +268,9 @@ def test_every_script_compiles_to_a_launch_list(cpu_device, script):
     np.random.seed(2)
     g = mod.build_graph(**ALL_SCRIPTS[script])
     for cost, op in ((g.gen_cost, g.gen_train_op), (g.disc_cost, g.disc_train_op)):
+        if op is None:                      # no-discriminator modes have only the generator step
+            assert g.CRITIC_ITERS == 0 and cost is None
+            continue
         roots = [cost] + [d for d in op.deps if d is not None]
         fed = [n for n in toposort(roots) if n.op == "placeholder"]
         plan = Plan(RT, [cost, op], fed)

@@ -200,6 +200,14 @@ FAMILIES = {
     "ssgan_inference_chairs": ("ssgan_inference_chairs", dict(BATCH_SIZE=4, LEN=4)),
     "gmgan_inference_face": ("gmgan_inference_face", dict(BATCH_SIZE=16)),
     "gan_inference_mnist_wali_gp_bn_double_backward": ("gan_inference_mnist", dict(MODE='wali-gp', BATCH_SIZE=20)),
+    # the discriminator-free VEGAN objectives (objs.kl_aggregated / objs.mmd behind MODE 'vegan-kl|ikl|jsd|mmd'): one step only
+    "gan_inference_mnist_vegan_kl": ("gan_inference_mnist", dict(MODE='vegan-kl', BATCH_SIZE=50)),
+    "gan_inference_mnist_vegan_jsd": ("gan_inference_mnist", dict(MODE='vegan-jsd', BATCH_SIZE=50)),
+    "gan_inference_svhn_vegan_ikl": ("gan_inference_svhn", dict(MODE='vegan-ikl', BATCH_SIZE=32)),
+    "gan_inference_cifar10_vegan_mmd": ("gan_inference_cifar10", dict(MODE='vegan-mmd', BATCH_SIZE=32)),
+    # the SSGAN ALI critics: tflib.ops.conv3d.Conv3D (depth taps folded into one 2-D convolution) and the concat_z variant
+    "ssgan_moving_mnist_ali_3dcnn": ("ssgan_inference_moving_mnist", dict(MODE='ali', ALI_MODE='3dcnn', BATCH_SIZE=4, LEN=4)),
+    "ssgan_moving_mnist_alice_z_concat_z": ("ssgan_inference_moving_mnist", dict(MODE='alice-z', ALI_MODE='concat_z', BATCH_SIZE=4, LEN=4)),
 }
 
 
@@ -216,26 +224,30 @@ def test_script_port_step_matches_fp64_interpreter(family):
     g = importlib.import_module(script).build_graph(**kw)
     grads = {}
     for tag, op in (("gen", g.gen_train_op), ("disc", g.disc_train_op)):
+        if op is None:
+            continue
         for v, d in zip(op.attrs["vars"], op.deps):
             if d is not None:
                 grads[(tag, v.name)] = d
-    roots = [g.gen_cost, g.disc_cost] + list(grads.values())
+    cost_nodes = [c for c in (g.gen_cost, g.disc_cost) if c is not None]
+    roots = cost_nodes + list(grads.values())
     feeds = _interp_feeds(toposort(roots), np.random.RandomState(99))
     it = Interp({k: np.asarray(v, np.float64) if v.dtype != np.int32 else v for k, v in feeds.items()})
     cabi.call("gg_set_conv_backend", 1)
     try:
         sess = tf.Session()
         keys = list(grads)
-        out = sess.run([g.gen_cost, g.disc_cost] + [grads[k] for k in keys], feed_dict=feeds)
+        out = sess.run(cost_nodes + [grads[k] for k in keys], feed_dict=feeds)
     finally:
         cabi.call("gg_set_conv_backend", 0)
-    for got, node in zip(out[:2], (g.gen_cost, g.disc_cost)):
+    nc = len(cost_nodes)
+    for got, node in zip(out[:nc], cost_nodes):
         ref = float(np.sum(it.run(node)))
         assert abs(float(np.sum(got)) - ref) <= 2e-3 * max(abs(ref), 1e-2), (family, float(np.sum(got)), ref)
     refs = {k: it.run(grads[k]) for k in keys}
     gmax = max(np.abs(r).max() for r in refs.values())
     worst = (0.0, None)
-    for k, got in zip(keys, out[2:]):
+    for k, got in zip(keys, out[nc:]):
         ref = refs[k].reshape(got.shape)
         if np.abs(ref).max() < 1e-7 * gmax:
             assert np.abs(got).max() < 1e-4 * gmax, k
