@@ -135,9 +135,11 @@ __global__ void __launch_bounds__(256) conv_small_fwd_kernel(const float* __rest
   }
 }
 
-// (A 4 pixel x 8 channel register-tile variant with the 5x5 tap loop unrolled was measured on the B200 and removed: 18.8 us
-// against 16.2 us for the kernel above at B=128 3->64, profiles/time_conv_r2.txt — the kernel is bound by its shared-memory
-// fills and the 8.4 MB output store, not by FMA issue density.)
+// Two variants were measured on the B200 and removed (B=128 3->64, 16.2 us for the kernel above; profiles/time_conv_r2.txt):
+// a 4 pixel x 8 channel register tile with the 5x5 tap loop unrolled (18.8 us), and a persistent form that keeps the filter slab
+// resident and double-buffers the input patch with cp.async (16.0 us: the per-tile fills were not the limit).  The inner loop
+// issues 1 LDS.128 + 4 LDS.32 per 16 FMAs — 8 shared-memory wavefronts per 16 FMA instructions: the kernel runs at the
+// shared-memory pipe's rate (2.45 M wavefronts / 148 SMs = 8.4 us) plus launch, fill and store tails.
 
 // ---------------------------------------------------------------------------------------------------------------------
 // dgrad (and Deconv2D forward) towards CI <= 4 channels

@@ -171,7 +171,7 @@ def test_local_ep_dynamic_matches_oracle():
     for cost, plist, ref in ((gen_cost, gen_params, rg), (disc_cost, disc_params, rd)):
         grads = tf.gradients(cost, plist)
         out = sess.run([cost] + grads, feed_dict=feeds)
-        assert abs(float(out[0]) - float(ref)) <= 1e-3 * abs(float(ref))
+        assert abs(float(out[0]) - float(ref.detach())) <= 1e-3 * abs(float(ref.detach()))
         refs = torch.autograd.grad(ref, [P[p.name] for p in plist], retain_graph=True)
         for p, got, r in zip(plist, out[1:], refs):
             r = r.numpy()

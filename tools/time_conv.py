@@ -102,6 +102,7 @@ if __name__ == "__main__":
     if which in ("all", "batched"):
         # the shapes the step actually launches after sibling batching (fake + real towers: 128 rows)
         conv_case(128, 32, 32, 3, 64)
+        conv_case(64, 32, 32, 3, 64)
         conv_case(128, 16, 16, 64, 128)
         conv_case(128, 8, 8, 128, 256)
     if which in ("all", "3x3"):
@@ -111,7 +112,6 @@ if __name__ == "__main__":
         conv_case(64, 16, 16, 64, 128, k=3, s=2)
         conv_case(64, 8, 8, 128, 256, k=3, s=1)
     if which == "all":
-        conv_case(64, 32, 32, 3, 64)
         conv_case(128, 32, 32, 32, 64)
         gemm_case(64, 512, 4608); gemm_case(64, 4608, 512, 0, 1); gemm_case(4608, 512, 64, 1, 0)
         gemm_case(64, 4096, 128); gemm_case(64, 512, 512); gemm_case(64, 1, 512); gemm_case(64, 512, 158)
