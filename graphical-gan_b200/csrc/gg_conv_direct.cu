@@ -20,6 +20,7 @@ size_t conv_tc_wgrad_workspace(int B, int H, int W, int Ci, int Co, int k, int s
 size_t conv_tc_workspace(int mode, int B, int H, int W, int Ci, int Co, int k, int stride, int Ho, int Wo);
 void conv_tc_set_debug(void* p);
 void conv_tc_set_max_ctas(int n);
+void conv_tc_set_pending_mask(const float* y, int act, float alpha);
 // gg_conv_small.cu: one-launch shared-memory kernels for the 1-/3-channel first conv and last deconv of every network
 int conv_small_fwd(const float* x, const float* w, const float* bias, float* y, int B, int H, int W, int Ci, int Co, int k,
                    int stride, int pad_t, int pad_l, int Ho, int Wo, int act, float alpha, cudaStream_t st, bool* handled);
@@ -427,6 +428,32 @@ extern "C" int gg_conv2d_dgrad(const float* dy, const float* w, const float* bia
     GG_LAUNCH((conv_dgrad_kernel<1>), ceil_div(total, 128), 128, 0, st, dy, w, bias, dx, p, act, alpha);
   }
   return check_launch("gg_conv2d_dgrad(direct)");
+}
+
+// dgrad followed by the gradient of the activation that produced the dgrad's target: dx = act'(y) * (dy (*) w^T), one launch.
+// Tensor-core path only (the write-out of gg_conv_tc.cu applies the mask); gg_conv2d_tc_supported tells the caller in advance.
+extern "C" int gg_conv2d_tc_supported(int mode, int B, int H, int W, int Ci, int Co, int k, int stride, int Ho, int Wo) {
+  if (g_conv_backend == 1) return 0;
+  return conv_tc_workspace(mode, B, H, W, Ci, Co, k, stride, Ho, Wo) != 0 ? 1 : 0;
+}
+
+extern "C" int gg_conv2d_dgrad_actgrad(const float* dy, const float* w, float* dx, const float* y_fwd, int act, float alpha, int B,
+                                       int H, int W, int Ci, int Co, int k, int stride, int pad_t, int pad_l, int Ho, int Wo,
+                                       void* workspace, size_t workspace_bytes, void* stream) {
+  ConvP p{B, H, W, Ci, Co, k, stride, pad_t, pad_l, Ho, Wo};
+  int rc = check_geom(p, "gg_conv2d_dgrad_actgrad");
+  if (rc) return rc;
+  if (y_fwd == nullptr) return fail(GG_ERR_BAD_ARG, "gg_conv2d_dgrad_actgrad: y_fwd is required%s");
+  if (g_conv_backend == 1) return fail(GG_ERR_UNSUPPORTED, "gg_conv2d_dgrad_actgrad: tensor-core path disabled (backend 1)%s");
+  bool handled = false;
+  conv_tc_set_pending_mask(y_fwd, act, alpha);
+  rc = conv_tc_dgrad(dy, w, nullptr, dx, B, H, W, Ci, Co, k, stride, pad_t, pad_l, Ho, Wo, GG_ACT_NONE, 0.f, workspace,
+                     workspace_bytes, as_stream(stream), &handled);
+  conv_tc_set_pending_mask(nullptr, 0, 0.f);
+  if (rc) return rc;
+  if (!handled) return fail(GG_ERR_UNSUPPORTED, "gg_conv2d_dgrad_actgrad: shape not supported by the tcgen05 path%s");
+  g_last_backend = 1;
+  return GG_OK;
 }
 
 extern "C" size_t gg_conv2d_wgrad_workspace(int B, int H, int W, int Ci, int Co, int k, int stride, int Ho, int Wo) {

@@ -65,6 +65,9 @@ struct TcParams {
   float alpha;
   float* out;
   const float* bias;
+  const float* mask;          // optional: forward activation y at the OUTPUT positions (same layout as out); the stored value
+  int mask_act;               // becomes act'(y) * value — the activation gradient that follows a dgrad, fused into its write-out
+  float mask_alpha;
   long long* dbg;             // optional timeline of CTA (0,0): see gg_debug_set_buffer
   int out_rows;               // wgrad: rows of the [taps*Ci, Co] result that exist in memory (im2col-padded K)
 };
@@ -564,6 +567,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               off[u] = rr < 128 ? s_row_off[rr] : -1;
               val[u] = lds128(sp_ + (uint32_t)((rr < 128 ? rr : 0) * ld) * 4u);
             }
+            if (p.mask != nullptr) {
+              // fused activation gradient (gmgan_inference_cifar10.py:122-123 LeakyReLU / :179 ReLU, backward): dx *= act'(y)
+              const float* mp_ = p.mask + (size_t)(cbeg + my_c) * 4;
+              float4 mk[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                mk[u] = off[u] >= 0 ? *reinterpret_cast<const float4*>(mp_ + off[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                val[u].x = act_grad_from_out(mk[u].x, val[u].x, p.mask_act, p.mask_alpha);
+                val[u].y = act_grad_from_out(mk[u].y, val[u].y, p.mask_act, p.mask_alpha);
+                val[u].z = act_grad_from_out(mk[u].z, val[u].z, p.mask_act, p.mask_alpha);
+                val[u].w = act_grad_from_out(mk[u].w, val[u].w, p.mask_act, p.mask_alpha);
+              }
+            }
 #pragma unroll
             for (int u = 0; u < 4; ++u)
               if (off[u] >= 0) *reinterpret_cast<float4*>(gp_ + off[u]) = val[u];
@@ -870,12 +888,22 @@ int conv_tc_fwd(const float* x, const float* w, const float* bias, float* y, int
   return GG_OK;
 }
 
+namespace {
+struct PendingMask { const float* y; int act; float alpha; };
+thread_local PendingMask g_pending_mask = {nullptr, 0, 0.f};
+}  // namespace
+// the next conv_tc_dgrad of this thread multiplies its result by act'(y) while storing it (gg_conv2d_dgrad_actgrad)
+void conv_tc_set_pending_mask(const float* y, int act, float alpha) { g_pending_mask = PendingMask{y, act, alpha}; }
+
 int conv_tc_dgrad(const float* dy, const float* w, const float* bias, float* dx, int B, int H, int W, int Ci, int Co, int k,
                   int stride, int pad_t, int pad_l, int Ho, int Wo, int act, float alpha, void* ws, size_t ws_bytes,
                   cudaStream_t st, bool* handled, int filt_rows) {
   *handled = false;
+  const PendingMask mask = g_pending_mask;
+  g_pending_mask = PendingMask{nullptr, 0, 0.f};
   TcPlan pl = make_plan(1, B, H, W, Ci, Co, k, stride, pad_t, pad_l, Ho, Wo);
   if (!pl.ok) return GG_OK;
+  pl.p.mask = mask.y; pl.p.mask_act = mask.act; pl.p.mask_alpha = mask.alpha;
   CUtensorMap tmA, tmB;
   int rc = act_map(&tmA, dy, B, Ho, Wo, Co, pl.p.wt, pl.p.ht, pl.p.bt, 1, 1);
   if (rc) return rc;

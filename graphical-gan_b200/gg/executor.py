@@ -280,6 +280,7 @@ class Plan(object):
                                     part=(0, 1), ordered=False))
         self._plan_inplace_concats()
         self._plan_grad_buckets(fetches)
+        self._plan_actgrad_fusion(fetches)
         for node in self.order:
             s0 = len(self.steps)
             self._emit(node)
@@ -310,6 +311,8 @@ class Plan(object):
         reads = set()
         for i in node.inputs:
             reads |= self._owners(i)
+        if node.id in getattr(self, "fuse_mask", {}):
+            reads |= self._owners(self.fuse_mask[node.id][0])
         if node.op == "random":
             reads.add("tick")
         self._add_groups(s0, len(self.steps), reads, node.id, barrier=False, node=node)
@@ -496,7 +499,8 @@ class Plan(object):
             # cut into buckets of roughly equal bytes in readiness order; the gradients that become ready LAST (split update,
             # _late_vars) form a small bucket of their own, so that the exchange exposed after the last backward kernel is a
             # few KB instead of a quarter of the model
-            late = self._late_vars([(e["var"], e["own"]) for e in entries])
+            # GG_DP_LATE_BUCKET=1: the small last bucket without the split update
+            late = self._late_vars([(e["var"], e["own"]) for e in entries], force=os.environ.get("GG_DP_LATE_BUCKET", "0") == "1")
             main = [e for e in entries if e["var"].id not in late]
             tail = [e for e in entries if e["var"].id in late]
             buckets, cur, acc, per = [], [], 0, total / float(n_buckets)
@@ -512,13 +516,52 @@ class Plan(object):
                 buckets.append(tail)
             self.bucket_plan[op.attrs["opt_id"]] = (entries, buckets, total)
 
-    def _late_vars(self, pairs):
+    def _plan_actgrad_fusion(self, fetches):
+        """dgrad -> activation-gradient pairs that run as ONE launch: `leaky_grad(y, conv_dgrad(dy, w))` (autodiff of
+        LeakyReLU(Conv2D(.)) / ReLU(Deconv2D(.)) stacks) becomes gg_conv2d_dgrad_actgrad, whose write-out multiplies by act'(y).
+        Four such pairs sit on the critical chain of each training step (3-5.5 us + a dependent launch each).  Conditions: the
+        dgrad runs on the tensor-core kernels, has no bias / activation of its own, is consumed only by the gradient node,
+        neither output is placed inside another buffer, and y is computed before the dgrad in the plan's order."""
+        self.fuse_mask, self.fused_alias = {}, {}
+        if os.environ.get("GG_FUSE_ACTGRAD", "1") == "0":
+            return
+        pos = {n.id: i for i, n in enumerate(self.order)}
+        uses = {}
+        for n in self.order:
+            if n.id in self.fed:
+                continue
+            for i in n.inputs:
+                uses[i.id] = uses.get(i.id, 0) + 1
+        for f in fetches:
+            if isinstance(f, Tensor):
+                uses[f.id] = uses.get(f.id, 0) + 1
+            else:
+                for d in self._op_roots(f):
+                    uses[d.id] = uses.get(d.id, 0) + 1
+        placed = set(getattr(self, "placed", {})) | set(getattr(self, "placed_flat", {}))
+        for n in self.order:
+            if n.op != "binary" or n.attrs.get("fn") not in ("leaky_grad", "relu_grad") or n.id in self.fed:
+                continue
+            y, g = n.inputs
+            if g.op != "conv" or g.attrs["mode"] != "dgrad" or g.attrs["act"] is not None or len(g.inputs) != 2:
+                continue
+            if g.id in self.fed or y.id not in pos or uses.get(g.id, 0) != 1 or g.id in placed or n.id in placed:
+                continue
+            if tuple(y.shape) != tuple(g.shape) or tuple(n.shape) != tuple(g.shape) or pos[y.id] > pos[g.id]:
+                continue
+            a = g.attrs
+            if cabi.lib.gg_conv2d_tc_supported(1, a["B"], a["H"], a["W"], a["Ci"], a["Co"], a["k"], a["stride"], a["Ho"], a["Wo"]) != 1:
+                continue
+            self.fuse_mask[g.id] = (y, n.attrs["fn"][:-5], float(n.attrs["alpha"]))
+            self.fused_alias[n.id] = g.id
+
+    def _late_vars(self, pairs, force=False):
         """ids of the variables whose gradients become ready last (within one tensor-core launch of the deepest one): the
         optimiser update is split so that only THEIR update waits for the end of the backward pass; every other parameter is
         updated as soon as its own gradient and the last kernel reading it are done.  OPT-IN (GG_SPLIT_UPDATE=1): measured on the
         B200 the early update (87-114 MB of L2 traffic) slows the last backward kernels it overlaps by more than it saves — 0.888
         vs 0.874 ms per iteration (profiles/sched_variants_r2.txt)."""
-        if os.environ.get("GG_SPLIT_UPDATE", "0") != "1" or len(pairs) < 2:
+        if (os.environ.get("GG_SPLIT_UPDATE", "0") != "1" and not force) or len(pairs) < 2:
             return set()
         pos = getattr(self, "ready_pos", {})
         ready = {}
@@ -623,6 +666,9 @@ class Plan(object):
         self.steps.append(lambda st: cabi.call("gg_binary", code, ap, bp, op_, dims, sa4, sb4, alpha, st))
 
     def _emit_binary(self, node):
+        if node.id in self.fused_alias:                   # computed by the producing dgrad launch (_plan_actgrad_fusion)
+            self.buf[node.id] = self.buf[self.fused_alias[node.id]]
+            return
         a, b, out = self._in(node, 0), self._in(node, 1), self._alloc(node)
         self._launch_binary(node.attrs["fn"], node.attrs["alpha"], a.data_ptr(), node.inputs[0].shape, b.data_ptr(),
                             node.inputs[1].shape, out.data_ptr(), tuple(node.shape))
@@ -810,6 +856,11 @@ class Plan(object):
                                                    g["stride"], g["Ho"], g["Wo"]))
         self.keep.append(ws)
         wp, wn = ws.data_ptr(), ws.numel()
+        if node.id in self.fuse_mask:                     # dgrad + the activation gradient that follows it, one launch
+            y, mact, malpha = self.fuse_mask[node.id]
+            yp, mcode = self.buf[y.id].data_ptr(), cabi.ACT[mact]
+            self.steps.append(lambda st: cabi.call("gg_conv2d_dgrad_actgrad", ap, bp, op_, yp, mcode, malpha, *geo, wp, wn, st))
+            return
         name = "gg_conv2d_fwd" if mode == "fwd" else "gg_conv2d_dgrad"
         self.steps.append(lambda st: cabi.call(name, ap, bp, bias, op_, *geo, act, alpha, wp, wn, st))
 

@@ -97,6 +97,15 @@ int gg_conv2d_wgrad(const float* x, const float* dy, float* dw,
                     int pad_t, int pad_l, int Ho, int Wo,
                     void* workspace, size_t workspace_bytes, void* stream);
 size_t gg_conv2d_wgrad_workspace(int B, int H, int W, int Ci, int Co, int k, int stride, int Ho, int Wo);
+/* dx = act'(y_fwd) * dgrad(dy, w): the input-gradient of the conv followed by the gradient of the activation whose OUTPUT y_fwd
+ * (same [B,H,W,Ci] layout as dx) fed the conv in the forward pass — autodiff of `LeakyReLU(Conv2D(...))` chains
+ * (gmgan_inference_cifar10.py:122-123,276-288) in one launch.  Tensor-core path only: returns GG_ERR_UNSUPPORTED when
+ * gg_conv2d_tc_supported(1, ...) is 0. */
+int gg_conv2d_dgrad_actgrad(const float* dy, const float* w, float* dx, const float* y_fwd, int act, float alpha,
+                            int B, int H, int W, int Ci, int Co, int k, int stride, int pad_t, int pad_l, int Ho, int Wo,
+                            void* workspace, size_t workspace_bytes, void* stream);
+/* 1 when mode (0 fwd, 1 dgrad, 2 wgrad) of this geometry runs on the tcgen05 kernels under the current backend setting */
+int gg_conv2d_tc_supported(int mode, int B, int H, int W, int Ci, int Co, int k, int stride, int Ho, int Wo);
 /* workspace bytes for mode 0 fwd / 1 dgrad / 2 wgrad.  The workspace holds split-K partial tiles and, in its first
  * bytes, per-tile arrival tickets: it must be ZERO-INITIALISED ONCE by the caller; every call leaves the tickets zero.
  * A smaller (or NULL) workspace is legal: the call then runs unsplit or on the direct kernels. */

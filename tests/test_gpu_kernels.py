@@ -382,3 +382,37 @@ def test_rng_statistics_and_replay():
     cabi.call("gg_rng_categorical", cabi.ptr(idx), 60000, cabi.ptr(probs), 30, 1234, 9, cabi.ptr(tick), st)
     cnt = torch.bincount(idx.long().cpu(), minlength=30)
     assert int(idx.min()) >= 0 and int(idx.max()) < 30 and int(cnt.min()) > 1700 and int(cnt.max()) < 2300
+
+
+@pytest.mark.parametrize("case", [
+    # B, H, W, Ci, Co, k, stride: the dgrad launches of the cifar plan that are followed by an activation gradient
+    (128, 16, 16, 64, 128, 5, 2), (128, 8, 8, 128, 256, 5, 2), (64, 16, 16, 64, 128, 5, 2), (64, 8, 8, 128, 256, 5, 2),
+    (4, 16, 16, 32, 64, 3, 1), (256, 32, 32, 32, 64, 5, 2),
+])
+@pytest.mark.parametrize("act", ["leaky", "relu"])
+def test_dgrad_with_fused_activation_gradient(case, act):
+    """gg_conv2d_dgrad_actgrad (dx = act'(y) * dgrad(dy, w), the tensor-core write-out applies the mask) is EXACTLY the separate
+    pair gg_conv2d_dgrad -> leaky_grad / relu_grad it replaces in the plan (same accumulation, one extra multiply), and is
+    within 1e-3 of the fp64 oracle."""
+    U, cabi = _mods()
+    B, H, W, Ci, Co, k, stride = case
+    g = torch.Generator().manual_seed(31 + B + Ci)
+    w = torch.randn(k, k, Ci, Co, generator=g, dtype=torch.float64) * 0.05
+    Ho, Wo, pt, pl = U.geom(H, W, k, stride, 'SAME')
+    dy = torch.randn(B, Co, Ho, Wo, generator=g, dtype=torch.float64)
+    y = torch.randn(B, Ci, H, W, generator=g, dtype=torch.float64)
+    x = torch.zeros(B, Ci, H, W, dtype=torch.float64, requires_grad=True)
+    dx_ref, = torch.autograd.grad(O.conv2d(x, w, stride, 'SAME'), x, dy)
+    slope = 0.2 if act == "leaky" else 0.0
+    ref = torch.where(y > 0, dx_ref, slope * dx_ref)
+    assert cabi.lib.gg_conv2d_tc_supported(1, B, H, W, Ci, Co, k, stride, Ho, Wo) == 1
+    dyd, wd, yd = U.dev(U.nhwc(dy)), U.dev(w), U.dev(U.nhwc(y))
+    plain = U.conv_dgrad(dyd, wd, None, H, W, stride, 'SAME')
+    two_step = torch.where(yd > 0, plain, slope * plain)
+    fused = torch.empty_like(plain)
+    wsp = U.ws(cabi.lib.gg_conv2d_workspace(1, B, H, W, Ci, Co, k, stride, Ho, Wo))
+    cabi.call("gg_conv2d_dgrad_actgrad", cabi.ptr(dyd), cabi.ptr(wd), cabi.ptr(fused), cabi.ptr(yd), cabi.ACT[act], 0.2, B, H, W,
+              Ci, Co, k, stride, pt, pl, Ho, Wo, cabi.ptr(wsp), wsp.numel(), cabi.stream_ptr())
+    assert cabi.lib.gg_last_backend() == 1
+    assert torch.equal(fused, two_step), "fused write-out differs from dgrad + mask: max |d| = %g" % float((fused - two_step).abs().max())
+    U.assert_close(U.nchw(fused), ref, 1e-3, "dgrad+actgrad %s %s" % (case, act))
