@@ -456,6 +456,7 @@ int launch_clustered(Kern kern, const BnPlan& pl, cudaStream_t st, const char* w
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
+  if (g_null_launch) { launch_null(st); return check_launch(what); }
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, args...);
   if (e != cudaSuccess) {
     cudaGetLastError();

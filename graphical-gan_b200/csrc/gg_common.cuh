@@ -58,9 +58,15 @@ constexpr int kNumSMs = 148;  // B200
   } while (0)
 
 extern int g_pdl;
+// measurement aid (gg_set_null_launch / GG_NULL_LAUNCH=1): every kernel launch of the library is replaced by an EMPTY one-warp
+// kernel on the same stream.  A captured training step then keeps its exact node / dependency structure but does no work: its
+// duration is the launch + dependency-resolution cost of the graph alone (tools/exp_null_step.py).  Results are garbage.
+extern int g_null_launch;
+void launch_null(cudaStream_t st);
 
 template <typename... KArgs, typename... Args>
 inline void launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  if (g_null_launch) { launch_null(st); return; }
   if (!g_pdl) {
     kernel<<<grid, block, smem, st>>>(static_cast<KArgs>(args)...);
     return;

@@ -660,6 +660,7 @@ int conv_small_wgrad(const float* x, const float* dy, float* dw, int B, int H, i
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
+  if (g_null_launch) { launch_null(st); *handled = true; return check_launch("gg_conv2d_wgrad(small-channel, null launch)"); }
   cudaError_t e = cudaSuccess;
 #define GG_WG(CI_)                                                                                                          \
   e = cudaLaunchKernelEx(&cfg, conv_small_wgrad_kernel<CI_>, x, dy, dw, part, ticket, p, pl.RH, pl.PW, pl.NT, pl.PS,        \

@@ -837,6 +837,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, TcPlan& pl, void* ws,
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
+  if (g_null_launch) { launch_null(st); return check_launch("gg_conv2d(tcgen05, null launch)"); }
   cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<MODE>, tmA, tmB, p);
   if (e != cudaSuccess) { cudaGetLastError(); return fail(GG_ERR_CUDA_BASE + (int)e, "conv_tc: launch failed: %s", cudaGetErrorString(e)); }
   return check_launch(MODE == 0 ? "gg_conv2d_fwd(tcgen05)" : (MODE == 1 ? "gg_conv2d_dgrad(tcgen05)" : "gg_conv2d_wgrad(tcgen05)"));

@@ -9,6 +9,9 @@ thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 thread_local int g_last_backend = 0;
 int g_conv_backend = 0;
+int g_null_launch = 0;
+namespace { __global__ void null_kernel() {} }
+void launch_null(cudaStream_t st) { null_kernel<<<1, 32, 0, st>>>(); }
 int g_pdl = 0;   // programmatic dependent launch for the stream-ordered kernels (gg_set_pdl / GG_PDL=1)
 }  // namespace gg
 
@@ -26,6 +29,10 @@ extern "C" int gg_set_conv_backend(int mode) {
 extern "C" int gg_get_conv_backend(void) { return g_conv_backend; }
 extern "C" int gg_set_pdl(int on) {
   g_pdl = on ? 1 : 0;
+  return GG_OK;
+}
+extern "C" int gg_set_null_launch(int on) {
+  g_null_launch = on ? 1 : 0;
   return GG_OK;
 }
 extern "C" int gg_last_backend(void) { return g_last_backend; }

@@ -115,9 +115,10 @@ __global__ void __launch_bounds__(256) gemm_splitk_finish(const float* __restric
 // the mixture-prior lookups ([64 x 30] @ [30 x 128] and its transpose) are 10^4..10^5 MACs: the tiled split-K kernel above spends
 // 8-12 us on them (two launches, 16 CTAs, a shared-memory round trip per 16-wide K tile; profiles/launches_r2_eager.csv) and four
 // of them sit on the step's critical path.  They get one flat launch each:
-//   gemm_rowdot_kernel   N <= 4, A row-major: one warp per output element, lanes stride K (coalesced), shuffle reduction;
-//   gemm_smallk_kernel   K <= 128 and <= 2^20 MACs (or K <= 4): one thread per output element, sequential fp32 FMA over K.
-template <int TB>
+//   gemm_rowdot_kernel   <= 8192 outputs and K >= 32: one warp per output element, lanes stride K, shuffle reduction (a thread
+//                        per output with a 64-128-long dependent-latency loop measured 13-27 us for [512 x 1] = [128 x 512]^T [128 x 1]);
+//   gemm_smallk_kernel   K < 32 and <= 2^21 MACs: one thread per output element, sequential fp32 FMA over K.
+template <int TA, int TB>
 __global__ void __launch_bounds__(256) gemm_rowdot_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                           const float* __restrict__ bias, float* __restrict__ C, int M, int N, int K,
                                                           int act, float alpha) {
@@ -125,9 +126,9 @@ __global__ void __launch_bounds__(256) gemm_rowdot_kernel(const float* __restric
   const int w = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (w >= M * N) return;
   const int m = w / N, n = w % N;
-  const float* a = A + (long long)m * K;
   float acc = 0.f;
-  for (int k = lane; k < K; k += 32) acc = fmaf(a[k], TB ? B[(long long)n * K + k] : B[(long long)k * N + n], acc);
+  for (int k = lane; k < K; k += 32)
+    acc = fmaf(TA ? A[(long long)k * M + m] : A[(long long)m * K + k], TB ? B[(long long)n * K + k] : B[(long long)k * N + n], acc);
   acc = warp_sum(acc);
   if (lane == 0) C[(long long)m * N + n] = apply_act(acc + (bias ? bias[n] : 0.f), act, alpha);
 }
@@ -197,14 +198,18 @@ extern "C" int gg_gemm(const float* A, const float* Bm, const float* bias, float
   }
   static int thin = -1;
   if (thin < 0) { const char* e = getenv("GG_GEMM_THIN"); thin = (e && e[0] == '0') ? 0 : 1; }
-  if (thin && N <= 4 && !ta) {
+  if (thin && (long long)M * N <= 8192 && K >= 32) {
     g_last_backend = 0;
-    const long long threads = (long long)M * N * 32;
-    if (tb) GG_LAUNCH((gemm_rowdot_kernel<1>), ceil_div(threads, 256), 256, 0, st, A, Bm, bias, C, M, N, K, act, alpha);
-    else GG_LAUNCH((gemm_rowdot_kernel<0>), ceil_div(threads, 256), 256, 0, st, A, Bm, bias, C, M, N, K, act, alpha);
+    const int blocks = ceil_div((long long)M * N * 32, 256);
+#define GG_LAUNCH_ROWDOT(TA, TB) GG_LAUNCH((gemm_rowdot_kernel<TA, TB>), blocks, 256, 0, st, A, Bm, bias, C, M, N, K, act, alpha)
+    if (!ta && !tb) GG_LAUNCH_ROWDOT(0, 0);
+    else if (ta && !tb) GG_LAUNCH_ROWDOT(1, 0);
+    else if (!ta && tb) GG_LAUNCH_ROWDOT(0, 1);
+    else GG_LAUNCH_ROWDOT(1, 1);
+#undef GG_LAUNCH_ROWDOT
     return check_launch("gg_gemm(rowdot)");
   }
-  if (thin && (K <= 4 || (K <= 128 && (long long)M * N * K <= (1 << 20)))) {
+  if (thin && K < 32 && (long long)M * N * K <= (1 << 21)) {
     g_last_backend = 0;
     const int blocks = ceil_div((long long)M * N, 256);
 #define GG_LAUNCH_SMALLK(TA, TB) GG_LAUNCH((gemm_smallk_kernel<TA, TB>), blocks, 256, 0, st, A, Bm, bias, C, M, N, K, act, alpha)

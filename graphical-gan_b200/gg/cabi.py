@@ -40,6 +40,7 @@ SIGNATURES = {
     "gg_get_conv_backend": (c_i, []),
     "gg_last_backend": (c_i, []),
     "gg_set_pdl": (c_i, [c_i]),
+    "gg_set_null_launch": (c_i, [c_i]),
     "gg_set_tc_max_ctas": (c_i, [c_i]),
     "gg_set_tc_stages": (c_i, [c_i]),
     "gg_last_tc_info": (c_i, [C.POINTER(c_i)]),

@@ -317,6 +317,10 @@ int gg_probe_umma_tf32(const float* A, const float* Bm, float* D, int N, int K, 
  * %globaltimer timeline (slot 0 start, 1+i TMA issue of k-block i, 64+i operands landed, 128 accumulator ready,
  * 129 partial written, 131 epilogue done).  NULL disables it. */
 int gg_debug_set_buffer(void* device_buffer_256_int64);
+/* measurement aid: on != 0 replaces EVERY kernel launch of the library by an empty one-warp kernel on the same stream, so a captured
+ * step keeps its node / dependency structure but does no work (tools/exp_null_step.py measures the graph's own launch + dependency
+ * cost this way).  Results are garbage while it is on. */
+int gg_set_null_launch(int on);
 /* development aid for the one-launch small-channel filter gradient (gg_conv2d_wgrad with Ci <= 4): when set to a device buffer
  * of >= 8 * 160 int64, CTA b writes %globaltimer stamps at [8*b + s]: s = 0 entry, 1 tiles staged, 2 FMA loops done,
  * 3 cluster rendezvous, 4 cluster partial in L2, 5 ticket taken, 6 (last cluster) dw written.  NULL disables it. */
