@@ -159,8 +159,10 @@ __device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((
 #define GG_DBG(slot) do { } while (0)
 #endif
 
+// min-blocks 2 for fwd / dgrad: ptxas then keeps the register count where two 352-thread CTAs fit an SM (un-split launches with
+// more tiles than SMs co-reside two CTAs so that one's epilogue overlaps the other's main loop); wgrad launches are always split
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, MODE == 2 ? 1 : 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -481,7 +483,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             sts128(ring + (uint32_t)(((c0 + i) >> 2) * 128 + m) * 16u, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
         }
         fence_proxy_async();                      // generic-proxy writes -> visible to the copy engine
-        asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");   // the 4 quadrant warps of this column half
+        // the 4 quadrant warps of this column half.  IMMEDIATE barrier ids: with a register operand ptxas reserves all 16 named
+        // barriers of the SM for every CTA ("used 16 barriers"), which silently capped the kernel at ONE CTA per SM — the
+        // 3-stage / 75-97 KB configurations meant to put two CTAs on an SM never did (profiles/timeline_face_r2.txt: 512 tiles
+        // took 3.5 waves of 148)
+        if (half == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
+        else asm volatile("bar.sync 3, 128;" ::: "memory");
         if (pusher) {
           const int c4lo = c0 >> 2, c4hi = (c0 + cw_chunk) >> 2;
           for (int j = 0; j < p.splits; ++j) {
@@ -783,6 +790,9 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, TcPlan& pl, void* ws,
     // opt-in limit is 227 KB per block INCLUDING the kernel's static shared memory (barriers, row table, bias: ~3 KB)
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
     if (e != cudaSuccess) return fail(GG_ERR_CUDA_BASE + (int)e, "conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    // largest shared-memory carveout: the driver's default choice follows the footprint of ONE block of the launch, which leaves
+    // no room for a second 75-97 KB CTA on the SM
+    cudaFuncSetAttribute(conv_tc_kernel<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     attr_set[MODE] = true;
   }
   p.stages = kMaxStages;

@@ -68,7 +68,13 @@ A2 = torch.randn(64, 4608, device="cuda"); B2 = torch.randn(4608, 512, device="c
 x1 = torch.randn(64, 32, 32, 3, device="cuda"); w1 = torch.randn(5, 5, 3, 64, device="cuda") * .05; b1 = torch.zeros(64, device="cuda")
 x3 = torch.randn(B, 8, 8, 128, device="cuda"); w3 = torch.randn(k, k, 128, 256, device="cuda") * .05; b3 = torch.zeros(256, device="cuda")
 xb = torch.randn(2 * B, H, W, Ci, device="cuda")
+# the face / SSGAN discriminators (DIM 32, 64x64 inputs): D.2 on the batched towers, 256 x 32x32x32 -> 64
+xf = torch.randn(256, 32, 32, 32, device="cuda"); wf = torch.randn(k, k, 32, 64, device="cuda") * .05; bf = torch.zeros(64, device="cuda")
+dyf = torch.randn(256, 16, 16, 64, device="cuda")
 cases = (
+    ("face D.2 fwd B=256 32->64", lambda: U.conv_fwd(xf, wf, bf, s, 'SAME', act="leaky")),
+    ("face D.2 dgrad B=256", lambda: U.conv_dgrad(dyf, wf, None, 32, 32, s, 'SAME')),
+    ("face D.2 wgrad B=256", lambda: U.conv_wgrad(xf, dyf, k, s, 'SAME')),
     ("D.2 fwd batched B=128", lambda: U.conv_fwd(xb, w, b, s, 'SAME', act="leaky")),
     ("gemm 64x512x512", lambda: U.gemm(A_, B_, bias_, 64, 512, 512, 0, 0, act="leaky")),
     ("gemm 64x512x4608", lambda: U.gemm(A2, B2, bias_, 64, 512, 4608, 0, 0, act="leaky")),
