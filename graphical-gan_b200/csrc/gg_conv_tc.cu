@@ -780,6 +780,16 @@ int max_active_clusters(int splits, size_t smem) {
   return n;
 }
 
+int unsplit_stages(int stages, int n_tile) {
+  if (g_tc_stage_cap < 2) return stages;
+  int cap = g_tc_stage_cap;
+  if (cap == 3) {
+    const int fit = (113 * 1024 - 4096) / (kABytes + n_tile * 128);
+    if (fit > cap) cap = fit;
+  }
+  return cap < stages ? cap : stages;
+}
+
 template <int MODE>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, TcPlan& pl, void* ws, size_t ws_bytes, cudaStream_t st) {
   TcParams& p = pl.p;
@@ -802,9 +812,10 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, TcPlan& pl, void* ws,
     int fit = (int)((113 * 1024 - 4096) / (kABytes + p.n_tile * 128));
     p.stages = fit < 3 ? 3 : (fit > kMaxStages ? kMaxStages : fit);
   }
-  // ring-depth cap (gg_set_tc_stages): 3 stages = 97 KB, so two un-split CTAs — of the same or of two concurrent launches
-  // on different streams — share an SM
-  if (p.splits == 1 && g_tc_stage_cap >= 2 && g_tc_stage_cap < p.stages) p.stages = g_tc_stage_cap;
+  // ring-depth cap (gg_set_tc_stages): two un-split CTAs — of the same or of two concurrent launches on different streams —
+  // share an SM when each stays under ~113 KB.  Cap 3 (the multi-stream plans' setting) means "as deep as that allows":
+  // 3 stages of 32 KB for 128-wide tiles, 4 of 24 KB for 64-wide, 5 of 20 KB for 32-wide ones.
+  if (p.splits == 1) p.stages = unsplit_stages(p.stages, p.n_tile);
   size_t smem = smem_layout(p);
   // split-K CTAs never share an SM (ring + landing slots exceed half of it) and the main loop is bound by ring depth /
   // round-trip latency (timeline: 0.7 us from TMA issue to the freed slot), so the ring is as deep as fits beside the
@@ -821,7 +832,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, TcPlan& pl, void* ws,
     p.stages = kMaxStages;
     smem = smem_layout(p);
     while (p.splits > 1 && smem > (size_t)kMaxDynSmem && p.stages > 2) { --p.stages; smem = smem_layout(p); }
-    if (p.splits == 1 && g_tc_stage_cap >= 2 && g_tc_stage_cap < p.stages) { p.stages = g_tc_stage_cap; smem = smem_layout(p); }
+    if (p.splits == 1) { p.stages = unsplit_stages(p.stages, p.n_tile); smem = smem_layout(p); }
   }
   dim3 grid(pl.grid_x, p.splits);
   g_last_info[0] = MODE; g_last_info[1] = pl.grid_x; g_last_info[2] = p.splits; g_last_info[3] = p.n_tile;

@@ -264,7 +264,7 @@ class Plan(object):
         self.order = self._toposort(roots)
         # split-K of the tensor-core kernels may use every SM (GG_TC_MAX_CTAS caps it); with the 3-stage ring two CTAs share an
         # SM, so two launches on different streams still overlap.  Workspace sizes depend on both: fixed before emission
-        self.n_streams = int(os.environ.get("GG_STREAMS", "6")) if rt.use_cuda_graph else 1
+        self.n_streams = int(os.environ.get("GG_STREAMS", "8")) if rt.use_cuda_graph else 1
         cabi.call("gg_set_tc_max_ctas", int(os.environ.get("GG_TC_MAX_CTAS", "148")))
         cabi.call("gg_set_pdl", 1 if (os.environ.get("GG_PDL", "0") == "1" and rt.use_cuda_graph) else 0)
         cabi.call("gg_set_tc_stages", int(os.environ.get("GG_TC_STAGES", "3" if self.n_streams > 1 else "0")))

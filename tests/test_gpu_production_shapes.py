@@ -153,8 +153,9 @@ def _run_workload(script, kw, must_have):
         mode, B, H, W, Ci, Co = key[:6]
         if Ci % 32 == 0 and Co % 32 == 0:
             assert backend == 1, "tensor-core path not taken for production launch %s" % (key,)
-            # un-split launches keep the 3-stage ring (two CTAs per SM); split-K clusters own their SM and run a deeper ring
-            assert (info["stages"] <= 3 or info["splits"] > 1) and 1 <= info["splits"] <= 8, info
+            # un-split launches keep their ring under half an SM (two CTAs per SM); split-K clusters own their SM and run a deeper ring
+            stage_bytes = 128 * 32 * 4 + info["n_tile"] * 128
+            assert (info["stages"] * stage_bytes <= 113 * 1024 or info["splits"] > 1) and 1 <= info["splits"] <= 8, info
             assert info["tiles"] * info["splits"] <= 2 * 148 or info["splits"] == 1, info
     for key, alpha in sorted(gemms.items(), key=str):
         backend, info = _check_gemm(U, cabi, key, alpha, report)
