@@ -404,6 +404,47 @@ extern "C" int gg_transpose_b2d(const float* x, float* y, int Bt, int R, int C, 
   return check_launch("gg_transpose_b2d");
 }
 
+// batched transpose whose batches need not be contiguous: input batch b starts at x + b*x_bs (rows of C floats), output batch b
+// at y + b*y_bs ([C][R]).  Serves (1) the NHWC -> NCHW flatten written straight into the column range of a concat buffer
+// (y_bs = the concat's row length) and (2) its mirror in the backward pass: the column slice of the dense layer's input
+// gradient transposed back without a slice copy (x_bs = the sliced tensor's row length) — optionally multiplied by act'(m) of
+// the forward activation m (same layout as the output), i.e. the activation gradient that follows.
+__global__ void __launch_bounds__(256) transpose_b2d_ex_kernel(const float* __restrict__ x, float* __restrict__ y, int R, int C,
+                                                               long long x_bs, long long y_bs, const float* __restrict__ mask,
+                                                               int mask_act, float mask_alpha) {
+  GG_PDL_ENTRY();
+  __shared__ float tile[32][33];
+  int b = blockIdx.z;
+  const float* xb = x + (long long)b * x_bs;
+  float* yb = y + (long long)b * y_bs;
+  const float* mb = mask ? mask + (long long)b * R * C : nullptr;
+  int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    int r = r0 + j, c = c0 + threadIdx.x;
+    if (r < R && c < C) tile[j][threadIdx.x] = xb[(long long)r * C + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    int c = c0 + j, r = r0 + threadIdx.x;
+    if (r < R && c < C) {
+      float v = tile[threadIdx.x][j];
+      if (mb) v = act_grad_from_out(mb[(long long)c * R + r], v, mask_act, mask_alpha);
+      yb[(long long)c * R + r] = v;
+    }
+  }
+}
+
+extern "C" int gg_transpose_b2d_ex(const float* x, float* y, int Bt, int R, int C, long long x_batch_stride,
+                                   long long y_batch_stride, const float* mask, int mask_act, float mask_alpha, void* stream) {
+  if (Bt <= 0 || R <= 0 || C <= 0) return GG_OK;
+  GG_REQUIRE(Bt <= 65535, "gg_transpose_b2d_ex");
+  GG_REQUIRE(x_batch_stride >= (long long)R * C && y_batch_stride >= (long long)R * C, "gg_transpose_b2d_ex");
+  dim3 grid(ceil_div(C, 32), ceil_div(R, 32), Bt), block(32, 8);
+  GG_LAUNCH(transpose_b2d_ex_kernel, grid, block, 0, as_stream(stream), x, y, R, C, x_batch_stride, y_batch_stride, mask, mask_act,
+            mask_alpha);
+  return check_launch("gg_transpose_b2d_ex");
+}
+
 struct Perm4 { int od[4]; long long is[4]; };
 __global__ void __launch_bounds__(256) transpose4_kernel(const float* __restrict__ x, float* __restrict__ y, Perm4 p, long long n) {
   GG_PDL_ENTRY();
@@ -590,4 +631,114 @@ extern "C" int gg_add_n(const float* const* ptrs, int count, float* out, long lo
   for (int i = 0; i < count; ++i) pl.p[i] = ptrs[i];
   GG_LAUNCH(add_n_kernel, ew_grid(n, 1), 256, 0, as_stream(stream), pl, count, out, n);
   return check_launch("gg_add_n");
+}
+
+// ------------------------------------------------------------------------------------------
+// fused element-wise programs (include/gg_b200.h: gg_ew_program)
+// ------------------------------------------------------------------------------------------
+// One thread evaluates the whole program for one element of the iteration space.  The register file lives in shared memory
+// ([register][thread]: conflict-free, dynamically indexable); the program itself is a __grid_constant__ kernel parameter, so
+// instruction fetch is a uniform constant-bank load.  Arithmetic goes through unary_apply / binary_apply — the code the
+// one-op kernels run — so a fused group is bit-identical to the launches it replaces (tests/test_gpu_fusion.py).
+#define GG_EW_THREADS 256
+
+__device__ __forceinline__ void ew_eval(const gg_ew_program& p, float (*regs)[GG_EW_THREADS], int t, long long idx) {
+  if (p.flat) {
+    for (int k = 0; k < p.n_in; ++k)
+      regs[k][t] = p.in_is_int[k] ? (float)reinterpret_cast<const int32_t*>(p.in[k])[idx] : reinterpret_cast<const float*>(p.in[k])[idx];
+  } else {
+    long long r = idx;
+    int i3 = (int)(r % p.dims[3]); r /= p.dims[3];
+    int i2 = (int)(r % p.dims[2]); r /= p.dims[2];
+    int i1 = (int)(r % p.dims[1]); r /= p.dims[1];
+    int i0 = (int)r;
+    for (int k = 0; k < p.n_in; ++k) {
+      long long o = (long long)i0 * p.in_stride[k][0] + (long long)i1 * p.in_stride[k][1] + (long long)i2 * p.in_stride[k][2] +
+                    (long long)i3 * p.in_stride[k][3];
+      regs[k][t] = p.in_is_int[k] ? (float)reinterpret_cast<const int32_t*>(p.in[k])[o] : reinterpret_cast<const float*>(p.in[k])[o];
+    }
+  }
+  for (int j = 0; j < p.n_instr; ++j) {
+    const gg_ew_instr& q = p.instr[j];
+    float v;
+    if (q.kind == 0) v = unary_apply(q.op, regs[q.src0][t], q.a, q.b);
+    else v = binary_apply(q.op, regs[q.src0][t], regs[q.src1][t], q.a);
+    regs[q.dst][t] = v;
+  }
+}
+
+__global__ void __launch_bounds__(GG_EW_THREADS) ew_program_kernel(const __grid_constant__ gg_ew_program p, long long n) {
+  GG_PDL_ENTRY();
+  __shared__ float regs[GG_EW_REGS][GG_EW_THREADS];
+  const int t = threadIdx.x;
+  long long i = (long long)blockIdx.x * blockDim.x + t;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    ew_eval(p, regs, t, i);
+    for (int k = 0; k < p.n_out; ++k) p.out[k][i] = regs[p.out_reg[k]][t];
+  }
+}
+
+// output 0 reduced along the last dimension, one CTA per row, with reduce_rows_kernel's summation order (thread-strided partial
+// sums, warp butterfly, per-warp partials in shared memory, one more butterfly); outputs 1.. are stored per element
+__global__ void __launch_bounds__(GG_EW_THREADS) ew_program_reduce_kernel(const __grid_constant__ gg_ew_program p, int rows, int red) {
+  GG_PDL_ENTRY();
+  __shared__ float regs[GG_EW_REGS][GG_EW_THREADS];
+  __shared__ float sh[32];
+  const int t = threadIdx.x;
+  const int o = blockIdx.x;
+  if (o >= rows) return;
+  const bool is_max = p.reduce_op == 3;
+  float acc = is_max ? -INFINITY : 0.f;
+  for (int r = t; r < red; r += blockDim.x) {
+    const long long idx = (long long)o * red + r;
+    ew_eval(p, regs, t, idx);
+    const float v = regs[p.out_reg[0]][t];
+    acc = is_max ? fmaxf(acc, v) : acc + v;
+    for (int k = 1; k < p.n_out; ++k) p.out[k][idx] = regs[p.out_reg[k]][t];
+  }
+  int lane = t & 31, w = t >> 5, nw = blockDim.x >> 5;
+  acc = is_max ? warp_max(acc) : warp_sum(acc);
+  if (lane == 0) sh[w] = acc;
+  __syncthreads();
+  if (w == 0) {
+    float r = (lane < nw) ? sh[lane] : (is_max ? -INFINITY : 0.f);
+    r = is_max ? warp_max(r) : warp_sum(r);
+    if (lane == 0) p.out[0][o] = (p.reduce_op == 2) ? r / (float)red : r;
+  }
+}
+
+extern "C" int gg_ew_program_bytes(void) { return (int)sizeof(gg_ew_program); }
+
+extern "C" int gg_ew_run(const gg_ew_program* prog, void* stream) {
+  if (prog == nullptr) return fail(GG_ERR_BAD_ARG, "gg_ew_run: null program%s");
+  const gg_ew_program& p = *prog;
+  GG_REQUIRE(p.n_in >= 0 && p.n_in <= GG_EW_MAX_IN && p.n_out >= 1 && p.n_out <= GG_EW_MAX_OUT && p.n_instr >= 0 &&
+             p.n_instr <= GG_EW_MAX_INSTR, "gg_ew_run");
+  GG_REQUIRE(p.reduce_op >= 0 && p.reduce_op <= 3, "gg_ew_run");
+  long long n = 1;
+  for (int i = 0; i < 4; ++i) {
+    if (p.dims[i] <= 0) return GG_OK;
+    n *= p.dims[i];
+  }
+  for (int k = 0; k < p.n_in; ++k) GG_REQUIRE(p.in[k] != nullptr, "gg_ew_run");
+  for (int k = 0; k < p.n_out; ++k) GG_REQUIRE(p.out[k] != nullptr && p.out_reg[k] >= 0 && p.out_reg[k] < GG_EW_REGS, "gg_ew_run");
+  for (int j = 0; j < p.n_instr; ++j) {
+    const gg_ew_instr& q = p.instr[j];
+    GG_REQUIRE(q.kind == 0 || q.kind == 1, "gg_ew_run");
+    GG_REQUIRE(q.dst >= 0 && q.dst < GG_EW_REGS && q.src0 >= 0 && q.src0 < GG_EW_REGS, "gg_ew_run");
+    GG_REQUIRE(q.kind == 0 ? (q.op >= 0 && q.op <= GG_U_RDIVC) : (q.op >= 0 && q.op <= GG_B_POW && q.src1 >= 0 && q.src1 < GG_EW_REGS),
+               "gg_ew_run");
+  }
+  cudaStream_t st = as_stream(stream);
+  if (p.reduce_op == 0) {
+    GG_LAUNCH(ew_program_kernel, ew_grid(n, 1, GG_EW_THREADS), GG_EW_THREADS, 0, st, p, n);
+  } else {
+    const int red = p.dims[3];
+    const long long rows = n / red;
+    GG_REQUIRE(rows <= 0x7fffffffLL, "gg_ew_run");
+    int threads = red >= 1024 ? 256 : (red >= 128 ? 128 : 32);          // = gg_reduce's row kernel
+    GG_LAUNCH(ew_program_reduce_kernel, (int)rows, threads, 0, st, p, (int)rows, red);
+  }
+  return check_launch("gg_ew_run");
 }

@@ -72,7 +72,10 @@ SIGNATURES = {
     "gg_softmax_fwd": (c_i, [c_p, c_p, c_i, c_i, c_p]),
     "gg_softmax_bwd": (c_i, [c_p, c_p, c_p, c_i, c_i, c_p]),
     "gg_transpose_b2d": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p]),
+    "gg_transpose_b2d_ex": (c_i, [c_p, c_p, c_i, c_i, c_i, c_ll, c_ll, c_p, c_i, c_f, c_p]),
     "gg_transpose4": (c_i, [c_p, c_p, C.POINTER(c_i), C.POINTER(c_i), c_p]),
+    "gg_ew_run": (c_i, [c_p, c_p]),
+    "gg_ew_program_bytes": (c_i, []),
     "gg_copy2d": (c_i, [c_p, c_ll, c_p, c_ll, c_ll, c_ll, c_i, c_p]),
     "gg_fill": (c_i, [c_p, c_ll, c_f, c_p]),
     "gg_one_hot": (c_i, [c_p, c_p, c_i, c_i, c_p]),
@@ -112,10 +115,28 @@ SIGNATURES = {
     "gg_probe_umma_tf32": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
 }
 
+GG_EW_MAX_IN, GG_EW_MAX_OUT, GG_EW_MAX_INSTR, GG_EW_REGS = 12, 4, 40, 32
+
+
+class EwInstr(C.Structure):
+    """gg_ew_instr of include/gg_b200.h"""
+    _fields_ = [("kind", c_i), ("op", c_i), ("dst", c_i), ("src0", c_i), ("src1", c_i), ("a", c_f), ("b", c_f)]
+
+
+class EwProgram(C.Structure):
+    """gg_ew_program of include/gg_b200.h (passed by pointer; the library copies it into the launch)"""
+    _fields_ = [("n_in", c_i), ("n_out", c_i), ("n_instr", c_i), ("flat", c_i), ("reduce_op", c_i), ("dims", c_i * 4),
+                ("inp", c_p * GG_EW_MAX_IN), ("in_is_int", c_i * GG_EW_MAX_IN), ("in_stride", (c_i * 4) * GG_EW_MAX_IN),
+                ("out", c_p * GG_EW_MAX_OUT), ("out_reg", c_i * GG_EW_MAX_OUT), ("instr", EwInstr * GG_EW_MAX_INSTR)]
+
+
 for _name, (_res, _args) in SIGNATURES.items():
     _fn = getattr(lib, _name)  # AttributeError here = the .so is stale w.r.t. the header
     _fn.restype = _res
     _fn.argtypes = _args
+
+if lib.gg_ew_program_bytes() != C.sizeof(EwProgram):
+    raise ImportError("gg_ew_program layout mismatch: library %d bytes, ctypes %d" % (lib.gg_ew_program_bytes(), C.sizeof(EwProgram)))
 
 GG_ADAM_CHUNK = 4096
 

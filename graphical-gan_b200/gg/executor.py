@@ -281,7 +281,13 @@ class Plan(object):
         self._plan_inplace_concats()
         self._plan_grad_buckets(fetches)
         self._plan_actgrad_fusion(fetches)
+        self._plan_ew_fusion(fetches)
         for node in self.order:
+            cl = self.ew_cluster_of.get(node.id)
+            if cl is not None:
+                if not cl.emitted:
+                    self._emit_ew_cluster(cl)
+                continue
             s0 = len(self.steps)
             self._emit(node)
             self._note_group(node, s0)
@@ -554,6 +560,93 @@ class Plan(object):
                 continue
             self.fuse_mask[g.id] = (y, n.attrs["fn"][:-5], float(n.attrs["alpha"]))
             self.fused_alias[n.id] = g.id
+
+    # ---- element-wise cluster fusion (gg/fuse.py) ------------------------------------------------------------------------
+    def _plan_ew_fusion(self, fetches):
+        """group connected element-wise nodes into clusters that run as one gg_ew_run launch each, and re-sort the plan so
+        that every cluster sits behind all of its inputs (GG_FUSE_EW=0: one launch per node, as before)"""
+        from . import fuse
+        self.ew_cluster_of, self.ew_clusters = {}, []
+        if os.environ.get("GG_FUSE_EW", "1") == "0":
+            return
+        ext = {}
+        for f in fetches:
+            if isinstance(f, Tensor):
+                ext[f.id] = ext.get(f.id, 0) + 1
+            else:
+                for d in self._op_roots(f):
+                    ext[d.id] = ext.get(d.id, 0) + 1
+        for gid, (y, _act, _alpha) in self.fuse_mask.items():
+            ext[y.id] = ext.get(y.id, 0) + 1
+        excluded = set(self.fused_alias)
+        clusters = fuse.Planner(self.order, self.fed, ext, excluded).build()
+        if not clusters:
+            return
+        for cl in clusters:
+            for n in cl.nodes():
+                assert n.id not in self.ew_cluster_of, "node %s in two element-wise clusters" % n
+                self.ew_cluster_of[n.id] = cl
+        self.ew_clusters = clusters
+        # stable topological re-sort with every cluster as ONE unit (keyed by its last node's old position)
+        pos = {n.id: i for i, n in enumerate(self.order)}
+        unit_of, unit_nodes, unit_key = {}, {}, {}
+        for n in self.order:
+            cl = self.ew_cluster_of.get(n.id)
+            u = ("c", id(cl)) if cl is not None else ("n", n.id)
+            unit_of[n.id] = u
+            unit_nodes.setdefault(u, []).append(n)
+            unit_key[u] = max(unit_key.get(u, -1), pos[n.id])
+        extra = {}
+        for gid, (y, _act, _alpha) in self.fuse_mask.items():     # the fused dgrad launch reads its activation mask y
+            extra.setdefault(gid, []).append(y)
+        deps, succ = {u: set() for u in unit_nodes}, {u: set() for u in unit_nodes}
+        for n in self.order:
+            if n.id in self.fed:
+                continue
+            for i in list(n.inputs) + extra.get(n.id, []):
+                if i.id in unit_of and unit_of[i.id] != unit_of[n.id]:
+                    deps[unit_of[n.id]].add(unit_of[i.id])
+                    succ[unit_of[i.id]].add(unit_of[n.id])
+        import heapq
+        ready = [(unit_key[u], u) for u in unit_nodes if not deps[u]]
+        heapq.heapify(ready)
+        left = {u: len(deps[u]) for u in unit_nodes}
+        order = []
+        while ready:
+            _, u = heapq.heappop(ready)
+            order.extend(unit_nodes[u])
+            for v in succ[u]:
+                left[v] -= 1
+                if left[v] == 0:
+                    heapq.heappush(ready, (unit_key[v], v))
+        assert len(order) == len(self.order), "element-wise clustering produced a dependency cycle"
+        self.order = order
+
+    def _emit_ew_cluster(self, cl):
+        from . import fuse
+        d = cl.desc
+        s0 = len(self.steps)
+        out_bufs = []
+        for m in d["out_nodes"]:
+            target = cl.reduce if (d["reduce"] and m is cl.members[-1]) else m
+            out_bufs.append(self._alloc(target))
+        for m in d["interior"]:
+            if m.id not in self.buf:
+                self.buf[m.id] = None               # lives in a register of the fused launch only
+        for a in cl.aliases:                        # in plan order: an alias of an alias resolves through its input
+            self.buf[a.id] = self.buf[a.inputs[0].id]
+        in_ptrs = [self.buf[ld["node"].id].data_ptr() for ld in d["loads"]]
+        prog = fuse.to_struct(d, in_ptrs, [t.data_ptr() for t in out_bufs])
+        self.keep.append(prog)
+        ref = C.byref(prog)
+        self.steps.append(lambda st: cabi.call("gg_ew_run", ref, st))
+        cl.emitted = True
+        reads = set()
+        for ld in d["loads"]:
+            reads |= self._owners(ld["node"])
+        for n in cl.nodes():
+            self.owner[n.id] = frozenset([cl.key])
+        self._add_groups(s0, len(self.steps), reads, cl.key, barrier=False, node=(cl.reduce if cl.reduce is not None else cl.members[-1]))
 
     def _late_vars(self, pairs, force=False):
         """ids of the variables whose gradients become ready last (within one tensor-core launch of the deepest one): the

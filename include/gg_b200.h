@@ -206,6 +206,12 @@ int gg_softmax_fwd(const float* x, float* y, int R, int C, void* stream);
 int gg_softmax_bwd(const float* y, const float* dy, float* dx, int R, int C, void* stream);
 /* y[b,c,r] = x[b,r,c]  (NHWC<->NCHW is a batched 2-D transpose) */
 int gg_transpose_b2d(const float* x, float* y, int Bt, int R, int C, void* stream);
+/* the same with non-contiguous batches (batch b of x at x + b*x_batch_stride, of y at y + b*y_batch_stride, strides in floats) and
+ * an optional fused activation gradient y = act'(mask) * transpose(x) (mask: forward activation in the OUTPUT layout, contiguous):
+ * the NCHW-flatten of `tf.reshape(output, [-1, 4*4*4*DIM])` written straight into `tf.concat([output, z_output], 1)`
+ * (gmgan_inference_cifar10.py:292-294) and its mirror in the backward pass, each without the copy launches around it. */
+int gg_transpose_b2d_ex(const float* x, float* y, int Bt, int R, int C, long long x_batch_stride, long long y_batch_stride,
+                        const float* mask, int mask_act, float mask_alpha, void* stream);
 /* generic permutation of up to 4 dims: y = transpose(x, perm), dims = shape of x */
 int gg_transpose4(const float* x, float* y, const int* dims4, const int* perm4, void* stream);
 /* strided 2-D copy (concat / slice building block): dst[r*dst_ld + c] = src[r*src_ld + c]; accumulate!=0 adds */
@@ -224,6 +230,41 @@ int gg_cast_f32_i32(const float* x, int32_t* y, long long n, void* stream);
 int gg_widen_u8_i32(const uint8_t* x, int32_t* y, long long n, void* stream);
 /* out = sum_i in[i] over `count` same-sized tensors whose device pointers are listed in ptrs (host array) */
 int gg_add_n(const float* const* ptrs, int count, float* out, long long n, void* stream);
+
+/* ---- fused element-wise programs ----------------------------------------------------------------------------------------
+ * The script-level glue of the reference is long chains of tiny tf.* ops: the Gumbel-softmax noise
+ * `-tf.log(-tf.log(U + eps) + eps)` and the soft assignment around it (gmgan_inference_cifar10.py:155-163), the input
+ * decode `2*((tf.cast(x, tf.float32)/255.)-.5)` (:341-342), the mixture-prior distances, and their gradients.  Each op is a
+ * 2-3 us launch on a KB-sized tensor; a connected group of them runs as ONE launch of a small register program evaluated
+ * per output element: values live in registers 0..GG_EW_REGS-1, registers 0..n_in-1 are loaded from the inputs (broadcast by
+ * per-dimension element strides, 0 = broadcast; int32 inputs are converted like tf.cast), then `instr` runs in order — the
+ * SAME arithmetic as gg_unary / gg_binary (bit-identical results) — and up to GG_EW_MAX_OUT registers are stored.
+ * reduce_op != 0: the iteration space is [rows, red] (red = dims[3]) and output 0 is reduced along `red` with the summation
+ * order of gg_reduce's row kernel (one CTA per row) instead of being stored per element: out[0][row] = sum / mean / max. */
+#define GG_EW_MAX_IN 12
+#define GG_EW_MAX_OUT 4
+#define GG_EW_MAX_INSTR 40
+#define GG_EW_REGS 32
+typedef struct {
+  int kind;        /* 0: regs[dst] = unary(op, regs[src0], a, b)   1: regs[dst] = binary(op, regs[src0], regs[src1], alpha = a) */
+  int op;          /* GG_U_* / GG_B_* */
+  int dst, src0, src1;
+  float a, b;
+} gg_ew_instr;
+typedef struct {
+  int n_in, n_out, n_instr;
+  int flat;                              /* 1: every input has the (contiguous) shape of the iteration space */
+  int reduce_op;                         /* 0 none, 1 sum, 2 mean, 3 max (output 0 only) */
+  int dims[4];
+  const void* in[GG_EW_MAX_IN];
+  int in_is_int[GG_EW_MAX_IN];
+  int in_stride[GG_EW_MAX_IN][4];
+  float* out[GG_EW_MAX_OUT];
+  int out_reg[GG_EW_MAX_OUT];
+  gg_ew_instr instr[GG_EW_MAX_INSTR];
+} gg_ew_program;
+int gg_ew_run(const gg_ew_program* prog, void* stream);
+int gg_ew_program_bytes(void);   /* sizeof(gg_ew_program): lets a foreign-language binding verify its struct layout */
 
 /* ---- fused loss reductions (tflib/objs/gan_inference.py:85-101; tflib/utils/distance.py:3-7; gan_inference_svhn.py:353-354) */
 /* out[0] (+)= weight * mean_i BCE(x_i, label); accumulate!=0 adds to out[0] */

@@ -1,0 +1,195 @@
+"""-m gpu: the fused element-wise program launches (gg_ew_run, gg/fuse.py) are BIT-IDENTICAL to the one-op launches they replace.
+
+(1) hand-written programs through the C-ABI against gg_unary / gg_binary / gg_reduce chains: broadcast strides, int32 loads,
+    several outputs, register reuse, the three thread-count tiers of the row reduction;
+(2) whole training plans of every model family with GG_FUSE_EW=1 vs GG_FUSE_EW=0 on the same parameters, batches and injected
+    noise: costs and every parameter after several iterations must be equal bit for bit."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "graphical-gan_b200", "scripts"))
+
+
+def _prog(dims, loads, instrs, outs, flat, reduce_op=0):
+    """loads: [(tensor, strides4, is_int)], instrs: [(kind, op, dst, src0, src1, a, b)], outs: [(tensor, reg)]"""
+    from gg import cabi
+    p = cabi.EwProgram()
+    p.n_in, p.n_out, p.n_instr, p.flat, p.reduce_op = len(loads), len(outs), len(instrs), int(flat), reduce_op
+    for i in range(4):
+        p.dims[i] = dims[i]
+    for k, (t, s, is_int) in enumerate(loads):
+        p.inp[k] = t.data_ptr()
+        p.in_is_int[k] = int(is_int)
+        for i in range(4):
+            p.in_stride[k][i] = s[i]
+    for k, (t, r) in enumerate(outs):
+        p.out[k] = t.data_ptr()
+        p.out_reg[k] = r
+    for j, (kind, op, dst, s0, s1, a, b) in enumerate(instrs):
+        q = p.instr[j]
+        q.kind, q.op, q.dst, q.src0, q.src1, q.a, q.b = kind, op, dst, s0, s1, a, b
+    return p
+
+
+def _unary(fn, x, a=0.0, b=0.0):
+    from gg import cabi
+    y = torch.empty_like(x)
+    cabi.call("gg_unary", cabi.UNARY[fn], x.data_ptr(), y.data_ptr(), x.numel(), a, b, cabi.stream_ptr())
+    return y
+
+
+def _binary(fn, a, b, out_shape, sa, sb, alpha=0.0):
+    from gg import cabi
+    out = torch.empty(out_shape, device="cuda")
+    d = list(out_shape)
+    d = [1] * (4 - len(d)) + d
+    cabi.call("gg_binary", cabi.BINARY[fn], a.data_ptr(), b.data_ptr(), out.data_ptr(), cabi.int4(d), cabi.int4(sa), cabi.int4(sb),
+              alpha, cabi.stream_ptr())
+    return out
+
+
+def test_flat_chain_with_int_load_and_two_outputs():
+    """the image decode 2*((float(x)/255)-.5) + noise, keeping an intermediate (gmgan_inference_cifar10.py:341-342)"""
+    from gg import cabi
+    U, B = cabi.UNARY, cabi.BINARY
+    n = 64 * 3072 + 3
+    xi = torch.randint(0, 256, (n,), dtype=torch.int32, device="cuda")
+    noise = torch.rand(n, device="cuda")
+    xf = torch.empty(n, device="cuda")
+    cabi.call("gg_cast_i32_f32", xi.data_ptr(), xf.data_ptr(), n, 1.0, 0.0, cabi.stream_ptr())
+    t1 = _unary("divc", xf, 255.0)
+    t2 = _unary("affine", t1, 1.0, -0.5)
+    t3 = _unary("affine", t2, 2.0, 0.0)
+    t4 = _binary("add", t3, noise, (n,), [0, 0, 0, 1], [0, 0, 0, 1])
+    t5 = _unary("tanh", t4)
+    o3, o5 = torch.empty(n, device="cuda"), torch.empty(n, device="cuda")
+    p = _prog([1, 1, 1, n], [(xi, [0, 0, 0, 1], True), (noise, [0, 0, 0, 1], False)],
+              [(0, U["divc"], 2, 0, 0, 255.0, 0.0), (0, U["affine"], 2, 2, 0, 1.0, -0.5), (0, U["affine"], 0, 2, 0, 2.0, 0.0),
+               (1, B["add"], 2, 0, 1, 0.0, 0.0), (0, U["tanh"], 31, 2, 0, 0.0, 0.0)],
+              [(o3, 0), (o5, 31)], flat=True)
+    cabi.call("gg_ew_run", C.byref(p), cabi.stream_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(o3, t3) and torch.equal(o5, t5)
+
+
+def test_broadcast_strides_match_gg_binary():
+    """(x[B,1,D] - mu[1,K,D])^2 scaled by a per-row weight w[B,K,1]: the mixture-prior distance (gmgan_inference_cifar10.py:155-160)"""
+    from gg import cabi
+    U, Bn = cabi.UNARY, cabi.BINARY
+    Bt, K, D = 64, 30, 128
+    x, mu, w = torch.randn(Bt, D, device="cuda"), torch.randn(K, D, device="cuda"), torch.rand(Bt, K, device="cuda")
+    diff = _binary("sub", x, mu, (Bt, K, D), [0, D, 0, 1], [0, 0, D, 1])
+    sq = _unary("square", diff)
+    ref = _binary("mul", sq, w, (Bt, K, D), [0, K * D, D, 1], [0, K, 1, 0])
+    o_diff, o = torch.empty(Bt, K, D, device="cuda"), torch.empty(Bt, K, D, device="cuda")
+    p = _prog([1, Bt, K, D], [(x, [0, D, 0, 1], False), (mu, [0, 0, D, 1], False), (w, [0, K, 1, 0], False)],
+              [(1, Bn["sub"], 3, 0, 1, 0.0, 0.0), (0, U["square"], 4, 3, 0, 0.0, 0.0), (1, Bn["mul"], 0, 4, 2, 0.0, 0.0)],
+              [(o_diff, 3), (o, 0)], flat=False)
+    cabi.call("gg_ew_run", C.byref(p), cabi.stream_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(o_diff, diff) and torch.equal(o, ref)
+
+
+@pytest.mark.parametrize("rows,red", [(1, 64), (7, 130), (3, 1500), (1920, 128), (1, 1)])
+@pytest.mark.parametrize("fn", ["sum", "mean", "max"])
+def test_row_reduction_matches_gg_reduce(rows, red, fn):
+    """BCE(x, label) -> mean: tflib/objs/gan_inference.py:85-101; every thread-count tier of gg_reduce's row kernel"""
+    from gg import cabi
+    x = torch.randn(rows, red, device="cuda") * 3
+    e = _unary("bce", x, 1.0)
+    ref = torch.empty(rows, device="cuda")
+    cabi.call("gg_reduce", cabi.REDUCE[fn], e.data_ptr(), ref.data_ptr(), rows, red, 1, cabi.stream_ptr())
+    out, keep = torch.empty(rows, device="cuda"), torch.empty(rows, red, device="cuda")
+    p = _prog([1, 1, rows, red], [(x, [0, 0, red, 1], False)], [(0, cabi.UNARY["bce"], 5, 0, 0, 1.0, 0.0)], [(out, 5), (keep, 5)],
+              flat=True, reduce_op={"sum": 1, "mean": 2, "max": 3}[fn])
+    cabi.call("gg_ew_run", C.byref(p), cabi.stream_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref), (out[:4], ref[:4])
+    assert torch.equal(keep, e)
+
+
+def test_bad_programs_are_refused():
+    from gg import cabi
+    x = torch.zeros(8, device="cuda")
+    p = _prog([1, 1, 1, 8], [(x, [0, 0, 0, 1], False)], [(0, 99, 1, 0, 0, 0.0, 0.0)], [(x, 1)], flat=True)
+    with pytest.raises(cabi.GGError):
+        cabi.call("gg_ew_run", C.byref(p), cabi.stream_ptr())
+    p = _prog([1, 1, 1, 8], [(x, [0, 0, 0, 1], False)], [(0, 0, 40, 0, 0, 0.0, 0.0)], [(x, 1)], flat=True)
+    with pytest.raises(cabi.GGError):
+        cabi.call("gg_ew_run", C.byref(p), cabi.stream_ptr())
+
+
+# ---- whole plans --------------------------------------------------------------------------------------------------------
+def _builders():
+    import gmgan_inference_cifar10 as Cf
+    return {
+        "gmgan_cifar10": lambda: Cf.build_graph(BATCH_SIZE=16),
+        "gmgan_cifar10_reinforce": lambda: Cf.build_graph(BATCH_SIZE=8, MODE_K='REINFORCE'),
+        "gmgan_mnist": lambda: __import__("gmgan_inference_mnist").build_graph(BATCH_SIZE=10),
+        "gan_svhn_wali_gp": lambda: __import__("gan_inference_svhn").build_graph(MODE='wali-gp', BATCH_SIZE=8),
+        "gan_mnist_ali": lambda: __import__("gan_inference_mnist").build_graph(MODE='ali', BATCH_SIZE=10),
+        "gan_face_ali": lambda: __import__("gan_inference_face").build_graph(BATCH_SIZE=8),
+        "ssgan_moving_mnist": lambda: __import__("ssgan_inference_moving_mnist").build_graph(BATCH_SIZE=4, LEN=4),
+        "gmgan_svhn_local_epce": lambda: __import__("gmgan_inference_svhn").build_graph(MODE='local_epce', BATCH_SIZE=8),
+    }
+
+
+def _train(family, fuse, iters=3):
+    import tensorflow as tf
+    import tflib as lib
+    from gg.executor import RT
+    from gg.ops import toposort
+    os.environ["GG_FUSE_EW"] = "1" if fuse else "0"
+    try:
+        tf.reset_default_graph()
+        lib.delete_all_params()
+        np.random.seed(31)
+        g = _builders()[family]()
+        sess = tf.Session()
+        steps = ((g.gen_cost, g.gen_train_op), (g.disc_cost, g.disc_train_op))
+        leaves = {}
+        for cost, op in steps:
+            roots = [cost] + [d for d in op.deps if d is not None]
+            leaves[id(op)] = sorted((n for n in toposort(roots) if n.op in ("placeholder", "random")), key=lambda n: n.id)
+        rs = np.random.RandomState(3)
+        costs, n_fused = [], 0
+        for it in range(iters):
+            for cost, op in steps:
+                feeds = {}
+                for n in leaves[id(op)]:           # placeholders AND in-graph random draws: both builds see the same numbers
+                    if n.dtype.name == "int32":
+                        hi = n.inputs[0].size if n.op == "random" else (256 if n.size >= 1024 else 10)
+                        feeds[n] = rs.randint(0, hi, size=tuple(n.shape)).astype(np.int32)
+                    elif n.op == "random" and n.attrs["kind"] == "normal":
+                        feeds[n] = rs.randn(*n.shape).astype(np.float32)
+                    else:
+                        feeds[n] = rs.uniform(0.05, 0.95, size=tuple(n.shape)).astype(np.float32)
+                c, _ = sess.run([cost, op], feed_dict=feeds)
+                costs.append(np.asarray(c, dtype=np.float32).copy())
+        for plan in RT.plans.values():
+            n_fused += len(plan.ew_clusters)
+        params = {n: RT.get_param(p).copy() for n, p in sorted(lib._params.items())}
+        return costs, params, n_fused
+    finally:
+        os.environ.pop("GG_FUSE_EW", None)
+
+
+@pytest.mark.parametrize("family", ["gmgan_cifar10", "gmgan_cifar10_reinforce", "gmgan_mnist", "gan_svhn_wali_gp", "gan_mnist_ali",
+                                    "gan_face_ali", "ssgan_moving_mnist", "gmgan_svhn_local_epce"])
+def test_fused_plans_are_bit_identical(family):
+    c0, p0, f0 = _train(family, False)
+    c1, p1, f1 = _train(family, True)
+    assert f0 == 0 and f1 >= 4, (f0, f1)
+    assert all(np.isfinite(c).all() for c in c0)
+    for a, b in zip(c0, c1):
+        assert np.array_equal(a, b), (family, a, b)
+    assert set(p0) == set(p1)
+    for n in p0:
+        assert np.array_equal(p0[n], p1[n]), "%s: parameter %s differs between the fused and the unfused plan" % (family, n)
