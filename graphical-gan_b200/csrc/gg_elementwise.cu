@@ -529,6 +529,31 @@ extern "C" int gg_one_hot(const int32_t* idx, float* out, int n, int depth, void
   return check_launch("gg_one_hot");
 }
 
+// out[m, :] = table[idx[m], :] (zeros when idx[m] is outside [0, depth)): tf.matmul(tf.one_hot(idx, depth), table) without the
+// one-hot matrix and the GEMM — the mixture-prior mean lookup `tf.matmul(tf.one_hot(k, N_COMS), mu)` at the head of both
+// training steps (gmgan_inference_cifar10.py:138-141).  1*w + 0*(...) of the fp32 GEMM is w: identical values.
+__global__ void __launch_bounds__(256) gather_rows_kernel(const int32_t* __restrict__ idx, const float* __restrict__ table,
+                                                          const float* __restrict__ addend, float* __restrict__ out, int M, int N,
+                                                          int depth) {
+  GG_PDL_ENTRY();
+  long long total = (long long)M * N;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    int m = (int)(i / N), n = (int)(i - (long long)m * N);
+    int k = idx[m];
+    float v = (k >= 0 && k < depth) ? table[(long long)k * N + n] : 0.f;
+    out[i] = addend ? v + addend[i] : v;
+  }
+}
+extern "C" int gg_gather_rows(const int32_t* idx, const float* table, const float* addend, float* out, int M, int N, int depth,
+                              void* stream) {
+  if (M <= 0 || N <= 0) return GG_OK;
+  GG_REQUIRE(depth > 0, "gg_gather_rows");
+  GG_LAUNCH(gather_rows_kernel, ew_grid((long long)M * N, 1), 256, 0, as_stream(stream), idx, table, addend, out, M, N, depth);
+  return check_launch("gg_gather_rows");
+}
+
 // first maximal index, like tf.argmax
 __global__ void __launch_bounds__(128) argmax_kernel(const float* __restrict__ x, int32_t* __restrict__ idx, int R, int C) {
   GG_PDL_ENTRY();

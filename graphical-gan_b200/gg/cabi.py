@@ -74,6 +74,7 @@ SIGNATURES = {
     "gg_transpose_b2d": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p]),
     "gg_transpose_b2d_ex": (c_i, [c_p, c_p, c_i, c_i, c_i, c_ll, c_ll, c_p, c_i, c_f, c_p]),
     "gg_transpose4": (c_i, [c_p, c_p, C.POINTER(c_i), C.POINTER(c_i), c_p]),
+    "gg_gather_rows": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p]),
     "gg_ew_run": (c_i, [c_p, c_p]),
     "gg_ew_program_bytes": (c_i, []),
     "gg_copy2d": (c_i, [c_p, c_ll, c_p, c_ll, c_ll, c_ll, c_i, c_p]),

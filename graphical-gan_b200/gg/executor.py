@@ -272,16 +272,22 @@ class Plan(object):
         # to the node whose kernels produce the storage
         self.groups = []     # dicts: start, end, reads (owner ids), writes (owner id), barrier
         self.owner = {}
+        self.read_override = {}   # node id -> the tensors its launch really reads (when a peephole bypasses an input node)
+        self.self_grouped = set()
+        # the in-graph random ops key their Philox streams with a per-run counter.  It is advanced AFTER the last draw of a run
+        # (GG_TICK_FIRST=1: before the first one, as in round 1): at the head of the step the one-thread tick launch sat on the
+        # critical chain in front of the prior sample; at the tail it depends only on the draws and overlaps the backward pass
+        tick_first = os.environ.get("GG_TICK_FIRST", "0") == "1"
         if any(n.op == "random" and n.id not in self.fed for n in self.order):
             self.has_random = True
-            tick = rt.tick()
-            self.steps.append(lambda st, tick=tick: cabi.call("gg_rng_tick", tick.data_ptr(), st))
-            self.groups.append(dict(start=0, end=1, reads=set(), writes="tick", barrier=False, collective=False, node=None,
-                                    part=(0, 1), ordered=False))
+            if tick_first:
+                self._emit_tick(set())
         self._plan_inplace_concats()
         self._plan_grad_buckets(fetches)
         self._plan_actgrad_fusion(fetches)
+        self._plan_transpose_fusion(fetches)
         self._plan_ew_fusion(fetches)
+        self._resort()
         for node in self.order:
             cl = self.ew_cluster_of.get(node.id)
             if cl is not None:
@@ -291,6 +297,8 @@ class Plan(object):
             s0 = len(self.steps)
             self._emit(node)
             self._note_group(node, s0)
+        if self.has_random and not tick_first:
+            self._emit_tick(set(n.id for n in self.order if n.op == "random" and n.id not in self.fed))
         for f in fetches:
             if isinstance(f, Operation):
                 self._emit_operation(f)
@@ -300,10 +308,19 @@ class Plan(object):
         self.kernel_launches = 0   # libgg_b200 kernels per run (counted at capture / eager launch)
         self.runs = 0
 
+    def _emit_tick(self, reads):
+        tick = self.rt.tick()
+        s0 = len(self.steps)
+        self.steps.append(lambda st, tick=tick: cabi.call("gg_rng_tick", tick.data_ptr(), st))
+        self.groups.append(dict(start=s0, end=s0 + 1, reads=set(reads), writes="tick", barrier=False, collective=False, node=None,
+                                part=(0, 1), ordered=False))
+
     def _owners(self, t):
         return self.owner.get(t.id, frozenset([t.id]))
 
     def _note_group(self, node, s0):
+        if node.id in self.self_grouped:          # the launcher registered its own groups (a concat: one per piece)
+            return
         if len(self.steps) == s0:        # no kernels: a leaf, or a view (reshape, axis-0 slice, in-place concat, ...)
             if node.inputs and node.id not in self.fed:
                 own = frozenset()
@@ -315,7 +332,7 @@ class Plan(object):
             return
         self.owner[node.id] = frozenset([node.id])
         reads = set()
-        for i in node.inputs:
+        for i in self.read_override.get(node.id, node.inputs):
             reads |= self._owners(i)
         if node.id in getattr(self, "fuse_mask", {}):
             reads |= self._owners(self.fuse_mask[node.id][0])
@@ -549,17 +566,158 @@ class Plan(object):
             if n.op != "binary" or n.attrs.get("fn") not in ("leaky_grad", "relu_grad") or n.id in self.fed:
                 continue
             y, g = n.inputs
-            if g.op != "conv" or g.attrs["mode"] != "dgrad" or g.attrs["act"] is not None or len(g.inputs) != 2:
+            dense = g.op == "matmul" and not g.attrs["ta"] and g.attrs["tb"]       # dx = dy W^T of a Linear layer (linear.py:133)
+            if not dense and (g.op != "conv" or g.attrs["mode"] != "dgrad"):
+                continue
+            if g.attrs["act"] is not None or len(g.inputs) != 2:
                 continue
             if g.id in self.fed or y.id not in pos or uses.get(g.id, 0) != 1 or g.id in placed or n.id in placed:
                 continue
             if tuple(y.shape) != tuple(g.shape) or tuple(n.shape) != tuple(g.shape) or pos[y.id] > pos[g.id]:
+                continue
+            if dense:
+                # a dense layer is a 1x1 convolution on a 1x1 image (gg_gemm maps dy W^T onto the same dgrad launch)
+                M, N = g.shape
+                K = g.inputs[0].shape[1]
+                if os.environ.get("GG_FUSE_ACTGRAD_DENSE", "1") == "0" or cabi.lib.gg_conv2d_tc_supported(1, M, 1, 1, N, K, 1, 1, 1, 1) != 1:
+                    continue
+                self.fuse_mask[g.id] = (y, n.attrs["fn"][:-5], float(n.attrs["alpha"]))
+                self.fused_alias[n.id] = g.id
                 continue
             a = g.attrs
             if cabi.lib.gg_conv2d_tc_supported(1, a["B"], a["H"], a["W"], a["Ci"], a["Co"], a["k"], a["stride"], a["Ho"], a["Wo"]) != 1:
                 continue
             self.fuse_mask[g.id] = (y, n.attrs["fn"][:-5], float(n.attrs["alpha"]))
             self.fused_alias[n.id] = g.id
+
+    def _use_counts(self, fetches):
+        uses = {}
+        for n in self.order:
+            if n.id in self.fed:
+                continue
+            for i in n.inputs:
+                uses[i.id] = uses.get(i.id, 0) + 1
+        for f in fetches:
+            if isinstance(f, Tensor):
+                uses[f.id] = uses.get(f.id, 0) + 1
+            else:
+                for d in self._op_roots(f):
+                    uses[d.id] = uses.get(d.id, 0) + 1
+        for _gid, (y, _a, _al) in self.fuse_mask.items():
+            uses[y.id] = uses.get(y.id, 0) + 1
+        return uses
+
+    def _is_ancestor(self, anc, node):
+        """does `node` depend on `anc`? (walks inputs; fed nodes cut the walk like they cut the plan)"""
+        seen, stack = set(), [node]
+        while stack:
+            n = stack.pop()
+            if n is anc:
+                return True
+            if n.id in seen or n.id in self.fed:
+                continue
+            seen.add(n.id)
+            stack.extend(n.inputs)
+        return False
+
+    @staticmethod
+    def _b2d_form(node):
+        """(Bt, R, C) when the transpose is a batched 2-D one ([Bt, R, C] -> [Bt, C, R]), else None"""
+        shp, perm = list(node.inputs[0].shape), list(node.attrs["perm"])
+        nd = len(shp)
+        if nd >= 3 and perm[0] == 0 and perm[1:] == list(range(2, nd)) + [1]:
+            return shp[0], shp[1], prod(shp[2:])
+        if nd >= 3 and perm[0] == 0 and perm[1:] == [nd - 1] + list(range(1, nd - 1)):
+            return shp[0], prod(shp[1:nd - 1]), shp[nd - 1]
+        return None
+
+    def _plan_transpose_fusion(self, fetches):
+        """The NCHW flatten / un-flatten around the dense layers that follow or precede an image stack
+        (`tf.reshape(output, [-1, 4*4*4*DIM])` then `tf.concat([output, z_output], 1)`, gmgan_inference_cifar10.py:292-294) is a
+        batched 2-D transpose with a copy on one side: transpose -> copy into the concat's columns (forward); column slice ->
+        transpose -> activation gradient (backward: three dependent launches on the step's critical chain).  gg_transpose_b2d_ex
+        reads batches at a row stride (the slice disappears), writes them at a row stride (the copy disappears) and can
+        multiply by act'(y) on the way out (the activation-gradient launch disappears)."""
+        self.tr_fuse, self.virtual_slice, self.col_placed, self.gather_add = {}, set(), {}, {}
+        if os.environ.get("GG_FUSE_TRANSPOSE", "1") == "0":
+            return
+        uses = self._use_counts(fetches)
+        pos = {n.id: i for i, n in enumerate(self.order)}
+        consumers = {}
+        for n in self.order:
+            if n.id in self.fed:
+                continue
+            for i in n.inputs:
+                consumers.setdefault(i.id, []).append(n)
+        placed = set(self.placed) | set(self.placed_flat)
+        # one_hot(idx) @ table + x  ->  the row gather adds x on its way out (the add launch disappears from the head of the chain)
+        if os.environ.get("GG_GATHER", "1") != "0":
+            for m in self.order:
+                if m.op != "matmul" or m.id in self.fed or m.inputs[0].op != "one_hot" or m.inputs[0].id in self.fed or len(m.inputs) != 2 \
+                        or m.attrs["ta"] or m.attrs["tb"] or m.attrs["act"] is not None or uses.get(m.id, 0) != 1 or m.id in placed \
+                        or m.id in self.fuse_mask or len(consumers.get(m.id, ())) != 1:
+                    continue
+                c = consumers[m.id][0]
+                if c.op != "binary" or c.attrs["fn"] != "add" or c.id in self.fed or c.id in self.fused_alias or c.inputs[0] is not m:
+                    continue
+                other = c.inputs[1]
+                if tuple(other.shape) != tuple(m.shape) or tuple(c.shape) != tuple(m.shape) or other.dtype != float32 \
+                        or other.id not in pos or self._is_ancestor(m, other):
+                    continue
+                self.gather_add[m.id] = (c, other)
+                self.fused_alias[c.id] = m.id
+        for t in self.order:
+            if t.op != "transpose" or t.id in self.fed or t.dtype != float32 or t.id in placed:
+                continue
+            form = self._b2d_form(t)
+            if form is None:
+                continue
+            Bt, R, Cc = form
+            if Bt > 65535:
+                continue
+            info = dict(x_node=None, x_off=0, x_bs=R * Cc, y_concat=None, y_off=0, y_bs=R * Cc, mask=None)
+            # input side: a column slice of a [Bt, total] matrix behind single-use reshapes
+            x, chain = t.inputs[0], []
+            while x.op == "reshape" and x.id not in self.fed and uses.get(x.id, 0) == 1:
+                chain.append(x)
+                x = x.inputs[0]
+            if x.op == "slice" and x.id not in self.fed and uses.get(x.id, 0) == 1 and x.id not in placed and not self._slice_is_view(x):
+                src = x.inputs[0]
+                if len(src.shape) == 2 and x.attrs["axis"] == 1 and src.shape[0] == Bt and x.attrs["size"] == R * Cc and src.dtype == float32:
+                    info.update(x_node=src, x_off=x.attrs["start"], x_bs=src.shape[1], slice=x)
+            # output side: the only reader is an activation gradient, or (through single-use reshapes) a column concat
+            if uses.get(t.id, 0) == 1 and len(consumers.get(t.id, ())) == 1:
+                c = consumers[t.id][0]
+                if c.op == "binary" and c.attrs.get("fn") in ("leaky_grad", "relu_grad", "tanh_grad", "sigmoid_grad") and c.inputs[1] is t \
+                        and c.id not in self.fed and c.id not in placed and c.id not in self.fused_alias \
+                        and tuple(c.inputs[0].shape) == tuple(t.shape) and tuple(c.shape) == tuple(t.shape) \
+                        and c.inputs[0].id in pos and not self._is_ancestor(t, c.inputs[0]):
+                    info["mask"] = (c.inputs[0], c.attrs["fn"][:-5], float(c.attrs["alpha"]), c)
+                else:
+                    while c.op == "reshape" and c.id not in self.fed and uses.get(c.id, 0) == 1 and len(consumers.get(c.id, ())) == 1:
+                        c = consumers[c.id][0]
+                    if c.op == "concat" and c.id not in self.fed and c.dtype == float32 and len(c.shape) == 2 and c.attrs["axis"] == 1 \
+                            and c.shape[0] == Bt and c.id not in self.inplace_concat and c.id not in placed:
+                        off = 0
+                        for inp in c.inputs:
+                            own = inp
+                            while own.op == "reshape" and own is not t:
+                                own = own.inputs[0]
+                            if own is t and inp.size == Bt * R * Cc:
+                                info.update(y_concat=c, y_off=off, y_bs=c.shape[1])
+                                break
+                            off += inp.shape[1]
+            if info["x_node"] is None and info["y_concat"] is None and info["mask"] is None:
+                continue
+            self.tr_fuse[t.id] = info
+            if info["x_node"] is not None:
+                self.virtual_slice.add(info["slice"].id)
+            if info["mask"] is not None:
+                y, act, alpha, c = info["mask"]
+                self.fuse_mask[t.id] = (y, act, alpha)
+                self.fused_alias[c.id] = t.id
+            if info["y_concat"] is not None:
+                self.col_placed.setdefault(info["y_concat"].id, {})[info["y_off"]] = t.id
 
     # ---- element-wise cluster fusion (gg/fuse.py) ------------------------------------------------------------------------
     def _plan_ew_fusion(self, fetches):
@@ -578,16 +736,22 @@ class Plan(object):
                     ext[d.id] = ext.get(d.id, 0) + 1
         for gid, (y, _act, _alpha) in self.fuse_mask.items():
             ext[y.id] = ext.get(y.id, 0) + 1
+        for nid, (_c, other) in self.gather_add.items():
+            ext[other.id] = ext.get(other.id, 0) + 1
         excluded = set(self.fused_alias)
-        clusters = fuse.Planner(self.order, self.fed, ext, excluded).build()
-        if not clusters:
-            return
+        node_of = {n.id: n for n in self.order}
+        edges = [(y, node_of[gid]) for gid, (y, _a, _al) in self.fuse_mask.items() if gid in node_of]
+        edges += [(other, node_of[mid]) for mid, (_c, other) in self.gather_add.items() if mid in node_of]
+        clusters = fuse.Planner(self.order, self.fed, ext, excluded, edges).build()
         for cl in clusters:
             for n in cl.nodes():
                 assert n.id not in self.ew_cluster_of, "node %s in two element-wise clusters" % n
                 self.ew_cluster_of[n.id] = cl
         self.ew_clusters = clusters
-        # stable topological re-sort with every cluster as ONE unit (keyed by its last node's old position)
+
+    def _resort(self):
+        """stable topological re-sort of the plan with every element-wise cluster as ONE unit (keyed by its last node's old
+        position) and with the operands the peepholes added (activation masks, the addend of a gather) as dependencies"""
         pos = {n.id: i for i, n in enumerate(self.order)}
         unit_of, unit_nodes, unit_key = {}, {}, {}
         for n in self.order:
@@ -597,8 +761,12 @@ class Plan(object):
             unit_nodes.setdefault(u, []).append(n)
             unit_key[u] = max(unit_key.get(u, -1), pos[n.id])
         extra = {}
-        for gid, (y, _act, _alpha) in self.fuse_mask.items():     # the fused dgrad launch reads its activation mask y
+        for gid, (y, _act, _alpha) in self.fuse_mask.items():     # the fused dgrad / transpose launch reads its activation mask y
             extra.setdefault(gid, []).append(y)
+        for mid, (_c, other) in self.gather_add.items():
+            extra.setdefault(mid, []).append(other)
+        if not self.ew_clusters and not extra:
+            return
         deps, succ = {u: set() for u in unit_nodes}, {u: set() for u in unit_nodes}
         for n in self.order:
             if n.id in self.fed:
@@ -838,6 +1006,26 @@ class Plan(object):
 
     # layout
     def _emit_transpose(self, node):
+        info = self.tr_fuse.get(node.id)
+        if info is not None:
+            Bt, R, Cc = self._b2d_form(node)
+            if info["x_node"] is not None:
+                xp = self.buf[info["x_node"].id].data_ptr() + 4 * info["x_off"]
+            else:
+                xp = self._in(node, 0).data_ptr()
+            if info["y_concat"] is not None:
+                store = self._concat_storage(info["y_concat"].id)
+                self.buf[node.id] = store[info["y_off"]:]            # rows of the concat at a column offset: only the concat reads it
+                yp = store.data_ptr() + 4 * info["y_off"]
+            else:
+                yp = self._alloc(node).data_ptr()
+            mp, mcode, malpha = None, 0, 0.0
+            if info["mask"] is not None:
+                ynode, act, malpha, _c = info["mask"]
+                mp, mcode = self.buf[ynode.id].data_ptr(), cabi.ACT[act]
+            x_bs, y_bs = info["x_bs"], info["y_bs"]
+            self.steps.append(lambda st: cabi.call("gg_transpose_b2d_ex", xp, yp, Bt, R, Cc, x_bs, y_bs, mp, mcode, malpha, st))
+            return
         x, y = self._in(node, 0), self._alloc(node)
         shp, perm = list(node.inputs[0].shape), list(node.attrs["perm"])
         xp, yp = x.data_ptr(), y.data_ptr()
@@ -867,7 +1055,11 @@ class Plan(object):
         if node.id in self.inplace_concat:
             self.buf[node.id] = self._concat_storage(node.id)      # the pieces were written in place by their producers
             return
-        out = self._alloc(node)
+        pre = self.col_placed.get(node.id, {})       # pieces a strided transpose already wrote in place (_plan_transpose_fusion)
+        if pre:
+            out = self.buf[node.id] = self._concat_storage(node.id)
+        else:
+            out = self._alloc(node)
         axis = node.attrs["axis"]
         outer = prod(node.shape[:axis])
         inner = prod(node.shape[axis + 1:])
@@ -875,11 +1067,23 @@ class Plan(object):
         off = 0
         if node.dtype != float32:
             raise NotImplementedError("concat of int tensors")
+        # one scheduling group per piece: a copy waits for ITS piece only, and a reader of the concat waits for all of them —
+        # the copy of an early piece (the z branch of `tf.concat([output, z_output], 1)`) leaves the critical chain
+        keys = set()
         for i, inp in enumerate(node.inputs):
             cols = inp.shape[axis] * inner
-            sp, dp = self._in(node, i).data_ptr(), out.data_ptr() + off * 4
-            self.steps.append(lambda st, sp=sp, dp=dp, cols=cols: cabi.call("gg_copy2d", sp, cols, dp, dst_ld, outer, cols, 0, st))
+            if off in pre:
+                keys |= self._owners(inp)
+            else:
+                sp, dp = self._in(node, i).data_ptr(), out.data_ptr() + off * 4
+                s0 = len(self.steps)
+                self.steps.append(lambda st, sp=sp, dp=dp, cols=cols: cabi.call("gg_copy2d", sp, cols, dp, dst_ld, outer, cols, 0, st))
+                key = "%d#piece%d" % (node.id, i)
+                self._add_groups(s0, len(self.steps), set(self._owners(inp)), key, barrier=False, node=node)
+                keys.add(key)
             off += cols
+        self.owner[node.id] = frozenset(keys)
+        self.self_grouped.add(node.id)
 
     def _emit_slice(self, node):
         axis, start, size = node.attrs["axis"], node.attrs["start"], node.attrs["size"]
@@ -887,6 +1091,9 @@ class Plan(object):
         if self._slice_is_view(node) and node.id not in self.placed and os.environ.get("GG_INPLACE_CONCAT", "1") != "0":
             inner = prod(shp[axis + 1:])
             self.buf[node.id] = self._in(node, 0)[start * inner:(start + size) * inner]   # rows of a contiguous tensor: a view
+            return
+        if node.id in self.virtual_slice:           # read in place by the strided transpose that consumes it
+            self.buf[node.id] = None
             return
         x, out = self._in(node, 0), self._alloc(node)
         outer, inner = prod(shp[:axis]), prod(shp[axis + 1:])
@@ -917,6 +1124,21 @@ class Plan(object):
 
     # dense / conv / bn
     def _emit_matmul(self, node):
+        oh = node.inputs[0]
+        if oh.op == "one_hot" and oh.id not in self.fed and len(node.inputs) == 2 and not node.attrs["ta"] and not node.attrs["tb"] \
+                and node.attrs["act"] is None and node.id not in self.fuse_mask and os.environ.get("GG_GATHER", "1") != "0" \
+                and len(oh.shape) == 2:
+            # one_hot(idx) @ table is a row gather: no one-hot matrix, no GEMM, and the launch waits for idx, not for one_hot
+            idx, table = self.buf[oh.inputs[0].id], self._in(node, 1)
+            M, N = node.shape
+            extra = self.gather_add.get(node.id)           # (the add node, its other operand): mu_k + noise in the same launch
+            out = self._alloc(extra[0] if extra else node)
+            self.buf[node.id] = out
+            adp = self.buf[extra[1].id].data_ptr() if extra else None
+            ip, tp, op_, depth = idx.data_ptr(), table.data_ptr(), out.data_ptr(), oh.attrs["depth"]
+            self.steps.append(lambda st: cabi.call("gg_gather_rows", ip, tp, adp, op_, M, N, depth, st))
+            self.read_override[node.id] = [oh.inputs[0], node.inputs[1]] + ([extra[1]] if extra else [])
+            return
         a, b = self._in(node, 0), self._in(node, 1)
         bias = self._in(node, 2).data_ptr() if len(node.inputs) == 3 else None
         out = self._alloc(node)
@@ -927,6 +1149,12 @@ class Plan(object):
         self.keep.append(ws)
         act, alpha = cabi.ACT[node.attrs["act"]], node.attrs["alpha"]
         ap, bp, op_, wp, wn = a.data_ptr(), b.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel()
+        if node.id in self.fuse_mask:                     # dx = act'(y) * (dy W^T): the dense dgrad + activation gradient, one launch
+            y, mact, malpha = self.fuse_mask[node.id]
+            yp, mcode = self.buf[y.id].data_ptr(), cabi.ACT[mact]
+            self.steps.append(lambda st: cabi.call("gg_conv2d_dgrad_actgrad", ap, bp, op_, yp, mcode, malpha, M, 1, 1, N, K, 1, 1, 0, 0,
+                                                   1, 1, wp, wn, st))
+            return
         self.steps.append(lambda st: cabi.call("gg_gemm", ap, bp, bias, op_, M, N, K, ta, tb, act, alpha, wp, wn, st))
 
     def _emit_conv(self, node):

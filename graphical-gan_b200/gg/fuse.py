@@ -45,7 +45,7 @@ class Planner(object):
     """clusters for one plan: `order` (topological), ids of fed nodes, nodes that must own a buffer for reasons the graph
     does not show (fetches, optimiser inputs, activation masks of fused dgrad launches), nodes computed elsewhere"""
 
-    def __init__(self, order, fed, external_use, excluded):
+    def __init__(self, order, fed, external_use, excluded, extra_edges=()):
         self.order = order
         self.fed = fed
         self.pos = {n.id: i for i, n in enumerate(order)}
@@ -58,6 +58,9 @@ class Planner(object):
             for i in n.inputs:
                 if i.id in self.consumers:
                     self.consumers[i.id].append(n)
+        for src, dst in extra_edges:     # operands a peephole added to a launch (activation masks, gather addends): real reads
+            if src.id in self.consumers and dst.id in self.pos:
+                self.consumers[src.id].append(dst)
         self.ext = external_use          # id -> count
         self.parent = {}
         self.members_of = {}

@@ -11,6 +11,8 @@ Build-time rewrites (all value-preserving):
   * an activation applied to a conv / matmul / batch-norm node is folded into that kernel's epilogue
     (the un-fused original stays in the graph and is pruned if nothing else reads it).
 """
+import os
+
 import numpy as np
 
 from .graph import Tensor, Operation, float32, int32, as_dtype, prod
@@ -460,6 +462,11 @@ def matmul(a, b, transpose_a=False, transpose_b=False, bias=None):
     N = b.shape[0] if transpose_b else b.shape[1]
     if Ka != Kb:
         raise ValueError("matmul inner dimensions differ: %s x %s" % (tuple(a.shape), tuple(b.shape)))
+    if Ka == 1 and bias is None and os.environ.get("GG_RANK1_MUL", "1") != "0":
+        # a rank-1 product is a broadcast multiply: out[m, n] = a[m] * b[n] — the input gradient of a 1-output dense layer
+        # (`Discriminator.Output`, gmgan_inference_cifar10.py:300, backward: dy [B,1] x W^T [1,512]).  fmaf(a, b, 0) of the GEMM
+        # kernels and a * b round identically; as an element-wise node it fuses with the activation gradient that follows it
+        return binary("mul", reshape(a, (M, 1)), reshape(b, (1, N)))
     inputs = (a, b) if bias is None else (a, b, bias)
     return Tensor("matmul", inputs, {"ta": bool(transpose_a), "tb": bool(transpose_b), "act": None, "alpha": 0.0}, (M, N), float32)
 

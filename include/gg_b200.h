@@ -220,6 +220,10 @@ int gg_copy2d(const float* src, long long src_ld, float* dst, long long dst_ld,
 int gg_fill(float* x, long long n, float v, void* stream);
 int gg_one_hot(const int32_t* idx, float* out, int n, int depth, void* stream);
 int gg_argmax(const float* x, int32_t* idx, int R, int C, void* stream);
+/* out[m,:] = table[idx[m],:] (zeros for idx[m] outside [0,depth)) + addend[m,:] (addend may be NULL):
+ * tf.matmul(tf.one_hot(idx, depth), table) + noise — the mixture-prior sample `mu_k + eps` of gmgan_inference_cifar10.py:138-141 —
+ * as a row gather */
+int gg_gather_rows(const int32_t* idx, const float* table, const float* addend, float* out, int M, int N, int depth, void* stream);
 /* y = a * float(x) + b ; x int32 (tf.cast of the int32 image placeholder, gmgan_inference_cifar10.py:341-342) */
 int gg_cast_i32_f32(const int32_t* x, float* y, long long n, float a, float b, void* stream);
 int gg_cast_u8_f32(const uint8_t* x, float* y, long long n, float a, float b, void* stream);

@@ -126,6 +126,74 @@ def test_bad_programs_are_refused():
         cabi.call("gg_ew_run", C.byref(p), cabi.stream_ptr())
 
 
+@pytest.mark.parametrize("Bt,R,Cc", [(128, 256, 16), (128, 16, 256), (5, 33, 7), (64, 3, 1024)])
+def test_strided_transpose_with_activation_gradient(Bt, R, Cc):
+    """gg_transpose_b2d_ex: batches read from / written into the columns of a wider matrix, optional act'(y) on the way out"""
+    from gg import cabi
+    wide = torch.randn(Bt, R * Cc + 72, device="cuda")
+    x = wide[:, 40:40 + R * Cc]
+    ref = x.reshape(Bt, R, Cc).transpose(1, 2).contiguous()
+    y_fwd = torch.randn(Bt, Cc, R, device="cuda")
+    for act, alpha in ((None, 0.0), ("leaky", 0.2), ("relu", 0.0), ("tanh", 0.0)):
+        out = torch.full((Bt, Cc * R + 24), 7.0, device="cuda")
+        mp = y_fwd.data_ptr() if act else None
+        cabi.call("gg_transpose_b2d_ex", wide.data_ptr() + 4 * 40, out.data_ptr() + 4 * 8, Bt, R, Cc, wide.shape[1], out.shape[1], mp,
+                  cabi.ACT[act], alpha, cabi.stream_ptr())
+        torch.cuda.synchronize()
+        want = ref
+        if act == "leaky":
+            want = torch.where(y_fwd > 0, ref, alpha * ref)
+        elif act == "relu":
+            want = torch.where(y_fwd > 0, ref, torch.zeros_like(ref))
+        elif act == "tanh":
+            want = (1.0 - y_fwd * y_fwd) * ref
+        got = out[:, 8:8 + R * Cc].reshape(Bt, Cc, R)
+        if act == "tanh":
+            assert (got - want).abs().max() <= 1e-6 * want.abs().max()
+        else:
+            assert torch.equal(got, want), act
+        assert bool((out[:, :8] == 7.0).all()) and bool((out[:, 8 + R * Cc:] == 7.0).all()), "wrote outside its columns"
+
+
+def test_gather_rows_matches_one_hot_matmul():
+    from gg import cabi
+    from gpu_util import gemm
+    M, N, depth = 64, 128, 30
+    idx = torch.randint(0, depth, (M,), dtype=torch.int32, device="cuda")
+    idx[3] = -1
+    idx[5] = depth
+    table, noise = torch.randn(depth, N, device="cuda"), torch.randn(M, N, device="cuda")
+    oh = torch.empty(M, depth, device="cuda")
+    cabi.call("gg_one_hot", idx.data_ptr(), oh.data_ptr(), M, depth, cabi.stream_ptr())
+    ref = gemm(oh, table, None, M, N, depth)
+    out, out2 = torch.empty(M, N, device="cuda"), torch.empty(M, N, device="cuda")
+    cabi.call("gg_gather_rows", idx.data_ptr(), table.data_ptr(), None, out.data_ptr(), M, N, depth, cabi.stream_ptr())
+    cabi.call("gg_gather_rows", idx.data_ptr(), table.data_ptr(), noise.data_ptr(), out2.data_ptr(), M, N, depth, cabi.stream_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref) and bool((out[3] == 0).all()) and bool((out[5] == 0).all())
+    assert torch.equal(out2, ref + noise)
+
+
+def test_dense_dgrad_with_fused_activation_gradient():
+    """dx = leaky'(y) * (dy W^T) for the Linear layers of the latent discriminators (gmgan_inference_cifar10.py:262-272, backward):
+    gg_conv2d_dgrad_actgrad on the 1x1 geometry gg_gemm itself uses == gg_gemm followed by gg_binary(leaky_grad)"""
+    from gg import cabi
+    from gpu_util import gemm, ws
+    for M, N, K in ((128, 512, 512), (128, 4608, 512), (64, 128, 4096)):
+        dy, W, y = torch.randn(M, K, device="cuda"), torch.randn(N, K, device="cuda") * 0.05, torch.randn(M, N, device="cuda")
+        if cabi.lib.gg_conv2d_tc_supported(1, M, 1, 1, N, K, 1, 1, 1, 1) != 1:
+            continue
+        two = gemm(dy, W, None, M, N, K, ta=0, tb=1)
+        assert cabi.lib.gg_last_backend() == 1
+        two = torch.where(y > 0, two, 0.2 * two)
+        one = torch.empty(M, N, device="cuda")
+        wsp = ws(cabi.lib.gg_gemm_workspace(M, N, K))
+        cabi.call("gg_conv2d_dgrad_actgrad", dy.data_ptr(), W.data_ptr(), one.data_ptr(), y.data_ptr(), cabi.ACT["leaky"], 0.2,
+                  M, 1, 1, N, K, 1, 1, 0, 0, 1, 1, wsp.data_ptr(), wsp.numel(), cabi.stream_ptr())
+        torch.cuda.synchronize()
+        assert torch.equal(one, two), (M, N, K)
+
+
 # ---- whole plans --------------------------------------------------------------------------------------------------------
 def _builders():
     import gmgan_inference_cifar10 as Cf
@@ -146,7 +214,9 @@ def _train(family, fuse, iters=3):
     import tflib as lib
     from gg.executor import RT
     from gg.ops import toposort
-    os.environ["GG_FUSE_EW"] = "1" if fuse else "0"
+    knobs = ("GG_FUSE_EW", "GG_FUSE_TRANSPOSE", "GG_FUSE_ACTGRAD_DENSE", "GG_RANK1_MUL", "GG_GATHER")
+    for k in knobs:                                  # every launch-list fusion of round 2 on, or the one-launch-per-node plan
+        os.environ[k] = "1" if fuse else "0"
     try:
         tf.reset_default_graph()
         lib.delete_all_params()
@@ -174,11 +244,12 @@ def _train(family, fuse, iters=3):
                 c, _ = sess.run([cost, op], feed_dict=feeds)
                 costs.append(np.asarray(c, dtype=np.float32).copy())
         for plan in RT.plans.values():
-            n_fused += len(plan.ew_clusters)
+            n_fused += len(plan.ew_clusters) + len(plan.tr_fuse) + len(plan.gather_add)
         params = {n: RT.get_param(p).copy() for n, p in sorted(lib._params.items())}
         return costs, params, n_fused
     finally:
-        os.environ.pop("GG_FUSE_EW", None)
+        for k in knobs:
+            os.environ.pop(k, None)
 
 
 @pytest.mark.parametrize("family", ["gmgan_cifar10", "gmgan_cifar10_reinforce", "gmgan_mnist", "gan_svhn_wali_gp", "gan_mnist_ali",
