@@ -1576,6 +1576,28 @@ class Plan(object):
         makespan = max([est[gi] + bottom[gi] for gi in idxs] or [0.0])
         slack_min = float(os.environ.get("GG_PRIO_SLACK_US", "40"))
         low_cls = {gi: (makespan - (est[gi] + bottom[gi]) > slack_min) for gi in idxs}
+        # ... but never a group that a HIGH-class group waits for: the CUPTI timeline of the G step (profiles/timeline_gen_r2.txt)
+        # has a 40 us hole with NO kernel in flight right after fake_x is complete — the image decode / dequantisation chain the
+        # discriminator's first layer also needs had been ready since t = 10 us, but sat on a low-priority stream (its modelled
+        # slack is 75 us) and low-priority queues are not served while a high-priority queue holds pending work, even work that
+        # is itself blocked on them: a priority inversion.  Low class = slack AND only the update (or other low groups) behind it.
+        # Measured (gpurun_out/quick_s27.txt, quick_s28.txt; ms per iteration, off / on / cheap-glue-only): face 1.844 / 1.795 / 1.826,
+        # SSGAN 6.31 / 5.69 / 5.86 — but gmgan-CIFAR 0.797 / 0.848 / 0.814: at batch 64 no launch fills the GPU and the step is
+        # its latency chain, which any early co-runner stretches.  "auto" turns the rule on for plans whose tensor-core launches are
+        # multi-wave (more output tiles than SMs), i.e. throughput-bound steps.
+        tail_mode = os.environ.get("GG_PRIO_TAIL", "auto")
+        if tail_mode == "auto":
+            convs = [self.groups[gi]["node"] for gi in idxs if self.groups[gi].get("node") is not None and self.groups[gi]["node"].op == "conv"]
+            big = sum(1 for n in convs if self._conv_tiles(n) > 148)
+            tail_mode = "1" if convs and big * 4 >= len(convs) else "0"
+        self.prio_tail_mode = tail_mode
+        if tail_mode in ("1", "2"):
+            for gi in reversed(idxs):
+                if low_cls[gi] and any(not self.groups[c]["barrier"] and not low_cls[c] for c in succ[gi]):
+                    if tail_mode == "2" and cost[gi] >= 8.0:
+                        continue                      # mode 2: only the cheap glue is pulled up, heavy launches keep their class
+                    low_cls[gi] = False
+        self.low_class = low_cls
         while ready:
             gi = heapq.heappop(ready)[-1]
             best = None
@@ -1613,6 +1635,16 @@ class Plan(object):
         assert len(order) == len(idxs)
         self.sched_estimate_us = max(finish.values()) if finish else 0.0
         return order, assign, waits, need_event
+
+    @staticmethod
+    def _conv_tiles(node):
+        """128 x 128 output tiles of a conv node's implicit GEMM (fwd / dgrad: pixels x channels; wgrad: filter rows x channels)"""
+        a = node.attrs
+        if a["mode"] == "wgrad":
+            return -(-a["k"] * a["k"] * a["Ci"] // 128) * -(-a["Co"] // 128)
+        if a["mode"] == "fwd":
+            return -(-a["B"] * a["Ho"] * a["Wo"] // 128) * -(-a["Co"] // 128)
+        return -(-a["B"] * a["H"] * a["W"] // 128) * -(-a["Ci"] // 128)
 
     @staticmethod
     def _stream_priorities(n_streams, has_comm):

@@ -50,7 +50,10 @@ def build(config, batch):
     else:
         import ssgan_inference_moving_mnist as S
         g = S.build_graph(BATCH_SIZE=batch or 32)
-        feeds = [g.real_x_int] if hasattr(g, "real_x_int") else [g.real_x]
+        feeds = [getattr(g, n) for n in ("real_x_int", "real_x", "real_x_unit") if hasattr(g, n)][:1]
+        from gg.ops import toposort
+        roots = [g.gen_cost, g.disc_cost] + [d for op in (g.gen_train_op, g.disc_train_op) for d in op.deps if d is not None]
+        feeds = [n for n in toposort(roots) if n.op == "placeholder"]
     return g, feeds
 
 
