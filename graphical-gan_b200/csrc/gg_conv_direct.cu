@@ -21,6 +21,8 @@ size_t conv_tc_workspace(int mode, int B, int H, int W, int Ci, int Co, int k, i
 void conv_tc_set_debug(void* p);
 void conv_tc_set_max_ctas(int n);
 void conv_tc_set_pending_mask(const float* y, int act, float alpha);
+void conv_tc_set_pending_stats(float* stats, int ld);
+int conv_tc_stats_tiles(int mode, int B, int H, int W, int Ci, int Co, int k, int stride, int pad_t, int pad_l, int Ho, int Wo);
 // gg_conv_small.cu: one-launch shared-memory kernels for the 1-/3-channel first conv and last deconv of every network
 int conv_small_fwd(const float* x, const float* w, const float* bias, float* y, int B, int H, int W, int Ci, int Co, int k,
                    int stride, int pad_t, int pad_l, int Ho, int Wo, int act, float alpha, cudaStream_t st, bool* handled);
@@ -465,6 +467,37 @@ extern "C" size_t gg_conv2d_wgrad_workspace(int B, int H, int W, int Ci, int Co,
   size_t small = conv_small_wgrad_workspace(B, H, W, Ci, Co, k, stride, Ho, Wo);
   if (small > tc) tc = small;
   return direct > tc ? direct : tc;
+}
+
+// conv / deconv / dense launch that also writes the batch-norm statistics of its output (include/gg_b200.h)
+extern "C" int gg_conv2d_stats_tiles(int mode, int B, int H, int W, int Ci, int Co, int k, int stride, int pad_t, int pad_l, int Ho,
+                                     int Wo) {
+  if (g_conv_backend == 1) return 0;
+  return conv_tc_stats_tiles(mode, B, H, W, Ci, Co, k, stride, pad_t, pad_l, Ho, Wo);
+}
+
+extern "C" int gg_conv2d_bnstats(int mode, const float* a, const float* w, const float* bias, float* out, float* stats, int B, int H,
+                                 int W, int Ci, int Co, int k, int stride, int pad_t, int pad_l, int Ho, int Wo, int act, float alpha,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  ConvP p{B, H, W, Ci, Co, k, stride, pad_t, pad_l, Ho, Wo};
+  int rc = check_geom(p, "gg_conv2d_bnstats");
+  if (rc) return rc;
+  if (mode != 0 && mode != 1) return fail(GG_ERR_BAD_ARG, "gg_conv2d_bnstats: mode must be 0 (fwd) or 1 (dgrad)%s");
+  if (stats == nullptr) return fail(GG_ERR_BAD_ARG, "gg_conv2d_bnstats: stats is required%s");
+  if (g_conv_backend == 1) return fail(GG_ERR_UNSUPPORTED, "gg_conv2d_bnstats: tensor-core path disabled (backend 1)%s");
+  bool handled = false;
+  conv_tc_set_pending_stats(stats, mode == 0 ? Co : Ci);
+  if (mode == 0)
+    rc = conv_tc_fwd(a, w, bias, out, B, H, W, Ci, Co, k, stride, pad_t, pad_l, Ho, Wo, act, alpha, workspace, workspace_bytes,
+                     as_stream(stream), &handled);
+  else
+    rc = conv_tc_dgrad(a, w, bias, out, B, H, W, Ci, Co, k, stride, pad_t, pad_l, Ho, Wo, act, alpha, workspace, workspace_bytes,
+                       as_stream(stream), &handled);
+  conv_tc_set_pending_stats(nullptr, 0);
+  if (rc) return rc;
+  if (!handled) return fail(GG_ERR_UNSUPPORTED, "gg_conv2d_bnstats: shape not supported by the tcgen05 path%s");
+  g_last_backend = 1;
+  return GG_OK;
 }
 
 namespace gg { void conv_tc_set_stage_cap(int n); void conv_tc_last_info(int* out8); }

@@ -68,6 +68,9 @@ struct TcParams {
   const float* mask;          // optional: forward activation y at the OUTPUT positions (same layout as out); the stored value
   int mask_act;               // becomes act'(y) * value — the activation gradient that follows a dgrad, fused into its write-out
   float mask_alpha;
+  float* stats;               // optional: per-m-tile column sums / sums of squares of the stored values, [m-tile][2][stats_ld]:
+  int stats_ld;               // the batch-norm statistics of the layer that follows (tflib/ops/batchnorm.py:29-30), taken in the
+                              // epilogue of the kernel that produces its input; folded by gg_bn_apply
   long long* dbg;             // optional timeline of CTA (0,0): see gg_debug_set_buffer
   int out_rows;               // wgrad: rows of the [taps*Ci, Co] result that exist in memory (im2col-padded K)
 };
@@ -597,6 +600,45 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (p.dbg && et == 0) p.dbg[203] = gtime();
     }
+    if (MODE != 2 && p.stats != nullptr) {
+      // ---- batch-norm statistics of the tile just written (fused producer of tf.nn.fused_batch_norm's moments) -----------
+      // the staging tile still holds the final values (bias and activation applied).  Thread (my_c, my_r) sums its float4
+      // column over rows my_r, my_r + rpp, ... (fixed order), the rpp partials of a column meet in shared memory (the staging
+      // tile itself, once everybody has left it) and thread my_c writes [sum ; sum of squares] of this m-tile's rows to
+      // stats[m-tile][0 / 1][channel]: every (m-tile, channel) is written by exactly one thread of the launch — no atomics,
+      // bit-reproducible; rows outside the image / batch (s_row_off < 0) do not count.
+      const int ncol = cend - cbeg;
+      const int rpp = ncol > 0 ? kEpiThreads / ncol : 0;
+      const int my_c = ncol > 0 ? et % ncol : 0, my_r = ncol > 0 ? et / ncol : 0;
+      float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), q4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (my_r < rpp) {
+        const uint32_t sp_ = stage_a + (uint32_t)my_c * 16u;
+        for (int r = my_r; r < 128; r += rpp) {
+          if (s_row_off[r] < 0) continue;
+          const float4 v = lds128(sp_ + (uint32_t)(r * ld) * 4u);
+          s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
+          q4.x = fmaf(v.x, v.x, q4.x); q4.y = fmaf(v.y, v.y, q4.y); q4.z = fmaf(v.z, v.z, q4.z); q4.w = fmaf(v.w, v.w, q4.w);
+        }
+      }
+      epi_bar();                                  // nobody reads the staging tile any more
+      if (my_r < rpp) {
+        sts128(stage_a + (uint32_t)et * 32u, s4);
+        sts128(stage_a + (uint32_t)et * 32u + 16u, q4);
+      }
+      epi_bar();
+      if (et < ncol) {                            // my_r == 0, my_c == et
+        float4 S = make_float4(0.f, 0.f, 0.f, 0.f), Q = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k2 = 0; k2 < rpp; ++k2) {
+          const float4 a = lds128(stage_a + (uint32_t)(et + k2 * ncol) * 32u);
+          const float4 b = lds128(stage_a + (uint32_t)(et + k2 * ncol) * 32u + 16u);
+          S.x += a.x; S.y += a.y; S.z += a.z; S.w += a.w;
+          Q.x += b.x; Q.y += b.y; Q.z += b.z; Q.w += b.w;
+        }
+        float* dst = p.stats + ((size_t)(tile / p.n_tiles) * 2) * (size_t)p.stats_ld + (size_t)n0 + (size_t)(cbeg + et) * 4;
+        *reinterpret_cast<float4*>(dst) = S;
+        *reinterpret_cast<float4*>(dst + p.stats_ld) = Q;
+      }
+    }
   }
   if (threadIdx.x == 64) GG_DBG(131);
 #ifdef GG_TIMELINE
@@ -747,7 +789,8 @@ size_t smem_layout(TcParams& p) {
   }
   const int nc = p.n_tile / 4;
   p.ncols_max = (nc + p.splits - 1) / p.splits;
-  const size_t staging = (size_t)128 * (p.ncols_max * 4 + 4) * 4;
+  size_t staging = (size_t)128 * (p.ncols_max * 4 + 4) * 4;
+  if (staging < 8192) staging = 8192;             // the batch-norm statistics fold parks 256 x 32 B in the staging tile
   if (ring < tile + staging) ring = tile + staging;
   ring = (ring + 1023) & ~size_t(1023);
   p.stage_off = (int)tile;
@@ -892,12 +935,29 @@ int act_map(CUtensorMap* tm, const float* x, int B, int H, int W, int C, int wt,
 
 }  // namespace
 
+namespace {
+struct PendingStats { float* stats; int ld; };
+thread_local PendingStats g_pending_stats = {nullptr, 0};
+}  // namespace
+// the next conv_tc_fwd / conv_tc_dgrad of this thread also writes the per-m-tile batch-norm statistics of its output
+void conv_tc_set_pending_stats(float* stats, int ld) { g_pending_stats = PendingStats{stats, ld}; }
+// m-tiles (rows of the statistics buffer) of a fwd / dgrad launch; 0 when the shape does not run on the tensor-core path
+int conv_tc_stats_tiles(int mode, int B, int H, int W, int Ci, int Co, int k, int stride, int pad_t, int pad_l, int Ho, int Wo) {
+  if (mode != 0 && mode != 1) return 0;
+  TcPlan pl = make_plan(mode, B, H, W, Ci, Co, k, stride, pad_t, pad_l, Ho, Wo);
+  if (!pl.ok) return 0;
+  return pl.grid_x / pl.p.n_tiles;
+}
+
 int conv_tc_fwd(const float* x, const float* w, const float* bias, float* y, int B, int H, int W, int Ci, int Co, int k,
                 int stride, int pad_t, int pad_l, int Ho, int Wo, int act, float alpha, void* ws, size_t ws_bytes,
                 cudaStream_t st, bool* handled, int filt_rows) {
   *handled = false;
+  const PendingStats pst = g_pending_stats;
+  g_pending_stats = PendingStats{nullptr, 0};
   TcPlan pl = make_plan(0, B, H, W, Ci, Co, k, stride, pad_t, pad_l, Ho, Wo);
   if (!pl.ok) return GG_OK;
+  pl.p.stats = pst.stats; pl.p.stats_ld = pst.ld;
   CUtensorMap tmA, tmB;
   int rc = act_map(&tmA, x, B, H, W, Ci, pl.p.wt, pl.p.ht, pl.p.bt, stride, 1);
   if (rc) return rc;
@@ -923,9 +983,12 @@ int conv_tc_dgrad(const float* dy, const float* w, const float* bias, float* dx,
   *handled = false;
   const PendingMask mask = g_pending_mask;
   g_pending_mask = PendingMask{nullptr, 0, 0.f};
+  const PendingStats pst = g_pending_stats;
+  g_pending_stats = PendingStats{nullptr, 0};
   TcPlan pl = make_plan(1, B, H, W, Ci, Co, k, stride, pad_t, pad_l, Ho, Wo);
   if (!pl.ok) return GG_OK;
   pl.p.mask = mask.y; pl.p.mask_act = mask.act; pl.p.mask_alpha = mask.alpha;
+  pl.p.stats = pst.stats; pl.p.stats_ld = pst.ld;
   CUtensorMap tmA, tmB;
   int rc = act_map(&tmA, dy, B, Ho, Wo, Co, pl.p.wt, pl.p.ht, pl.p.bt, 1, 1);
   if (rc) return rc;

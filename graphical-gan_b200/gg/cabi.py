@@ -51,6 +51,8 @@ SIGNATURES = {
     "gg_conv2d_wgrad": (c_i, [c_p, c_p, c_p] + [c_i] * 11 + [c_p, c_sz, c_p]),
     "gg_conv2d_dgrad_actgrad": (c_i, [c_p, c_p, c_p, c_p, c_i, c_f] + [c_i] * 11 + [c_p, c_sz, c_p]),
     "gg_conv2d_tc_supported": (c_i, [c_i] * 10),
+    "gg_conv2d_stats_tiles": (c_i, [c_i] * 12),
+    "gg_conv2d_bnstats": (c_i, [c_i, c_p, c_p, c_p, c_p, c_p] + [c_i] * 11 + [c_i, c_f, c_p, c_sz, c_p]),
     "gg_conv2d_wgrad_workspace": (c_sz, [c_i] * 9),
     "gg_conv2d_workspace": (c_sz, [c_i] * 10),
     "gg_gemm": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p, c_sz, c_p]),

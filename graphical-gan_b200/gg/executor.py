@@ -286,6 +286,7 @@ class Plan(object):
         self._plan_grad_buckets(fetches)
         self._plan_actgrad_fusion(fetches)
         self._plan_transpose_fusion(fetches)
+        self._plan_bn_stats()
         self._plan_ew_fusion(fetches)
         self._resort()
         for node in self.order:
@@ -589,6 +590,52 @@ class Plan(object):
                 continue
             self.fuse_mask[g.id] = (y, n.attrs["fn"][:-5], float(n.attrs["alpha"]))
             self.fused_alias[n.id] = g.id
+
+    @staticmethod
+    def _tc_geometry(node):
+        """(mode, geometry tuple) of a conv / dense node as the tensor-core kernels see it, or None (wgrad-type products)"""
+        if node.op == "conv":
+            g = node.attrs
+            if g["mode"] not in ("fwd", "dgrad"):
+                return None
+            return (0 if g["mode"] == "fwd" else 1,
+                    (g["B"], g["H"], g["W"], g["Ci"], g["Co"], g["k"], g["stride"], g["pad_t"], g["pad_l"], g["Ho"], g["Wo"]))
+        if node.op == "matmul" and not node.attrs["ta"]:
+            M, N = node.shape
+            K = node.inputs[0].shape[1]
+            # a dense layer is a 1x1 convolution on a 1x1 image: y = x W is its fwd (Ci = K, Co = N), dx = dy W^T its dgrad
+            return (1, (M, 1, 1, N, K, 1, 1, 0, 0, 1, 1)) if node.attrs["tb"] else (0, (M, 1, 1, K, N, 1, 1, 0, 0, 1, 1))
+        return None
+
+    def _plan_bn_stats(self):
+        """`Batchnorm` always normalises the output of a Conv2D / Deconv2D / Linear (tflib/ops/batchnorm.py:29-30 after
+        conv2d.py:106-120).  When that producer runs on the tensor-core kernels its epilogue also writes the per-m-tile column
+        sums and sums of squares (gg_conv2d_bnstats), and the batch norm becomes ONE element-wise pass (gg_bn_apply folds the
+        tile rows in double precision and normalises): the statistics pass over the activation — and the cluster rendezvous of
+        the one-launch batch-norm kernel — disappear from the step's critical chain."""
+        self.bn_stats, self.bn_from_stats = {}, {}
+        if os.environ.get("GG_BN_CONV_STATS", "1") == "0" or (ggdist.world_size() > 1 and self.rt.sync_bn):
+            return
+        placed = set(self.placed) | set(self.placed_flat)
+        for n in self.order:
+            if n.op != "bn" or n.id in self.fed:
+                continue
+            x = n.inputs[0]
+            prod_node = x
+            if x.op == "reshape" and x.id not in self.fed and x.shape[-1] == x.inputs[0].shape[-1]:
+                prod_node = x.inputs[0]
+            if prod_node.op not in ("conv", "matmul") or prod_node.id in self.fed or prod_node.id in self.fuse_mask \
+                    or prod_node.id in self.bn_stats or prod_node.id in placed or prod_node.dtype != float32:
+                continue
+            geo = self._tc_geometry(prod_node)
+            Cc = n.shape[-1]
+            if geo is None or prod_node.shape[-1] != Cc or prod_node.size != n.size:
+                continue
+            tiles = cabi.lib.gg_conv2d_stats_tiles(geo[0], *geo[1])
+            if tiles <= 0:
+                continue
+            self.bn_stats[prod_node.id] = dict(mode=geo[0], geo=geo[1], tiles=tiles, C=Cc, buf=None)
+            self.bn_from_stats[n.id] = prod_node.id
 
     def _use_counts(self, fetches):
         uses = {}
@@ -1149,6 +1196,9 @@ class Plan(object):
         self.keep.append(ws)
         act, alpha = cabi.ACT[node.attrs["act"]], node.attrs["alpha"]
         ap, bp, op_, wp, wn = a.data_ptr(), b.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel()
+        if node.id in self.bn_stats:
+            self._emit_bnstats_launch(node, ap, bp, bias, op_, act, alpha, wp, wn)
+            return
         if node.id in self.fuse_mask:                     # dx = act'(y) * (dy W^T): the dense dgrad + activation gradient, one launch
             y, mact, malpha = self.fuse_mask[node.id]
             yp, mcode = self.buf[y.id].data_ptr(), cabi.ACT[mact]
@@ -1182,8 +1232,17 @@ class Plan(object):
             yp, mcode = self.buf[y.id].data_ptr(), cabi.ACT[mact]
             self.steps.append(lambda st: cabi.call("gg_conv2d_dgrad_actgrad", ap, bp, op_, yp, mcode, malpha, *geo, wp, wn, st))
             return
+        if node.id in self.bn_stats:                      # + the statistics of the batch norm that follows (_plan_bn_stats)
+            self._emit_bnstats_launch(node, ap, bp, bias, op_, act, alpha, wp, wn)
+            return
         name = "gg_conv2d_fwd" if mode == "fwd" else "gg_conv2d_dgrad"
         self.steps.append(lambda st: cabi.call(name, ap, bp, bias, op_, *geo, act, alpha, wp, wn, st))
+
+    def _emit_bnstats_launch(self, node, ap, bp, bias, op_, act, alpha, wp, wn):
+        info = self.bn_stats[node.id]
+        info["buf"] = self.rt.empty((info["tiles"], 2, info["C"]))
+        sp, mode, geo = info["buf"].data_ptr(), info["mode"], info["geo"]
+        self.steps.append(lambda st: cabi.call("gg_conv2d_bnstats", mode, ap, bp, bias, op_, sp, *geo, act, alpha, wp, wn, st))
 
     def _emit_bn(self, node):
         torch = _torch()
@@ -1196,6 +1255,13 @@ class Plan(object):
         self.extra[(node.id, 1)], self.extra[(node.id, 2)] = mean, rstd
         act, alpha, eps = cabi.ACT[node.attrs["act"]], node.attrs["alpha"], node.attrs["eps"]
         world = ggdist.world_size()
+        if node.id in self.bn_from_stats:
+            # the producing conv / dense launch left per-m-tile sums: fold + normalise + activation in one element-wise pass
+            info = self.bn_stats[self.bn_from_stats[node.id]]
+            xp, pp, gp, bp, yp, mp, rp = (t.data_ptr() for t in (x, info["buf"], gamma, beta, y, mean, rstd))
+            S = info["tiles"]
+            self.steps.append(lambda st: cabi.call("gg_bn_apply", xp, pp, S, float(R), gp, bp, eps, yp, mp, rp, R, Cc, act, alpha, st))
+            return
         if self._bn_fused(R, Cc, world):
             # statistics + normalise + activation in ONE launch (no cross-rank exchange needed)
             xp, gp, bp, yp, mp, rp = (t.data_ptr() for t in (x, gamma, beta, y, mean, rstd))

@@ -104,6 +104,17 @@ size_t gg_conv2d_wgrad_workspace(int B, int H, int W, int Ci, int Co, int k, int
 int gg_conv2d_dgrad_actgrad(const float* dy, const float* w, float* dx, const float* y_fwd, int act, float alpha,
                             int B, int H, int W, int Ci, int Co, int k, int stride, int pad_t, int pad_l, int Ho, int Wo,
                             void* workspace, size_t workspace_bytes, void* stream);
+/* Convolution (mode 0, a = x) / transposed convolution (mode 1, a = dy; gg_conv2d_dgrad's argument meaning) that ALSO writes the
+ * batch-norm statistics of its output: stats[t][0][c] = sum, stats[t][1][c] = sum of squares of out[., c] over the output rows of
+ * m-tile t, t < gg_conv2d_stats_tiles(...), c < (mode 0 ? Co : Ci).  `Batchnorm` always follows a Conv2D / Deconv2D / Linear
+ * (tflib/ops/batchnorm.py:29-30 applied to the output of conv2d.py:106-120, e.g. gmgan_inference_cifar10.py:173-180): the moments
+ * pass over the activation disappears — gg_bn_apply(x, stats, S = tiles, count = rows, ...) folds the partial rows and
+ * normalises.  A Linear layer is the 1x1 geometry (B = rows, H = W = Ho = Wo = k = stride = 1).  Tensor-core path only:
+ * gg_conv2d_stats_tiles returns 0 when the shape does not run there, and gg_conv2d_bnstats then fails with GG_ERR_UNSUPPORTED. */
+int gg_conv2d_stats_tiles(int mode, int B, int H, int W, int Ci, int Co, int k, int stride, int pad_t, int pad_l, int Ho, int Wo);
+int gg_conv2d_bnstats(int mode, const float* a, const float* w, const float* bias, float* out, float* stats,
+                      int B, int H, int W, int Ci, int Co, int k, int stride, int pad_t, int pad_l, int Ho, int Wo,
+                      int act, float alpha, void* workspace, size_t workspace_bytes, void* stream);
 /* 1 when mode (0 fwd, 1 dgrad, 2 wgrad) of this geometry runs on the tcgen05 kernels under the current backend setting */
 int gg_conv2d_tc_supported(int mode, int B, int H, int W, int Ci, int Co, int k, int stride, int Ho, int Wo);
 /* workspace bytes for mode 0 fwd / 1 dgrad / 2 wgrad.  The workspace holds split-K partial tiles and, in its first

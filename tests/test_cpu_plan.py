@@ -125,16 +125,34 @@ def test_sibling_batching_halves_discriminator_launches_and_concat_is_zero_copy(
                 assert plan.buf[node.id].data_ptr() == src.data_ptr() + 4 * node.attrs["start"] * inner
 
 
-def test_launch_list_uses_single_launch_batchnorm_and_fused_epilogues(cpu_device):
+def test_launch_list_uses_single_launch_batchnorm_and_fused_epilogues(cpu_device, monkeypatch):
     record = cpu_device
     gplan, _ = _plans(_gmgan())
     del record[:]
     for f in gplan.steps:
         f(0)
     names = [n for n, _ in record]
-    assert "gg_bn_fwd_fused" in names and "gg_bn_bwd_fused" in names and "gg_bn_stats" not in names
+    # every batch norm of the step sits behind a tensor-core conv / deconv / dense launch: that launch's epilogue takes the
+    # statistics (gg_conv2d_bnstats) and the batch norm is one element-wise pass (gg_bn_apply) — no moments pass at all
+    assert names.count("gg_conv2d_bnstats") == 5 and names.count("gg_bn_apply") == 5 and "gg_bn_fwd_fused" not in names
+    assert "gg_bn_bwd_fused" in names and "gg_bn_stats" not in names
     assert names.count("gg_adam_multi") == 1 and names.count("gg_rng_tick") == 1
-    assert len(names) < 170, "G-step launch list grew to %d C-ABI calls" % len(names)
+    assert len(names) < 115, "G-step launch list grew to %d C-ABI calls" % len(names)
+    for n, a in record:
+        if n == "gg_conv2d_bnstats":
+            assert a[5] is not None and a[5] != 0, "statistics buffer missing"
+    # without the epilogue statistics: the one-launch cluster batch norm
+    monkeypatch.setenv("GG_BN_CONV_STATS", "0")
+    gplan0, _ = _plans(_gmgan())
+    del record[:]
+    for f in gplan0.steps:
+        f(0)
+    names0 = [n for n, _ in record]
+    assert names0.count("gg_bn_fwd_fused") == 5 and "gg_conv2d_bnstats" not in names0 and "gg_bn_apply" not in names0
+    monkeypatch.delenv("GG_BN_CONV_STATS")
+    del record[:]
+    for f in gplan.steps:
+        f(0)
     # LeakyReLU / ReLU / tanh never appear as their own launches: they ride conv / dense / BN epilogues
     from gg import cabi
     act_codes = {cabi.UNARY[k] for k in ("relu", "leaky", "tanh", "sigmoid")}

@@ -209,7 +209,7 @@ def _builders():
     }
 
 
-def _train(family, fuse, iters=3):
+def _train(family, fuse, iters=3, bn_stats=False):
     import tensorflow as tf
     import tflib as lib
     from gg.executor import RT
@@ -217,6 +217,7 @@ def _train(family, fuse, iters=3):
     knobs = ("GG_FUSE_EW", "GG_FUSE_TRANSPOSE", "GG_FUSE_ACTGRAD_DENSE", "GG_RANK1_MUL", "GG_GATHER")
     for k in knobs:                                  # every launch-list fusion of round 2 on, or the one-launch-per-node plan
         os.environ[k] = "1" if fuse else "0"
+    os.environ["GG_BN_CONV_STATS"] = "1" if bn_stats else "0"    # (changes the summation order of the moments: not bit-identical)
     try:
         tf.reset_default_graph()
         lib.delete_all_params()
@@ -245,10 +246,12 @@ def _train(family, fuse, iters=3):
                 costs.append(np.asarray(c, dtype=np.float32).copy())
         for plan in RT.plans.values():
             n_fused += len(plan.ew_clusters) + len(plan.tr_fuse) + len(plan.gather_add)
+            if bn_stats:
+                n_fused += 1000 * len(plan.bn_stats)
         params = {n: RT.get_param(p).copy() for n, p in sorted(lib._params.items())}
         return costs, params, n_fused
     finally:
-        for k in knobs:
+        for k in knobs + ("GG_BN_CONV_STATS",):
             os.environ.pop(k, None)
 
 
@@ -264,3 +267,87 @@ def test_fused_plans_are_bit_identical(family):
     assert set(p0) == set(p1)
     for n in p0:
         assert np.array_equal(p0[n], p1[n]), "%s: parameter %s differs between the fused and the unfused plan" % (family, n)
+
+
+# ---- batch-norm statistics in the epilogue of the producing conv / deconv / dense launch ----------------------------------
+BNSTAT_CASES = [
+    # mode, B, H, W, Ci, Co, k, stride      (mode 1: the Deconv2D forward = gg_conv2d_dgrad geometry)
+    (0, 64, 16, 16, 64, 128, 5, 2),      # Extractor.2 (gmgan_inference_cifar10.py:173-176), split-K cluster
+    (0, 64, 8, 8, 128, 256, 5, 2),       # Extractor.3
+    (1, 64, 8, 8, 128, 256, 5, 2),       # Generator.2 deconv 256 -> 128
+    (1, 64, 16, 16, 64, 128, 5, 2),      # Generator.3 deconv 128 -> 64
+    (0, 64, 1, 1, 128, 4096, 1, 1),      # Generator.1 Linear (rows 64 of a 128-row tile)
+    (0, 128, 32, 32, 32, 64, 5, 2),      # face Discriminator-sized, un-split multi-wave launch (two CTAs per SM)
+    (1, 128, 16, 16, 64, 128, 5, 2),     # face Generator deconv
+    (0, 6, 8, 8, 32, 96, 3, 1),          # ragged batch box, n_tile 32
+]
+
+
+@pytest.mark.parametrize("case", BNSTAT_CASES)
+def test_conv_epilogue_batchnorm_statistics(case):
+    from gg import cabi
+    from gpu_util import ws, geom
+    mode, B, H, W, Ci, Co, k, stride = case
+    Ho, Wo, pt, pl = geom(H, W, k, stride, "SAME")
+    geo = (B, H, W, Ci, Co, k, stride, pt, pl, Ho, Wo)
+    T = cabi.lib.gg_conv2d_stats_tiles(mode, *geo)
+    assert T > 0, "shape should run on the tensor-core path"
+    g = torch.Generator(device="cuda").manual_seed(3)
+    w = torch.randn(k, k, Ci, Co, device="cuda", generator=g) * 0.05
+    if mode == 0:
+        a = torch.randn(B, H, W, Ci, device="cuda", generator=g)
+        C, out_shape = Co, (B, Ho, Wo, Co)
+    else:
+        a = torch.randn(B, Ho, Wo, Co, device="cuda", generator=g)
+        C, out_shape = Ci, (B, H, W, Ci)
+    bias = torch.randn(C, device="cuda", generator=g)
+    gamma, beta = torch.rand(C, device="cuda", generator=g) + 0.5, torch.randn(C, device="cuda", generator=g)
+    ref, out = torch.empty(out_shape, device="cuda"), torch.empty(out_shape, device="cuda")
+    wsp = ws(cabi.lib.gg_conv2d_workspace(mode, B, H, W, Ci, Co, k, stride, Ho, Wo))
+    name = "gg_conv2d_fwd" if mode == 0 else "gg_conv2d_dgrad"
+    cabi.call(name, a.data_ptr(), w.data_ptr(), bias.data_ptr(), ref.data_ptr(), *geo, cabi.ACT[None], 0.0, wsp.data_ptr(), wsp.numel(),
+              cabi.stream_ptr())
+    assert cabi.lib.gg_last_backend() == 1
+    stats = torch.full((T, 2, C), float("nan"), device="cuda")
+    cabi.call("gg_conv2d_bnstats", mode, a.data_ptr(), w.data_ptr(), bias.data_ptr(), out.data_ptr(), stats.data_ptr(), *geo,
+              cabi.ACT[None], 0.0, wsp.data_ptr(), wsp.numel(), cabi.stream_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref), "the statistics epilogue changed the convolution's output"
+    assert bool(torch.isfinite(stats).all()), "an (m-tile, channel) slot of the statistics was never written"
+    R = out.numel() // C
+    x2 = ref.reshape(R, C).double()
+    tot = stats.double().sum(0)
+    assert (tot[0] - x2.sum(0)).abs().max() <= 1e-5 * x2.abs().sum(0).max()
+    assert (tot[1] - (x2 * x2).sum(0)).abs().max() <= 1e-5 * (x2 * x2).sum(0).max()
+    # through gg_bn_apply == the one-launch batch norm (and the fp64 formula)
+    y1, y2 = torch.empty(R, C, device="cuda"), torch.empty(R, C, device="cuda")
+    m1, r1, m2, r2 = (torch.empty(C, device="cuda") for _ in range(4))
+    cabi.call("gg_bn_apply", ref.data_ptr(), stats.data_ptr(), T, float(R), gamma.data_ptr(), beta.data_ptr(), 1e-5, y1.data_ptr(),
+              m1.data_ptr(), r1.data_ptr(), R, C, cabi.ACT["relu"], 0.0, cabi.stream_ptr())
+    mean = x2.mean(0)
+    var = x2.var(0, unbiased=False)
+    want = torch.clamp((x2 - mean) * torch.rsqrt(var + 1e-5) * gamma.double() + beta.double(), min=0)
+    torch.cuda.synchronize()
+    assert (y1.double() - want).abs().max() <= 2e-5 * max(1.0, float(want.abs().max()))
+    assert (m1.double() - mean).abs().max() <= 1e-5 * max(1.0, float(mean.abs().max()))
+    if cabi.lib.gg_bn_fused_supported(R, C) == 1:
+        cabi.call("gg_bn_fwd_fused", ref.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1e-5, y2.data_ptr(), m2.data_ptr(), r2.data_ptr(),
+                  R, C, cabi.ACT["relu"], 0.0, cabi.stream_ptr())
+        torch.cuda.synchronize()
+        assert (y1 - y2).abs().max() <= 2e-5 * max(1.0, float(y2.abs().max()))
+        assert (r1 - r2).abs().max() <= 1e-5 * float(r2.abs().max())
+
+
+@pytest.mark.parametrize("family", ["gmgan_cifar10", "gan_face_ali", "gan_mnist_ali"])
+def test_plans_with_epilogue_statistics_track_the_one_launch_batchnorm(family):
+    c0, p0, f0 = _train(family, True, iters=2, bn_stats=False)
+    c1, p1, f1 = _train(family, True, iters=2, bn_stats=True)
+    assert f1 >= 1000, "no batch norm took its statistics from the producing launch"
+    for a, b in zip(c0, c1):
+        assert np.allclose(a, b, rtol=2e-3, atol=2e-4), (family, a, b)
+    # parameters after two Adam steps: an update is lr * m / (sqrt(v) + eps), i.e. it has the size of lr whatever the size of
+    # the gradient, so the rounding-level change of the moments shows up relative to lr (2e-4), not to the parameter
+    for n in p0:
+        d = np.abs(p0[n] - p1[n])
+        assert d.max() <= 0.25 * 2e-4, (n, float(d.max()))
+        assert np.sqrt((d * d).mean()) <= 0.05 * 2e-4, (n, float(np.sqrt((d * d).mean())))
