@@ -667,22 +667,11 @@ extern "C" int gg_add_n(const float* const* ptrs, int count, float* out, long lo
 // one-op kernels run — so a fused group is bit-identical to the launches it replaces (tests/test_gpu_fusion.py).
 #define GG_EW_THREADS 256
 
-__device__ __forceinline__ void ew_eval(const gg_ew_program& p, float (*regs)[GG_EW_THREADS], int t, long long idx) {
-  if (p.flat) {
-    for (int k = 0; k < p.n_in; ++k)
-      regs[k][t] = p.in_is_int[k] ? (float)reinterpret_cast<const int32_t*>(p.in[k])[idx] : reinterpret_cast<const float*>(p.in[k])[idx];
-  } else {
-    long long r = idx;
-    int i3 = (int)(r % p.dims[3]); r /= p.dims[3];
-    int i2 = (int)(r % p.dims[2]); r /= p.dims[2];
-    int i1 = (int)(r % p.dims[1]); r /= p.dims[1];
-    int i0 = (int)r;
-    for (int k = 0; k < p.n_in; ++k) {
-      long long o = (long long)i0 * p.in_stride[k][0] + (long long)i1 * p.in_stride[k][1] + (long long)i2 * p.in_stride[k][2] +
-                    (long long)i3 * p.in_stride[k][3];
-      regs[k][t] = p.in_is_int[k] ? (float)reinterpret_cast<const int32_t*>(p.in[k])[o] : reinterpret_cast<const float*>(p.in[k])[o];
-    }
-  }
+__device__ __forceinline__ float ew_load(const gg_ew_program& p, int k, long long off) {
+  return p.in_is_int[k] ? (float)reinterpret_cast<const int32_t*>(p.in[k])[off] : reinterpret_cast<const float*>(p.in[k])[off];
+}
+
+__device__ __forceinline__ void ew_run_instrs(const gg_ew_program& p, float (*regs)[GG_EW_THREADS], int t) {
   for (int j = 0; j < p.n_instr; ++j) {
     const gg_ew_instr& q = p.instr[j];
     float v;
@@ -699,25 +688,48 @@ __global__ void __launch_bounds__(GG_EW_THREADS) ew_program_kernel(const __grid_
   long long i = (long long)blockIdx.x * blockDim.x + t;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
-    ew_eval(p, regs, t, i);
+    if (p.flat) {
+      for (int k = 0; k < p.n_in; ++k) regs[k][t] = ew_load(p, k, i);
+    } else {
+      // the iteration space has < 2^31 elements (checked by the host): 32-bit divisions
+      uint32_t r = (uint32_t)i;
+      const uint32_t i3 = r % (uint32_t)p.dims[3]; r /= (uint32_t)p.dims[3];
+      const uint32_t i2 = r % (uint32_t)p.dims[2]; r /= (uint32_t)p.dims[2];
+      const uint32_t i1 = r % (uint32_t)p.dims[1]; r /= (uint32_t)p.dims[1];
+      const uint32_t i0 = r;
+      for (int k = 0; k < p.n_in; ++k)
+        regs[k][t] = ew_load(p, k, (long long)i0 * p.in_stride[k][0] + (long long)i1 * p.in_stride[k][1] +
+                                       (long long)i2 * p.in_stride[k][2] + (long long)i3 * p.in_stride[k][3]);
+    }
+    ew_run_instrs(p, regs, t);
     for (int k = 0; k < p.n_out; ++k) p.out[k][i] = regs[p.out_reg[k]][t];
   }
 }
 
 // output 0 reduced along the last dimension, one CTA per row, with reduce_rows_kernel's summation order (thread-strided partial
-// sums, warp butterfly, per-warp partials in shared memory, one more butterfly); outputs 1.. are stored per element
+// sums, warp butterfly, per-warp partials in shared memory, one more butterfly); outputs 1.. are stored per element.  The row's
+// coordinates are decomposed ONCE per CTA (thread k computes the row base offset of input k): no division in the element loop
 __global__ void __launch_bounds__(GG_EW_THREADS) ew_program_reduce_kernel(const __grid_constant__ gg_ew_program p, int rows, int red) {
   GG_PDL_ENTRY();
   __shared__ float regs[GG_EW_REGS][GG_EW_THREADS];
   __shared__ float sh[32];
+  __shared__ long long s_base[GG_EW_MAX_IN];
   const int t = threadIdx.x;
   const int o = blockIdx.x;
   if (o >= rows) return;
+  if (t < p.n_in) {
+    uint32_t r = (uint32_t)o;
+    const uint32_t i2 = r % (uint32_t)p.dims[2]; r /= (uint32_t)p.dims[2];
+    const uint32_t i1 = r % (uint32_t)p.dims[1]; r /= (uint32_t)p.dims[1];
+    s_base[t] = (long long)r * p.in_stride[t][0] + (long long)i1 * p.in_stride[t][1] + (long long)i2 * p.in_stride[t][2];
+  }
+  __syncthreads();
   const bool is_max = p.reduce_op == 3;
   float acc = is_max ? -INFINITY : 0.f;
   for (int r = t; r < red; r += blockDim.x) {
+    for (int k = 0; k < p.n_in; ++k) regs[k][t] = ew_load(p, k, s_base[k] + (long long)r * p.in_stride[k][3]);
+    ew_run_instrs(p, regs, t);
     const long long idx = (long long)o * red + r;
-    ew_eval(p, regs, t, idx);
     const float v = regs[p.out_reg[0]][t];
     acc = is_max ? fmaxf(acc, v) : acc + v;
     for (int k = 1; k < p.n_out; ++k) p.out[k][idx] = regs[p.out_reg[k]][t];
@@ -746,6 +758,7 @@ extern "C" int gg_ew_run(const gg_ew_program* prog, void* stream) {
     if (p.dims[i] <= 0) return GG_OK;
     n *= p.dims[i];
   }
+  GG_REQUIRE(n <= 0x7fffffffLL, "gg_ew_run");
   for (int k = 0; k < p.n_in; ++k) GG_REQUIRE(p.in[k] != nullptr, "gg_ew_run");
   for (int k = 0; k < p.n_out; ++k) GG_REQUIRE(p.out[k] != nullptr && p.out_reg[k] >= 0 && p.out_reg[k] < GG_EW_REGS, "gg_ew_run");
   for (int j = 0; j < p.n_instr; ++j) {
