@@ -186,3 +186,135 @@ def test_fusion_cuts_the_launch_list_and_can_be_switched_off(cpu_device, monkeyp
     assert chain and len(chain[0].desc["instrs"]) >= 8
     # the four sigmoid-cross-entropy means of LOCAL_EP each run as program + row reduction
     assert sum(1 for cl in gp.ew_clusters if cl.reduce is not None and cl.desc["reduce"]["op"] == 2) >= 4
+
+
+# ---- launch-list peepholes (gg/executor.py): structure of the compiled gmgan-CIFAR step ------------------------------------
+def _cifar_plans(batch=64):
+    import tensorflow as tf
+    import tflib as lib
+    import gmgan_inference_cifar10 as S
+    from gg.executor import RT, Plan
+    tf.reset_default_graph()
+    lib.delete_all_params()
+    np.random.seed(1234)
+    g = S.build_graph(BATCH_SIZE=batch)
+    return g, Plan(RT, [g.gen_cost, g.gen_train_op], [g.real_x_int]), Plan(RT, [g.disc_cost, g.disc_train_op], [g.real_x_int])
+
+
+def _calls(plan, record):
+    del record[:]
+    for f in plan.steps:
+        f(0)
+    return list(record)
+
+
+def test_strided_transposes_replace_slice_copy_and_activation_gradient(cpu_device):
+    """`tf.reshape(output, [-1, 4*4*4*DIM])` -> `tf.concat([output, z_output], 1)` (gmgan_inference_cifar10.py:292-294): the forward
+    transpose writes into the concat's columns, the backward one reads the dense gradient's columns and applies LeakyReLU'"""
+    from gg import cabi
+    g, gplan, dplan = _cifar_plans()
+    for plan in (gplan, dplan):
+        calls = _calls(plan, cpu_device)
+        ex = [a for n, a in calls if n == "gg_transpose_b2d_ex"]
+        assert len(ex) == 2
+        fwd = [a for a in ex if a[7] is None]
+        bwd = [a for a in ex if a[7] is not None]
+        assert len(fwd) == 1 and len(bwd) == 1
+        # forward: [128, 4*4, 256] -> [128, 256, 4*4], contiguous in, rows of the [128, 4096 + 512] concat out
+        assert fwd[0][2:7] == (128, 16, 256, 4096, 4608)
+        # backward: columns 0..4095 of the [128, 4608] gradient in, contiguous out, mask = the conv output (leaky 0.2)
+        assert bwd[0][2:7] == (128, 256, 16, 4608, 4096) and bwd[0][8] == cabi.ACT["leaky"] and abs(bwd[0][9] - 0.2) < 1e-7
+        info = [i for i in plan.tr_fuse.values() if i["y_concat"] is not None][0]
+        store = plan._concat_storage(info["y_concat"].id)
+        assert fwd[0][1] == store.data_ptr() + 4 * info["y_off"] and plan.buf[info["y_concat"].id].data_ptr() == store.data_ptr()
+        binfo = [i for i in plan.tr_fuse.values() if i["x_node"] is not None][0]
+        assert bwd[0][0] == plan.buf[binfo["x_node"].id].data_ptr() + 4 * binfo["x_off"]
+        assert bwd[0][7] == plan.buf[binfo["mask"][0].id].data_ptr()
+        # the slice in front of the backward transpose owns no launch and no buffer; the concat copies only its other piece
+        assert plan.buf[binfo["slice"].id] is None
+        cat = info["y_concat"]
+        copies = [a for n, a in calls if n == "gg_copy2d" and store.data_ptr() <= a[2] < store.data_ptr() + 4 * cat.size]
+        assert len(copies) == len(cat.inputs) - 1
+
+
+def test_prior_sample_is_a_gather_with_the_noise_added_and_the_tick_comes_last(cpu_device):
+    g, gplan, dplan = _cifar_plans()
+    for plan in (gplan, dplan):
+        calls = _calls(plan, cpu_device)
+        names = [n for n, _ in calls]
+        assert names.count("gg_gather_rows") == 1
+        ga = [a for n, a in calls if n == "gg_gather_rows"][0]
+        (mid, (add_node, noise)), = plan.gather_add.items()
+        m = [n for n in plan.order if n.id == mid][0]
+        idx = m.inputs[0].inputs[0]
+        assert ga[0] == plan.buf[idx.id].data_ptr() and ga[1] == plan.buf[m.inputs[1].id].data_ptr()
+        assert ga[2] == plan.buf[noise.id].data_ptr() and ga[3] == plan.buf[add_node.id].data_ptr()
+        assert ga[4:7] == (64, 128, 30)
+        # the launch waits for the index and the noise, not for the one-hot matrix
+        pos = {n: i for i, (n, _) in enumerate(calls)}
+        assert pos["gg_rng_categorical"] < pos["gg_gather_rows"] and pos["gg_rng_normal"] < pos["gg_gather_rows"]
+        grp = [q for q in plan.groups if q.get("node") is m][0]
+        assert m.inputs[0].id not in grp["reads"] and idx.id in grp["reads"]
+        # every random draw of the step happens before the counter is advanced
+        last_rng = max(i for i, n in enumerate(names) if n.startswith("gg_rng_") and n != "gg_rng_tick")
+        assert names.count("gg_rng_tick") == 1 and names.index("gg_rng_tick") > last_rng
+
+
+def test_dense_activation_gradients_and_rank1_products_leave_the_launch_list(cpu_device, monkeypatch):
+    g, gplan, dplan = _cifar_plans()
+    for plan in (gplan, dplan):
+        calls = _calls(plan, cpu_device)
+        dense = [a for n, a in calls if n == "gg_conv2d_dgrad_actgrad" and a[7:9] == (1, 1)]
+        assert len(dense) >= 2 and all(a[4] != 0 for a in dense)
+        # no K = 1 GEMM is left: dy [128,1] x W^T [1,512] is an element-wise multiply inside a cluster
+        assert not [a for n, a in calls if n == "gg_gemm" and a[6] == 1]
+
+
+def test_batchnorm_statistics_buffer_is_shared_between_producer_and_apply(cpu_device):
+    g, gplan, dplan = _cifar_plans()
+    for plan in (gplan, dplan):
+        calls = _calls(plan, cpu_device)
+        prod = {a[5]: a for n, a in calls if n == "gg_conv2d_bnstats"}
+        app = [a for n, a in calls if n == "gg_bn_apply"]
+        assert len(prod) == 5 and len(app) == 5
+        from gg import cabi
+        for a in app:
+            assert a[1] in prod, "gg_bn_apply reads a statistics buffer no launch wrote"
+            p = prod[a[1]]
+            assert a[2] == cabi.lib.gg_conv2d_stats_tiles(p[0], *p[6:17])            # S = m-tiles of the producer
+            assert a[0] == p[4], "the batch norm does not read the producer's output"
+            R, C = a[10], a[11]
+            assert abs(a[3] - float(R)) < 0.5 and C == (p[10] if p[0] == 0 else p[9])  # channels = Co (fwd) / Ci (dgrad)
+        order = [n for n, _ in calls]
+        for ptr, p in prod.items():
+            i_prod = [i for i, (n, a) in enumerate(calls) if n == "gg_conv2d_bnstats" and a[5] == ptr][0]
+            i_app = [i for i, (n, a) in enumerate(calls) if n == "gg_bn_apply" and a[1] == ptr][0]
+            assert i_prod < i_app
+
+
+def test_no_high_priority_group_waits_for_a_low_priority_one(cpu_device, monkeypatch):
+    """GG_PRIO_TAIL: on (auto) for the multi-wave face plans, off for the latency-bound batch-64 cifar plans"""
+    import tensorflow as tf
+    import tflib as lib
+    import gan_inference_face as F
+    from gg.executor import RT, Plan
+    g, gplan, dplan = _cifar_plans()
+    for plan in (gplan, dplan):
+        plan._schedule_range(range(len(plan.groups)), 8)
+        assert plan.prio_tail_mode == "0"
+    tf.reset_default_graph()
+    lib.delete_all_params()
+    np.random.seed(2)
+    gf = F.build_graph(BATCH_SIZE=128)
+    for fetch in ([gf.gen_cost, gf.gen_train_op], [gf.disc_cost, gf.disc_train_op]):
+        plan = Plan(RT, fetch, [gf.real_x_int])
+        plan._schedule_range(range(len(plan.groups)), 8)
+        assert plan.prio_tail_mode == "1"
+        producer = {}
+        for gi, grp in enumerate(plan.groups):
+            for o in grp["reads"]:
+                d = producer.get(o)
+                if d is not None and not grp["barrier"] and not plan.low_class[gi]:
+                    assert not plan.low_class[d], "high-priority group %d waits for low-priority group %d" % (gi, d)
+            producer[grp["writes"]] = gi
+        assert any(plan.low_class.values()), "nothing is left in the low class"
