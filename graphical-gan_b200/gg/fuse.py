@@ -13,8 +13,6 @@ Vocabulary: a cluster iterates over D = the non-1 extents of its largest member 
 external input spans a subset of those extents (its `mask`) and is broadcast along the others, which is how
 `tf.expand_dims` / implicit broadcasting inside a chain is evaluated without materialising the broadcast.
 """
-import ctypes as C
-
 from . import cabi
 from .graph import float32, int32, prod
 

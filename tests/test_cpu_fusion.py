@@ -3,7 +3,6 @@ with NumPy (float64) on the values the graph interpreter computes for the cluste
 interpreter's values of the nodes it replaces; the re-sorted plan must still be a topological order; the ctypes struct handed to
 gg_ew_run must say what the description says.  (The kernel itself is checked on the GPU: tests/test_gpu_fusion.py.)"""
 import os
-import sys
 
 import numpy as np
 import pytest
